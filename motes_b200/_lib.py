@@ -1,0 +1,134 @@
+"""ctypes binding of libmotes_b200.so (the C ABI in include/motes_b200.h).
+
+There is no CPU implementation behind this module: if the shared library has not
+been built (``python -c 'import __graft_entry__ as g; g.build()'`` or
+``make -C motes_b200/csrc``) importing it raises, and if no CUDA device is usable
+every compute call raises ``MotesCudaError``.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmotes_b200.so")
+
+MOTES_OK, E_CUDA, E_ARG, E_NOMEM, E_NOSKY, E_FIT = 0, -1, -2, -3, -4, -5
+
+
+class MotesCudaError(RuntimeError):
+    """CUDA runtime failure inside libmotes_b200 (includes 'no device')."""
+
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} is missing: build the CUDA extension first (make -C motes_b200/csrc). "
+        "motes_b200 has no CPU fallback.")
+
+lib = ctypes.CDLL(LIB_PATH)
+
+c_dp = ctypes.POINTER(ctypes.c_double)
+c_ip = ctypes.POINTER(ctypes.c_int32)
+c_u8p = ctypes.POINTER(ctypes.c_uint8)
+c_u32p = ctypes.POINTER(ctypes.c_uint32)
+c_handle = ctypes.c_void_p
+
+# name -> (restype, argtypes); one entry per declaration in include/motes_b200.h
+SIGNATURES = {
+    "motes_create": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(c_handle)]),
+    "motes_destroy": (ctypes.c_int, [c_handle]),
+    "motes_last_error": (ctypes.c_char_p, []),
+    "motes_version": (ctypes.c_char_p, []),
+    "motes_stream": (ctypes.c_void_p, [c_handle]),
+    "motes_set_stream": (ctypes.c_int, [c_handle, ctypes.c_void_p]),
+    "motes_synchronize": (ctypes.c_int, [c_handle]),
+    "motes_launch_count": (ctypes.c_longlong, [c_handle]),
+    "motes_moffat_fit_batch_host": (ctypes.c_int, [c_handle, c_dp, ctypes.c_int, ctypes.c_int, c_dp, c_dp,
+                                                   c_dp, c_ip, c_ip, c_ip]),
+    "motes_moffat_fit_batch_dev": (ctypes.c_int, [c_handle, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+                                                  ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                                  ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "motes_optimal_extract_host": (ctypes.c_int, [c_handle, c_dp, c_dp, ctypes.c_int, ctypes.c_int, c_dp, c_dp,
+                                                  c_dp, ctypes.c_int, ctypes.c_int, c_dp, c_ip, c_ip, c_u8p]),
+}
+for _name, (_res, _args) in SIGNATURES.items():
+    _fn = getattr(lib, _name)
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+
+def last_error() -> str:
+    return (lib.motes_last_error() or b"").decode()
+
+
+def check(rc: int) -> None:
+    """Map a C status to the exception the reference would raise at that point."""
+    if rc == MOTES_OK:
+        return
+    msg = last_error()
+    if rc == E_CUDA:
+        raise MotesCudaError(msg or "CUDA error")
+    if rc == E_NOMEM:
+        raise MemoryError(msg or "device allocation failed")
+    if rc == E_NOSKY:
+        raise RuntimeError(msg or "No pixels contained inside sky region.")
+    if rc == E_FIT:
+        raise ValueError(msg or "Moffat fit could not start")
+    raise ValueError(msg or f"motes_b200 error {rc}")
+
+
+def f64(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype="<f8")
+
+
+def ptr(a: np.ndarray, ctype=c_dp):
+    return a.ctypes.data_as(ctype) if a is not None else None
+
+
+class Handle:
+    """One library handle (device + stream + scratch).  Calls on a handle are serialised."""
+
+    def __init__(self, device: int = 0):
+        self._h = c_handle()
+        check(lib.motes_create(int(device), ctypes.byref(self._h)))
+        self.device = int(device)
+        self.lock = threading.Lock()
+
+    @property
+    def raw(self):
+        return self._h
+
+    def synchronize(self):
+        check(lib.motes_synchronize(self._h))
+
+    def launch_count(self) -> int:
+        return int(lib.motes_launch_count(self._h))
+
+    def close(self):
+        if self._h:
+            lib.motes_destroy(self._h)
+            self._h = c_handle()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_default = {}
+_default_lock = threading.Lock()
+
+
+def default_handle(device: int | None = None) -> Handle:
+    """Process-wide handle per device (MOTES_B200_DEVICE or LOCAL_RANK picks the default device)."""
+    if device is None:
+        device = int(os.environ.get("MOTES_B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+    with _default_lock:
+        if device not in _default:
+            _default[device] = Handle(device)
+        return _default[device]

@@ -1,0 +1,57 @@
+"""GPU parity: batched TRF Moffat fit (C ABI motes_moffat_fit_batch_host) vs reference-generated golden fits."""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from parity import param_errors, summarize
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", ["t1_sky0", "t2_cr_sky0", "t1_faint", "t2_unbinned", "c1_sky0"])
+def test_fit_batch_matches_reference(name):
+    from motes_b200 import tracing
+    meta, g = load_golden(name)
+    scale = g["scale"]
+    profiles = g["ext_profiles"] * scale
+    alpha0 = g["seeing_px"] / meta["spec"]["pixel_resolution"]
+    params, info = tracing.moffat_fit_batch(profiles, alpha0, full_output=True)
+    ref = g["ext_params"][:, :6].copy()
+    ref[:, [0, 4, 5]] *= scale
+    err = param_errors(params, ref, profiles.shape[1])
+    s = summarize(err)
+    print(name, "median", s["median"], "p99", s["p99"], "max", s["max"])
+    # the reference's own jitter under a 1-ulp input perturbation, same metric
+    ctl = g["ctl_ext_params"][:, :6].copy()
+    if ctl.shape == ref.shape:
+        ctl[:, [0, 4, 5]] *= scale
+        print(name, "self-noise control max", param_errors(ctl, ref, profiles.shape[1]).max(axis=0))
+    assert np.all((info["status"] >= 1) & (info["status"] <= 4))
+    assert np.all(s["median"] < 1e-7)
+    assert np.all(np.percentile(err, 90, axis=0) < 1e-6)       # north_star tolerance for the bulk
+    assert err.max() < 1e-5                                       # stopping-point jitter tail
+    assert np.allclose(info["cost"], g["ext_fitinfo"][:, 3], rtol=1e-9)
+
+
+def test_single_profile_api_and_errors():
+    from motes_b200 import tracing
+    meta, g = load_golden("t1_nosky")
+    prof = g["median_profile"] * g["scale"]
+    axis = np.arange(prof.size, dtype=np.float64)
+    p = tracing.moffat_least_squares(axis, prof, meta["spec"]["seeing"], meta["spec"]["pixel_resolution"])
+    ref = g["median_params"].copy()
+    ref[[0, 4, 5]] *= g["scale"]
+    assert np.allclose(p, ref, rtol=1e-6, atol=1e-6 * abs(ref[0]))
+    with pytest.raises(ValueError):
+        tracing.moffat_least_squares(axis, np.linspace(-5.0, -1.0, prof.size), 0.8, 0.16)
+
+
+def test_median_moffat_fitting_mutates_header():
+    from motes_b200 import tracing
+    meta, g = load_golden("t1_nosky")
+    header = {"seeing": meta["spec"]["seeing"], "pixel_resolution": meta["spec"]["pixel_resolution"]}
+    axis = np.arange(g["median_profile"].size, dtype=np.float64)
+    params, scale = tracing.median_moffat_fitting(g["median_profile"], header, axis)
+    assert scale == g["scale"]
+    assert np.allclose(params, g["median_params"], rtol=1e-6, atol=1e-9)
+    assert header["seeing"] == pytest.approx(float(g["seeing_px"]), rel=1e-6)
