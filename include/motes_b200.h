@@ -52,6 +52,70 @@ int motes_synchronize(motes_handle* h);
 /* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */
 long long motes_launch_count(motes_handle* h);
 
+/* ---------------------------------------------------------------------------------------
+ * Whole path for a batch of frames (core.motes stage order, core.py:80-275).
+ * ------------------------------------------------------------------------------------- */
+typedef struct motes_params {
+    double minimum_column_limit;   /* -m   (xmotes.py), tracing.py:165 */
+    double extraction_snr_limit;   /* -xs  tracing.py:162 */
+    double sky_snr_limit;          /* -ks  tracing.py:160 */
+    double sky_fwhm_multiplier;    /* -kf  used for BOTH the sky and the extraction limits (core.py:208) */
+    int32_t subtract_sky;          /* -k   */
+    int32_t sky_order;             /* -ko  0 = bootstrap median (sky.py:17-43) */
+    int32_t spatial_floor;         /* axes_dict["data_spatial_floor"] */
+    int32_t wavelength_start;      /* axes_dict["wavelength_start"] */
+} motes_params;
+
+/* Output block.  Every pointer may be NULL (that output is then not produced / copied).
+ * F = nframes, cap = bin capacity passed to the call. */
+typedef struct motes_outputs {
+    double* spectra;          /* [F][4][ndisp] optimal, optimal_err, aperture, aperture_err (extraction.py:208) */
+    double* ext_limits;       /* [F][2][ndisp] final extraction limits (core.py:248-252) */
+    double* sky_limits;       /* [F][2][ndisp] sky limits after the in-place clamp (sky.py:303-307) */
+    double* ext_params;       /* [F][cap][8]  per-bin [A,c,alpha,beta,B,m,first+wavstart,last+wavstart] (tracing.py:544-545) */
+    double* sky_params;       /* [F][cap][8] */
+    int32_t* ext_bins;        /* [F][cap][2]  bin first/last column (tracing.py:207,246) */
+    int32_t* sky_bins;        /* [F][cap][2] */
+    double* ext_bin_snr;      /* [F][cap] */
+    double* sky_bin_snr;      /* [F][cap] */
+    int32_t* n_ext_bins;      /* [F] */
+    int32_t* n_sky_bins;      /* [F] */
+    double* median_params;    /* [F][6]  fit of the full-frame median profile (tracing.py:403-456) */
+    double* scale;            /* [F]  data_scaling_factor */
+    double* seeing_px;        /* [F]  header_parameters["seeing"] after tracing.py:449 */
+    double* sky_model;        /* [F][ndisp] per-column sky level (order 0); 0 where not modelled */
+    double* sky_uncertainty;  /* [F][ndisp] */
+    int32_t* sky_flag;        /* [F][ndisp] 0 modelled, 1 skipped as constant (sky.py:338-339), 2 no sky pixels */
+    int32_t* frame_status;    /* [F] 0, MOTES_E_NOSKY or MOTES_E_FIT: what the reference would have raised for that frame */
+} motes_outputs;
+
+/* Upper bound on the number of bins get_bins can produce; use as `cap`. */
+int motes_bin_capacity(int ndisp, double minimum_column_limit);
+
+/* np.random.seed(seed[i]) for every frame: fills states[i*625 .. i*625+624] with the 624 MT19937
+ * state words followed by the position (624).  Pure host code. */
+int motes_seed_states(const uint32_t* seeds, int nframes, uint32_t* states);
+
+/* data / errs are modified in place on the device exactly as the reference modifies frame_dict
+ * (sky subtraction sky.py:375-397, scrub extraction.py:31-34); with copy_back != 0 the host
+ * version copies them back.  qual: uint8, 1 = good.  seeing / pixres: per frame.
+ * rng_states: [F][625] in/out, the numpy legacy RandomState of each frame (see motes_seed_states). */
+int motes_run_frames_host(motes_handle* h, double* data, double* errs, const uint8_t* qual, int nframes,
+                          int nspat, int ndisp, int cap, const motes_params* params, const double* seeing,
+                          const double* pixres, uint32_t* rng_states, int copy_back, const motes_outputs* out);
+int motes_run_frames_dev(motes_handle* h, double* data, double* errs, const uint8_t* qual, int nframes,
+                         int nspat, int ndisp, int cap, const motes_params* params, const double* seeing,
+                         const double* pixres, uint32_t* rng_states, const motes_outputs* out);
+/* float64 {0,1} quality frame -> uint8 on the device (harvesters produce float64, io/gmosio.py:50-52) */
+int motes_qual_pack_dev(motes_handle* h, const double* qual, size_t count, uint8_t* out);
+
+/* ---------------------------------------------------------------------------------------
+ * Stage entry points (one frame, host pointers): what each reference function would bind.
+ * ------------------------------------------------------------------------------------- */
+
+/* a1: np.nanmedian(frame_dict["data"], axis=1) (core.py:80) -> out[nspat] */
+int motes_row_median_host(motes_handle* h, const double* data, int nspat, int ndisp, double* out);
+
 /* a3: batched bounded-TRF Moffat fit.
  * Replaces tracing.moffat_least_squares (tracing.py:550-607) including the scipy
  * least_squares(method="trf", ftol=1e-12) call, for nfit profiles of nspat points on the
@@ -63,6 +127,28 @@ int motes_moffat_fit_batch_host(motes_handle* h, const double* profiles, int nfi
 int motes_moffat_fit_batch_dev(motes_handle* h, const double* profiles, int nfit, int nspat,
                                const double* alpha0, double* params, double* cost,
                                int32_t* nfev, int32_t* njev, int32_t* status);
+
+/* a5: tracing.get_bins (tracing.py:114-254).  bins: [cap][2], snr: [cap]; returns the count in *nbins.
+ * gap (optional, ndisp): 1 where np.median(data[:, c]) == 1 (chip-gap columns, tracing.py:506). */
+int motes_get_bins_host(motes_handle* h, const double* data, const double* errs, const uint8_t* qual,
+                        int nspat, int ndisp, int row_lo, int row_hi, double snr_limit,
+                        double minimum_column_limit, int cap, int32_t* bins, double* snr, int32_t* nbins,
+                        uint8_t* gap);
+
+/* a6: per-bin median spatial profiles (tracing.py:505-507) -> profiles[nbins][nspat] */
+int motes_bin_profiles_host(motes_handle* h, const double* data, int nspat, int ndisp, const int32_t* bins,
+                            int nbins, double* profiles);
+
+/* a8: tracing.interpolate_extraction_lims (tracing.py:315-375).  table: [4][nbins]. */
+int motes_interp_limits_host(motes_handle* h, const double* table, int nbins, int ndisp, double* lim_lo,
+                             double* lim_hi);
+
+/* a9: sky.subtract_sky with sky_order 0 (sky.py:257-399).  data / errs / lim_lo / lim_hi are updated
+ * in place as the reference does; rng_state[625] is numpy's legacy RandomState, advanced by exactly
+ * the draws the reference consumes.  Returns MOTES_E_NOSKY where the reference raises RuntimeError. */
+int motes_sky_subtract_host(motes_handle* h, double* data, double* errs, int nspat, int ndisp, double* lim_lo,
+                            double* lim_hi, int spatial_floor, int sky_order, uint32_t* rng_state,
+                            double* sky, double* sky_err, int32_t* flag, int32_t* n_sky, int32_t* n_good);
 
 /* a10: Horne optimal + aperture extraction with the single-pass 5-sigma mask.
  * Replaces extraction.optimal_extraction (extraction.py:39-210) for one frame.

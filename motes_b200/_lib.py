@@ -37,8 +37,47 @@ c_u8p = ctypes.POINTER(ctypes.c_uint8)
 c_u32p = ctypes.POINTER(ctypes.c_uint32)
 c_handle = ctypes.c_void_p
 
+
+
+class MotesParams(ctypes.Structure):
+    """struct motes_params (include/motes_b200.h)."""
+    _fields_ = [("minimum_column_limit", ctypes.c_double), ("extraction_snr_limit", ctypes.c_double),
+                ("sky_snr_limit", ctypes.c_double), ("sky_fwhm_multiplier", ctypes.c_double),
+                ("subtract_sky", ctypes.c_int32), ("sky_order", ctypes.c_int32),
+                ("spatial_floor", ctypes.c_int32), ("wavelength_start", ctypes.c_int32)]
+
+
+OUTPUT_FIELDS = ["spectra", "ext_limits", "sky_limits", "ext_params", "sky_params", "ext_bins", "sky_bins",
+                 "ext_bin_snr", "sky_bin_snr", "n_ext_bins", "n_sky_bins", "median_params", "scale", "seeing_px",
+                 "sky_model", "sky_uncertainty", "sky_flag", "frame_status"]
+
+
+class MotesOutputs(ctypes.Structure):
+    """struct motes_outputs (include/motes_b200.h): one void* per output, NULL = not wanted."""
+    _fields_ = [(name, ctypes.c_void_p) for name in OUTPUT_FIELDS]
+
+
+c_vp = ctypes.c_void_p
+c_int = ctypes.c_int
+
 # name -> (restype, argtypes); one entry per declaration in include/motes_b200.h
 SIGNATURES = {
+    "motes_bin_capacity": (ctypes.c_int, [c_int, ctypes.c_double]),
+    "motes_seed_states": (ctypes.c_int, [c_u32p, c_int, c_u32p]),
+    "motes_run_frames_host": (ctypes.c_int, [c_handle, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int,
+                                             ctypes.POINTER(MotesParams), c_vp, c_vp, c_vp, c_int,
+                                             ctypes.POINTER(MotesOutputs)]),
+    "motes_run_frames_dev": (ctypes.c_int, [c_handle, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int,
+                                            ctypes.POINTER(MotesParams), c_vp, c_vp, c_vp,
+                                            ctypes.POINTER(MotesOutputs)]),
+    "motes_qual_pack_dev": (ctypes.c_int, [c_handle, c_vp, ctypes.c_size_t, c_vp]),
+    "motes_row_median_host": (ctypes.c_int, [c_handle, c_dp, c_int, c_int, c_dp]),
+    "motes_get_bins_host": (ctypes.c_int, [c_handle, c_dp, c_dp, c_u8p, c_int, c_int, c_int, c_int, ctypes.c_double,
+                                           ctypes.c_double, c_int, c_ip, c_dp, c_ip, c_u8p]),
+    "motes_bin_profiles_host": (ctypes.c_int, [c_handle, c_dp, c_int, c_int, c_ip, c_int, c_dp]),
+    "motes_interp_limits_host": (ctypes.c_int, [c_handle, c_dp, c_int, c_int, c_dp, c_dp]),
+    "motes_sky_subtract_host": (ctypes.c_int, [c_handle, c_dp, c_dp, c_int, c_int, c_dp, c_dp, c_int, c_int, c_u32p,
+                                               c_dp, c_dp, c_ip, c_ip, c_ip]),
     "motes_create": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(c_handle)]),
     "motes_destroy": (ctypes.c_int, [c_handle]),
     "motes_last_error": (ctypes.c_char_p, []),

@@ -1,0 +1,137 @@
+// S/N-driven binning of the dispersion axis (tracing.get_bins, tracing.py:114-254) and the
+// per-column statistics it needs.
+//
+// The reference re-sums the whole (rows x width) window every time a bin grows by one column
+// (O(width^2) work per bin).  Here a first pass reduces every column once to
+//   S[c] = nansum(data[row_lo:row_hi, c]),  V[c] = nansum(errs[row_lo:row_hi, c]^2)
+// (Python slice semantics for row_lo/row_hi) and the greedy scan then grows windows by adding
+// one S/V pair per step.  The "every spatial row must hold more than min_cols good pixels"
+// test (tracing.py:281-312) keeps one running counter per row.
+#pragma once
+
+#include "common.cuh"
+
+namespace motes {
+
+// Neumaier-compensated accumulator: the reference sums pairwise, we sum sequentially; both stay
+// within an ulp or two of the exact sum, so threshold decisions (snr <= limit) agree unless the
+// exact value sits on the threshold.
+struct Accum {
+    double s = 0.0, c = 0.0;
+    MOTES_HD void add(double v) {
+        double t = s + v;
+        if (fabs(s) >= fabs(v)) c += (s - t) + v; else c += (v - t) + s;
+        s = t;
+    }
+    MOTES_HD double value() const { return s + c; }
+};
+
+struct ColumnStats {
+    double sum_data;     // S[c]
+    double sum_var;      // V[c]
+    uint8_t gap;         // np.median(data[:, c]) == 1  -> chip-gap column (tracing.py:506)
+};
+
+// One thread: statistics of column c of one frame (nspat x ndisp, dispersion fastest).
+MOTES_HD ColumnStats column_stats(const double* data, const double* errs, int nspat, int ndisp, int c,
+                                  int row_lo, int row_hi) {
+    int start, stop;
+    python_slice(row_lo, row_hi, nspat, &start, &stop);
+    Accum sd, sv;
+    int lt = 0, eq = 0, nan = 0;
+    double max_lt = -INFINITY, min_gt = INFINITY;
+    for (int r = 0; r < nspat; ++r) {
+        double d = data[(size_t)r * ndisp + c];
+        if (r >= start && r < stop) {
+            double e = errs[(size_t)r * ndisp + c];
+            double e2 = e * e;
+            if (d == d) sd.add(d);
+            if (e2 == e2) sv.add(e2);
+        }
+        if (d != d) ++nan;
+        else if (d < 1.0) { ++lt; if (d > max_lt) max_lt = d; }
+        else if (d == 1.0) ++eq;
+        else if (d < min_gt) min_gt = d;
+    }
+    ColumnStats out;
+    out.sum_data = sd.value();
+    out.sum_var = sv.value();
+    out.gap = (nan == 0 && median_equals(1.0, nspat, lt, eq, max_lt, min_gt)) ? 1 : 0;
+    return out;
+}
+
+// Greedy centre-outward scan for one frame by one thread scope.
+//   qual      nspat x ndisp, 1 = good, 0 = bad (uint8)
+//   S, V      per-column sums from column_stats
+//   counts    scratch, nspat ints shared by the scope
+//   bins_i    out, [2*maxbins] first/last column of each bin, sorted by first
+//   bins_snr  out, [maxbins]
+//   tmp_i / tmp_snr  scratch of the same sizes (blue-ward bins are produced in reverse order)
+// Returns the number of bins.
+template <class Scope>
+MOTES_HD int snr_bins_scan(const Scope& sc, const uint8_t* qual, const double* S, const double* V, int nspat,
+                           int ndisp, double snr_limit, double min_cols, int* counts, int32_t* bins_i,
+                           double* bins_snr, int32_t* tmp_i, double* tmp_snr) {
+    const int centre = ndisp / 2;
+    int n_blue = 0, n_red = 0;
+    for (int dir = 0; dir < 2; ++dir) {
+        int edge = centre, width = 0;
+        while (dir == 0 ? (edge - width > 0) : (edge + width < ndisp)) {
+            double snr = 0.0;
+            Accum sum_s, sum_v;
+            for (int r = sc.tid; r < nspat; r += sc.size()) counts[r] = 0;
+            sc.sync();
+            while (snr <= snr_limit) {
+                width += 1;
+                if (dir == 0 ? (edge - width < 0) : (edge + width > ndisp)) {
+                    width = (dir == 0) ? edge : ndisp - edge;
+                    break;
+                }
+                int col = (dir == 0) ? edge - width : edge + width - 1;
+                int is_short = 0;
+                for (int r = sc.tid; r < nspat; r += sc.size()) {
+                    int cnt = counts[r] + (int)qual[(size_t)r * ndisp + col];
+                    counts[r] = cnt;
+                    is_short |= ((double)cnt <= min_cols);
+                }
+                sum_s.add(S[col]);
+                sum_v.add(V[col]);
+                if (sc.any(is_short)) continue;
+                snr = sum_s.value() / sqrt(sum_v.value());
+            }
+            if (sc.tid == 0) {
+                if (dir == 0) {
+                    tmp_i[2 * n_blue] = edge - width;
+                    tmp_i[2 * n_blue + 1] = edge;
+                    tmp_snr[n_blue] = snr;
+                } else {
+                    bins_i[2 * n_red] = edge;          // parked at the front, shifted below
+                    bins_i[2 * n_red + 1] = edge + width;
+                    bins_snr[n_red] = snr;
+                }
+            }
+            if (dir == 0) { ++n_blue; edge -= width; } else { ++n_red; edge += width; }
+            width = 0;
+            sc.sync();
+        }
+    }
+    // bin_locations.sort(key=first): blue-ward bins reversed, then the red-ward ones
+    sc.sync();
+    // (simple two-step copy through the scratch arrays keeps this free of overlap hazards)
+    for (int i = sc.tid; i < n_red; i += sc.size()) {
+        tmp_i[2 * (n_blue + i)] = bins_i[2 * i];
+        tmp_i[2 * (n_blue + i) + 1] = bins_i[2 * i + 1];
+        tmp_snr[n_blue + i] = bins_snr[i];
+    }
+    sc.sync();
+    for (int i = sc.tid; i < n_blue + n_red; i += sc.size()) {
+        int src = (i < n_blue) ? (n_blue - 1 - i) : i;
+        bins_i[2 * i] = tmp_i[2 * src];
+        bins_i[2 * i + 1] = tmp_i[2 * src + 1];
+        bins_snr[i] = tmp_snr[src];
+    }
+    sc.sync();
+    return n_blue + n_red;
+}
+
+}  // namespace motes

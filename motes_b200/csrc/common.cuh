@@ -66,7 +66,148 @@ struct WarpCtx {
 };
 #endif
 
+// ---------------------------------------------------------------------------------------
+// Thread scopes for the cooperative (non-solver) routines: the same source runs on a warp,
+// on a whole CTA, or on one host thread (tests/hostsim).
+//   tid / size      this thread's index and the number of cooperating threads
+//   sync()          barrier over the scope (also orders shared-memory traffic)
+//   inc(p)          atomic ++ on a 32-bit counter shared by the scope
+//   umin(v)/dsum(v) scope-wide reductions; every thread receives the result
+// ---------------------------------------------------------------------------------------
+struct SeqScope {
+    int tid = 0;
+    static constexpr int size_c = 1;
+    MOTES_HD int size() const { return 1; }
+    MOTES_HD void sync() const {}
+    MOTES_HD void inc(uint32_t* p) const { ++*p; }
+    MOTES_HD void add(uint32_t* p, uint32_t v) const { *p += v; }
+    MOTES_HD unsigned long long umin(unsigned long long v, unsigned long long*) const { return v; }
+    MOTES_HD double dsum(double v, double*) const { return v; }
+    MOTES_HD int isum(int v, int*) const { return v; }
+    MOTES_HD int any(int p) const { return p; }
+    // exclusive prefix count of `flag` over the scope in thread order; *total = scope-wide count
+    MOTES_HD int scan_flags(int flag, int* total, uint32_t*) const { *total = flag; return 0; }
+};
+
+#if defined(__CUDACC__)
+struct WarpScope {
+    int tid;   // lane
+    __device__ __forceinline__ int size() const { return 32; }
+    __device__ __forceinline__ void sync() const { __syncwarp(); }
+    __device__ __forceinline__ void inc(uint32_t* p) const { atomicAdd(p, 1u); }
+    __device__ __forceinline__ void add(uint32_t* p, uint32_t v) const { atomicAdd(p, v); }
+    __device__ __forceinline__ unsigned long long umin(unsigned long long v, unsigned long long*) const {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            unsigned long long t = __shfl_xor_sync(0xffffffffu, v, o);
+            v = t < v ? t : v;
+        }
+        return v;
+    }
+    __device__ __forceinline__ double dsum(double v, double*) const {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        return v;
+    }
+    __device__ __forceinline__ int isum(int v, int*) const {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        return v;
+    }
+    __device__ __forceinline__ int any(int p) const { return __any_sync(0xffffffffu, p); }
+    __device__ __forceinline__ int scan_flags(int flag, int* total, uint32_t*) const {
+        unsigned b = __ballot_sync(0xffffffffu, flag);
+        *total = __popc(b);
+        return __popc(b & ((1u << tid) - 1u));
+    }
+};
+
+// Whole CTA.  Reductions go through a caller-provided shared-memory cell.
+struct BlockScope {
+    int tid;
+    __device__ __forceinline__ int size() const { return blockDim.x; }
+    __device__ __forceinline__ void sync() const { __syncthreads(); }
+    __device__ __forceinline__ void inc(uint32_t* p) const { atomicAdd(p, 1u); }
+    __device__ __forceinline__ void add(uint32_t* p, uint32_t v) const { atomicAdd(p, v); }
+    __device__ __forceinline__ unsigned long long umin(unsigned long long v, unsigned long long* cell) const {
+        if (tid == 0) *cell = ~0ull;
+        __syncthreads();
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            unsigned long long t = __shfl_xor_sync(0xffffffffu, v, o);
+            v = t < v ? t : v;
+        }
+        if ((tid & 31) == 0) atomicMin(cell, v);
+        __syncthreads();
+        unsigned long long r = *cell;
+        __syncthreads();
+        return r;
+    }
+    __device__ __forceinline__ int isum(int v, int* cell) const {
+        if (tid == 0) *cell = 0;
+        __syncthreads();
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((tid & 31) == 0) atomicAdd(cell, v);
+        __syncthreads();
+        int r = *cell;
+        __syncthreads();
+        return r;
+    }
+    __device__ __forceinline__ int any(int p) const { return __syncthreads_or(p); }
+    // scratch: 33 shared words.  Thread order = tid order.
+    __device__ __forceinline__ int scan_flags(int flag, int* total, uint32_t* scratch) const {
+        unsigned b = __ballot_sync(0xffffffffu, flag);
+        int lane = tid & 31, warp = tid >> 5, nwarp = (blockDim.x + 31) >> 5;
+        if (lane == 0) scratch[warp] = __popc(b);
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t v = (lane < nwarp) ? scratch[lane] : 0u;
+            uint32_t incl = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            scratch[lane] = incl - v;                  // exclusive warp offsets
+            if (lane == 31) scratch[32] = incl;        // grand total
+        }
+        __syncthreads();
+        int off = (int)scratch[warp] + __popc(b & ((1u << lane) - 1u));
+        *total = (int)scratch[32];
+        __syncthreads();
+        return off;
+    }
+};
+#endif
+
 MOTES_HD bool is_finite(double x) { return fabs(x) <= DBL_MAX; }   // false for NaN and +-inf
+
+// Python slice [lo:hi] on a sequence of length n -> [start, stop)
+MOTES_HD void python_slice(int lo, int hi, int n, int* start, int* stop) {
+    int a = lo < 0 ? (lo + n < 0 ? 0 : lo + n) : (lo > n ? n : lo);
+    int b = hi < 0 ? (hi + n < 0 ? 0 : hi + n) : (hi > n ? n : hi);
+    if (b < a) b = a;
+    *start = a;
+    *stop = b;
+}
+
+// Does the median (np.median over n values, none NaN) equal `thr` exactly?  Decided from counts
+// and the two neighbours of thr instead of a sort:  lt / eq = number of values < thr / == thr,
+// max_lt = largest value below thr, min_gt = smallest value above (only read when they decide).
+MOTES_HD bool median_equals(double thr, int n, int lt, int eq, double max_lt, double min_gt) {
+    if (n <= 0) return false;
+    int k1 = (n - 1) / 2, k2 = n / 2;
+    // class of an order statistic: -1 below thr, 0 equal, +1 above
+    int c1 = (k1 < lt) ? -1 : (k1 < lt + eq ? 0 : 1);
+    int c2 = (k2 < lt) ? -1 : (k2 < lt + eq ? 0 : 1);
+    if (c1 == 0 && c2 == 0) return true;
+    if (c1 == c2) return false;                 // both strictly on one side: the mean stays there
+    // the two middle values straddle: they are exactly the neighbours of the boundary
+    double a = (c1 == -1) ? max_lt : thr;
+    double b = (c2 == 1) ? min_gt : thr;
+    return (a + b) * 0.5 == thr;
+}
 
 // Moffat profile on a linear background, same operation order as common.py:89-92
 // (the library is compiled with -fmad=false so nothing here is contracted).

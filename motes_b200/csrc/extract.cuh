@@ -15,15 +15,6 @@ struct ColumnSpectrum {
     int lo, hi;          // int(floor(lim_lo)), int(ceil(lim_hi)) + 1 as the reference computes them
 };
 
-// Python slice [lo:hi] on a sequence of length n -> [start, stop)
-MOTES_HD void python_slice(int lo, int hi, int n, int* start, int* stop) {
-    int a = lo < 0 ? (lo + n < 0 ? 0 : lo + n) : (lo > n ? n : lo);
-    int b = hi < 0 ? (hi + n < 0 ? 0 : hi + n) : (hi > n ? n : hi);
-    if (b < a) b = a;
-    *start = a;
-    *stop = b;
-}
-
 // Median of the entries of col[0..n) (stride `st`) that are != 0, by rank counting.
 // Only used on the rare columns that contain zero errors (extraction.py:139).
 template <class Ctx>

@@ -1,0 +1,462 @@
+// __global__ kernels of libmotes_b200 (sm_100a).  Every kernel handles a batch of frames;
+// blockIdx.y (or a flattened work index) selects the frame.  Frames are (nspat, ndisp) float64,
+// dispersion fastest, `frame_stride` elements apart.
+#pragma once
+
+#include "common.cuh"
+#include "select.cuh"
+#include "trf.cuh"
+#include "bins.cuh"
+#include "limits.cuh"
+#include "sky.cuh"
+#include "extract.cuh"
+
+namespace motes {
+
+// Per-frame scalars that flow between the stages (device resident).
+struct FrameState {
+    double seeing;          // header seeing handed to the first fit [arcsec] (gmosio.py:118-126)
+    double pixres;          // arcsec / pixel
+    double scale;           // data_scaling_factor (tracing.py:435-437)
+    double seeing_px;       // FWHM of the median-profile fit in pixels (tracing.py:449)
+    double alpha0_first;    // seeing / pixres
+    double alpha0_bins;     // seeing_px / pixres  (quirk: tracing.py:449,580)
+    double median_params[6];
+    int row_lo, row_hi;     // int(floor(c - 3 FWHM)), int(ceil(c + 3 FWHM))  (core.py:134-135)
+    int status;             // 0, MOTES_E_FIT or MOTES_E_NOSKY
+    int pad;
+};
+
+// ---------------------------------------------------------------------------------------------
+// a1: np.nanmedian(data, axis=1) (core.py:80).  One CTA per (row, frame).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+row_median_kernel(const double* __restrict__ data, size_t frame_stride, int nspat, int ndisp,
+                  double* __restrict__ out /* [F][nspat] */) {
+    extern __shared__ __align__(16) unsigned char rm_smem[];
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(rm_smem);
+    uint32_t* hist = reinterpret_cast<uint32_t*>(keys + ndisp);
+    unsigned long long* cell = reinterpret_cast<unsigned long long*>(hist + 256);
+    int* icell = reinterpret_cast<int*>(cell + 1);
+    BlockScope sc{(int)threadIdx.x};
+    const int row = blockIdx.x, f = blockIdx.y;
+    const double* src = data + (size_t)f * frame_stride + (size_t)row * ndisp;
+    int nan = 0;
+    for (int i = threadIdx.x; i < ndisp; i += blockDim.x) {
+        double v = src[i];
+        nan += (v != v);
+        keys[i] = key_or_excluded(v);
+    }
+    int n_nan = sc.isum(nan, icell);
+    double med = median_of(sc, ArrayKeys{keys}, ndisp, ndisp - n_nan, hist, cell);
+    if (threadIdx.x == 0) out[(size_t)f * nspat + row] = med;
+}
+
+// exact 10^k for the scale factor (10 ** np.abs(np.floor(...)), tracing.py:437)
+__device__ __forceinline__ double pow10_int(double k) {
+    if (k >= 0.0 && k <= 22.0) {
+        double r = 1.0;
+        for (int i = 0; i < (int)k; ++i) r *= 10.0;
+        return r;
+    }
+    return pow(10.0, k);
+}
+
+// a2 (first half): scale factor of the median profile; one warp per frame.
+__global__ void __launch_bounds__(32)
+frame_prep_kernel(const double* __restrict__ medprof, int nspat, FrameState* __restrict__ st) {
+    __shared__ uint32_t hist[256];
+    __shared__ unsigned long long cell;
+    WarpScope sc{(int)threadIdx.x};
+    const int f = blockIdx.x;
+    const double* prof = medprof + (size_t)f * nspat;
+    int nan = 0;
+    for (int i = threadIdx.x; i < nspat; i += 32) nan += (prof[i] != prof[i]);
+    int n_nan = sc.isum(nan, nullptr);
+    struct ProfKeys {
+        const double* p;
+        __device__ unsigned long long operator()(int i) const { return key_or_excluded(p[i]); }
+    };
+    double med = median_of(sc, ProfKeys{prof}, nspat, nspat - n_nan, hist, &cell);
+    if (threadIdx.x == 0) {
+        FrameState& s = st[f];
+        s.scale = pow10_int(fabs(floor(log10(fabs(med)))));
+        s.alpha0_first = s.seeing / s.pixres;
+        s.status = 0;
+    }
+}
+
+// a2 (second half) + a7: after the median-profile fit.  One thread per frame.
+__global__ void frame_post_kernel(int nframes, const double* __restrict__ fit_params, const int32_t* __restrict__ fit_status,
+                                  FrameState* __restrict__ st) {
+    int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nframes) return;
+    FrameState& s = st[f];
+    const double* p = fit_params + (size_t)f * kParams;
+    if (fit_status[f] < 0) s.status = MOTES_E_FIT;
+    double fwhm = moffat_fwhm(p[2], p[3]);
+    s.seeing_px = fwhm;                         // header_parameters["seeing"] is now in pixels
+    s.alpha0_bins = fwhm / s.pixres;
+    for (int k = 0; k < kParams; ++k) s.median_params[k] = p[k];
+    s.median_params[0] = p[0] / s.scale;
+    s.median_params[4] = p[4] / s.scale;
+    s.median_params[5] = p[5] / s.scale;
+    double lo = p[1] - (3.0 * fwhm), hi = p[1] + (3.0 * fwhm);
+    s.row_lo = (int)floor(lo);
+    s.row_hi = (int)ceil(hi);
+}
+
+// ---------------------------------------------------------------------------------------------
+// a5 / a6 support: per-column sums over the binning rows and the chip-gap flag.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+column_stats_kernel(const double* __restrict__ data, const double* __restrict__ errs, size_t frame_stride, int nspat,
+                    int ndisp, const FrameState* __restrict__ st, double* __restrict__ S, double* __restrict__ V,
+                    uint8_t* __restrict__ gap) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x, f = blockIdx.y;
+    if (c >= ndisp) return;
+    ColumnStats cs = column_stats(data + (size_t)f * frame_stride, errs + (size_t)f * frame_stride, nspat, ndisp, c,
+                                  st[f].row_lo, st[f].row_hi);
+    S[(size_t)f * ndisp + c] = cs.sum_data;
+    V[(size_t)f * ndisp + c] = cs.sum_var;
+    gap[(size_t)f * ndisp + c] = cs.gap;
+}
+
+// a5: greedy S/N binning, one CTA per frame (tracing.py:114-254).
+__global__ void __launch_bounds__(1024)
+bins_kernel(const uint8_t* __restrict__ qual, size_t qual_stride, const double* __restrict__ S,
+            const double* __restrict__ V, int nspat, int ndisp, double snr_limit, double min_cols, int cap,
+            int32_t* __restrict__ bins_i /* [F][2*cap] */, double* __restrict__ bins_snr /* [F][cap] */,
+            int32_t* __restrict__ tmp_i, double* __restrict__ tmp_snr, int32_t* __restrict__ nbins) {
+    extern __shared__ __align__(16) int bins_counts[];
+    BlockScope sc{(int)threadIdx.x};
+    const int f = blockIdx.x;
+    int nb = snr_bins_scan(sc, qual + (size_t)f * qual_stride, S + (size_t)f * ndisp, V + (size_t)f * ndisp, nspat,
+                           ndisp, snr_limit, min_cols, bins_counts, bins_i + (size_t)f * 2 * cap,
+                           bins_snr + (size_t)f * cap, tmp_i + (size_t)f * 2 * cap, tmp_snr + (size_t)f * cap);
+    if (threadIdx.x == 0) nbins[f] = nb;
+}
+
+// a6 (first half): median spatial profile of every bin, leaving out chip-gap columns
+// (tracing.py:505-507).  One warp per (frame, bin, row); keys are read straight from the frame.
+constexpr int kProfWarps = 8;
+__global__ void __launch_bounds__(kProfWarps * 32)
+bin_profile_kernel(const double* __restrict__ data, size_t frame_stride, int nspat, int ndisp,
+                   const uint8_t* __restrict__ gap, const int32_t* __restrict__ bins_i, const int32_t* __restrict__ nbins,
+                   int cap, double* __restrict__ profiles /* [F][cap][nspat] */) {
+    __shared__ uint32_t hist_all[kProfWarps][256];
+    __shared__ unsigned long long cells[kProfWarps];
+    const int warp = threadIdx.x >> 5;
+    WarpScope sc{(int)(threadIdx.x & 31)};
+    const int f = blockIdx.y;
+    const long long item = (long long)blockIdx.x * kProfWarps + warp;
+    const int b = (int)(item / nspat), row = (int)(item % nspat);
+    if (b >= nbins[f]) return;
+    const int first = bins_i[((size_t)f * cap + b) * 2], last = bins_i[((size_t)f * cap + b) * 2 + 1];
+    const int w = last - first;
+    struct BinKeys {
+        const double* p;
+        const uint8_t* g;
+        __device__ unsigned long long operator()(int i) const { return g[i] ? kKeyExcluded : key_or_excluded(p[i]); }
+    };
+    BinKeys keys{data + (size_t)f * frame_stride + (size_t)row * ndisp + first, gap + (size_t)f * ndisp + first};
+    int valid = 0;
+    for (int i = sc.tid; i < w; i += 32) valid += (keys(i) != kKeyExcluded);
+    int n_valid = sc.isum(valid, nullptr);
+    double med = median_of(sc, keys, w, n_valid, hist_all[warp], &cells[warp]);
+    if (sc.tid == 0) profiles[((size_t)f * cap + b) * nspat + row] = med;
+}
+
+// ---------------------------------------------------------------------------------------------
+// a3: one warp per Moffat fit; slab in shared memory; work handed out by an atomic counter.
+// Work item i -> frame i / bound, slot i % bound; slots >= nbins[frame] are skipped.
+// ---------------------------------------------------------------------------------------------
+constexpr int kFitMaxWarps = 8;
+
+struct FitBatch {
+    const double* profiles;     // [(frame * cap + slot) * m]
+    int m;
+    int nframes, bound, cap;
+    const int32_t* nbins;       // per frame, or nullptr: every slot < bound is a fit
+    const double* alpha0;       // per fit [(frame*cap+slot)] or per frame when alpha0_frame_stride > 0
+    size_t alpha0_frame_stride; // in bytes between frames when alpha0 lives inside FrameState; 0 = per-fit array
+    const double* scale;        // per frame (same addressing as alpha0), or nullptr = 1
+    size_t scale_frame_stride;
+    double* params;             // [(frame*cap+slot) * 6]
+    double* cost;
+    int32_t* nfev;
+    int32_t* njev;
+    int32_t* status;
+};
+
+__global__ void __launch_bounds__(kFitMaxWarps * 32)
+moffat_fit_kernel(FitBatch fb, unsigned int* work_counter) {
+    extern __shared__ __align__(16) double fit_smem[];
+    const int warp = threadIdx.x >> 5;
+    WarpCtx ctx{(int)(threadIdx.x & 31)};
+    const int m = fb.m;
+    const size_t per_warp = fit_scratch_doubles(m);
+    double* slab = fit_smem + per_warp * warp;
+    FitScratch ws;
+    ws.y = slab;
+    ws.unit = ws.y + m;
+    ws.a = ws.unit + m;
+    ws.w = ws.a + 7 * (size_t)m;
+    ws.v = ws.w + 36;
+    const unsigned int total = (unsigned int)fb.nframes * (unsigned int)fb.bound;
+    while (true) {
+        unsigned int item = 0;
+        if (ctx.lane == 0) item = atomicAdd(work_counter, 1u);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= total) break;
+        const int f = item / fb.bound, slot = item % fb.bound;
+        if (fb.nbins && slot >= fb.nbins[f]) continue;
+        const size_t idx = (size_t)f * fb.cap + slot;
+        double alpha0 = fb.alpha0_frame_stride
+                            ? *reinterpret_cast<const double*>(reinterpret_cast<const char*>(fb.alpha0) + f * fb.alpha0_frame_stride)
+                            : fb.alpha0[idx];
+        double scale = 1.0;
+        if (fb.scale)
+            scale = *reinterpret_cast<const double*>(reinterpret_cast<const char*>(fb.scale) + f * fb.scale_frame_stride);
+        FitResult r;
+        trf_fit_moffat(ctx, m, fb.profiles + idx * m, scale, alpha0, ws, &r);
+        if (ctx.lane == 0) {
+            for (int k = 0; k < kParams; ++k) fb.params[idx * kParams + k] = r.x[k];
+            if (fb.cost) fb.cost[idx] = r.cost;
+            if (fb.nfev) fb.nfev[idx] = r.nfev;
+            if (fb.njev) fb.njev[idx] = r.njev;
+            if (fb.status) fb.status[idx] = r.status;
+        }
+        __syncwarp();
+    }
+}
+
+// a6 (second half): un-scale, extraction limits, limit table row and the 8-vector of a bin
+// (tracing.py:517-545).  One thread per (frame, slot).
+__global__ void bin_post_kernel(int nframes, int bound, int cap, const int32_t* __restrict__ nbins,
+                                const int32_t* __restrict__ bins_i, const double* __restrict__ fit_params,
+                                const int32_t* __restrict__ fit_status, FrameState* __restrict__ st,
+                                double fwhm_multiplier, int wavelength_start,
+                                double* __restrict__ params8 /* [F][cap][8] */, double* __restrict__ table /* [F][4][cap] */) {
+    int item = blockIdx.x * blockDim.x + threadIdx.x;
+    if (item >= nframes * bound) return;
+    int f = item / bound, b = item % bound;
+    if (b >= nbins[f]) return;
+    size_t idx = (size_t)f * cap + b;
+    const double* p = fit_params + idx * kParams;
+    if (fit_status[idx] < 0) atomicMin(&st[f].status, (int)MOTES_E_FIT);
+    const double scale = st[f].scale;
+    double q[kParams];
+    for (int k = 0; k < kParams; ++k) q[k] = p[k];
+    q[0] = p[0] / scale;
+    q[4] = p[4] / scale;
+    q[5] = p[5] / scale;
+    double fwhm = moffat_fwhm(q[2], q[3]);
+    int first = bins_i[idx * 2], last = bins_i[idx * 2 + 1];
+    double* t = table + (size_t)f * 4 * cap;
+    t[b] = (double)(first + last) * 0.5;
+    t[cap + b] = q[1] - (fwhm_multiplier * fwhm);
+    t[2 * cap + b] = q[1] + (fwhm_multiplier * fwhm);
+    t[3 * cap + b] = q[1];
+    double* o = params8 + idx * 8;
+    for (int k = 0; k < kParams; ++k) o[k] = q[k];
+    o[6] = (double)(first + wavelength_start);
+    o[7] = (double)(last + wavelength_start);
+}
+
+// a8: limits for every dispersion pixel; one CTA per frame.
+__global__ void __launch_bounds__(256)
+limits_kernel(const double* __restrict__ table, int cap, const int32_t* __restrict__ nbins, int ndisp,
+              double* __restrict__ limits /* [F][2][ndisp] */, double* __restrict__ inner /* [F][2*(ndisp+2)] */) {
+    __shared__ unsigned long long keys[160];
+    __shared__ uint32_t hist[256];
+    __shared__ unsigned long long cell;
+    __shared__ int icell;
+    BlockScope sc{(int)threadIdx.x};
+    const int f = blockIdx.x;
+    interpolate_limits(sc, table + (size_t)f * 4 * cap, cap, nbins[f], ndisp, limits + (size_t)f * 2 * ndisp,
+                       limits + (size_t)f * 2 * ndisp + ndisp, inner + (size_t)f * 2 * (ndisp + 2), keys, hist, &cell,
+                       &icell);
+}
+
+// ---------------------------------------------------------------------------------------------
+// a9: sky.  Tile geometry shared with the extraction kernel: a CTA stages kTileCols consecutive
+// columns through shared memory with coalesced row-segment loads; row stride is odd in doubles so
+// a warp walking down a column is bank-conflict free.
+// ---------------------------------------------------------------------------------------------
+constexpr int kTileCols = 16;
+constexpr int kTileStride = kTileCols + 1;
+constexpr int kTileThreads = 256;
+constexpr int kTileWarps = kTileThreads / 32;
+
+__global__ void __launch_bounds__(kTileThreads)
+sky_prepare_kernel(const double* __restrict__ data, size_t frame_stride, int nspat, int ndisp,
+                   double* __restrict__ limits /* [F][2][ndisp], clamped in place */, int spatial_floor,
+                   int32_t* __restrict__ n_sky, int32_t* __restrict__ n_good, int32_t* __restrict__ flag,
+                   double* __restrict__ sorted /* [F][ndisp][nspat] */, uint16_t* __restrict__ rank_of,
+                   FrameState* __restrict__ st) {
+    extern __shared__ __align__(16) unsigned char sp_smem[];
+    double* tile = reinterpret_cast<double*>(sp_smem);
+    unsigned long long* keys_all = reinterpret_cast<unsigned long long*>(tile + (size_t)nspat * kTileStride);
+    uint32_t* hist_all = reinterpret_cast<uint32_t*>(keys_all + (size_t)kTileWarps * nspat);
+    unsigned long long* cells = reinterpret_cast<unsigned long long*>(hist_all + kTileWarps * 256);
+    uint16_t* rows_all = reinterpret_cast<uint16_t*>(cells + kTileWarps);
+    const int f = blockIdx.y;
+    const int col0 = blockIdx.x * kTileCols;
+    const int ncols = min(kTileCols, ndisp - col0);
+    const double* src = data + (size_t)f * frame_stride;
+    for (int idx = threadIdx.x; idx < nspat * kTileCols; idx += blockDim.x) {
+        int row = idx / kTileCols, c = idx % kTileCols;
+        if (c < ncols) tile[row * kTileStride + c] = src[(size_t)row * ndisp + col0 + c];
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5;
+    WarpScope sc{(int)(threadIdx.x & 31)};
+    for (int c = warp; c < ncols; c += kTileWarps) {
+        const size_t col = (size_t)f * ndisp + col0 + c;
+        double* lo = limits + (size_t)f * 2 * ndisp + col0 + c;
+        double* hi = lo + ndisp;
+        int ns, ng, fl;
+        int icell;
+        sky_prepare_column(sc, tile + c, kTileStride, nspat, lo, hi, spatial_floor, &ns, &ng, &fl,
+                           sorted + col * nspat, rank_of + col * nspat, rows_all + (size_t)warp * nspat,
+                           keys_all + (size_t)warp * nspat, hist_all + warp * 256, cells + warp, &icell);
+        if (sc.tid == 0) {
+            n_sky[col] = ns;
+            n_good[col] = ng;
+            flag[col] = fl;
+            if (fl == kSkyNoPixels) atomicMin(&st[f].status, (int)MOTES_E_NOSKY);
+        }
+        __syncwarp();
+    }
+}
+
+// One CTA per frame walks the columns in order and consumes the frame's MT19937 stream.
+constexpr int kBootThreads = 640;     // >= 624: one pass of the CTA covers a whole block of outputs
+
+__global__ void __launch_bounds__(kBootThreads)
+sky_bootstrap_kernel(uint32_t* __restrict__ rng /* [F][625]: 624 state words + position */, int nspat, int ndisp,
+                     const int32_t* __restrict__ n_good, const int32_t* __restrict__ flag,
+                     const double* __restrict__ sorted, const uint16_t* __restrict__ rank_of,
+                     double* __restrict__ sky, double* __restrict__ sky_err, const FrameState* __restrict__ st) {
+    extern __shared__ __align__(16) unsigned char sb_smem[];
+    double* meds = reinterpret_cast<double*>(sb_smem);
+    uint32_t* mt = reinterpret_cast<uint32_t*>(meds + kBootstrap);
+    uint32_t* scan = mt + kMtN;
+    int* ctl = reinterpret_cast<int*>(scan + 34);
+    uint32_t* hist = reinterpret_cast<uint32_t*>(ctl + 2);
+    uint16_t* ranks = reinterpret_cast<uint16_t*>(hist + (size_t)50 * nspat);
+    BlockScope sc{(int)threadIdx.x};
+    const int f = blockIdx.x;
+    uint32_t* state = rng + (size_t)f * 625;
+    for (int i = threadIdx.x; i < kMtN; i += blockDim.x) mt[i] = state[i];
+    if (threadIdx.x == 0) ctl[1] = (int)state[624];
+    __syncthreads();
+    int pos = ctl[1];
+    __syncthreads();
+    if (st[f].status == 0) {
+        const size_t base = (size_t)f * ndisp;
+        sky_bootstrap_frame(sc, mt, &pos, ndisp, n_good + base, flag + base, sorted + base * nspat,
+                            rank_of + base * nspat, (size_t)nspat, sky + base, sky_err + base, hist, ranks, meds,
+                            scan, ctl);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kMtN; i += blockDim.x) state[i] = mt[i];
+    if (threadIdx.x == 0) state[624] = (uint32_t)pos;
+}
+
+__global__ void __launch_bounds__(128)
+sky_apply_kernel(double* __restrict__ data, double* __restrict__ errs, size_t frame_stride, int nspat, int ndisp,
+                 const int32_t* __restrict__ flag, const double* __restrict__ sky, const double* __restrict__ sky_err,
+                 const FrameState* __restrict__ st) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x, f = blockIdx.y;
+    if (c >= ndisp || st[f].status != 0) return;
+    const size_t col = (size_t)f * ndisp + c;
+    sky_apply_column(data + (size_t)f * frame_stride, errs + (size_t)f * frame_stride, nspat, ndisp, c, flag[col],
+                     sky[col], sky_err[col]);
+}
+
+// np.random.seed(k) for every frame: state words + position 624 (regenerate before the first draw).
+__global__ void seed_states_kernel(const uint32_t* __restrict__ seeds, int nframes, uint32_t* __restrict__ rng) {
+    int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nframes) return;
+    mt_seed(rng + (size_t)f * 625, seeds[f]);
+    rng[(size_t)f * 625 + 624] = kMtN;
+}
+
+// ---------------------------------------------------------------------------------------------
+// a10: extraction (extraction.py:39-210).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kTileThreads)
+optimal_extract_kernel(double* __restrict__ data, const double* __restrict__ errs, size_t frame_stride, int nspat,
+                       int ndisp, const double* __restrict__ limits /* [F][2][ndisp] */,
+                       const double* __restrict__ bin_params /* [F][cap][8] */, const int32_t* __restrict__ nbins,
+                       int cap, int wavelength_start, double* __restrict__ spectra /* [F][4][ndisp] */,
+                       int32_t* __restrict__ lo_idx, int32_t* __restrict__ hi_idx, uint8_t* __restrict__ crmask) {
+    extern __shared__ __align__(16) double ext_smem[];
+    double* sd = ext_smem;
+    double* se = ext_smem + (size_t)nspat * kTileStride;
+    const int f = blockIdx.y;
+    const int col0 = blockIdx.x * kTileCols;
+    const int ncols = min(kTileCols, ndisp - col0);
+    double* fdata = data + (size_t)f * frame_stride;
+    const double* ferrs = errs + (size_t)f * frame_stride;
+    // stage + scrub (extraction.py:31-34, 86)
+    for (int idx = threadIdx.x; idx < nspat * kTileCols; idx += blockDim.x) {
+        int row = idx / kTileCols, c = idx % kTileCols;
+        if (c < ncols) {
+            size_t g = (size_t)row * ndisp + col0 + c;
+            double d = fdata[g];
+            double e = fabs(ferrs[g]);
+            if (!is_finite(e)) e = 0.0;
+            if (!is_finite(d)) { d = 0.0; fdata[g] = 0.0; }
+            sd[row * kTileStride + c] = d;
+            se[row * kTileStride + c] = e;
+        }
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5;
+    WarpCtx ctx{(int)(threadIdx.x & 31)};
+    const int nb = nbins[f];
+    const double* bp = bin_params + (size_t)f * cap * 8;
+    const double* lim_lo = limits + (size_t)f * 2 * ndisp;
+    const double* lim_hi = lim_lo + ndisp;
+    for (int c = warp; c < ncols; c += kTileWarps) {
+        int col = col0 + c;
+        // the bin whose parameters the reference holds when it reaches this column
+        // (extraction.py:104-112): bins tile the axis in order, so it is the last bin whose
+        // first column is <= this column.
+        int which = -1;
+        {
+            int lo_b = 0, hi_b = nb - 1;
+            double key = (double)(col + wavelength_start);
+            while (lo_b <= hi_b) {
+                int mid = (lo_b + hi_b) >> 1;
+                if (bp[(size_t)mid * 8 + 6] <= key) { which = mid; lo_b = mid + 1; }
+                else hi_b = mid - 1;
+            }
+        }
+        double zero_bin[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        const double* bin = (which >= 0) ? bp + (size_t)which * 8 : zero_bin;
+        ColumnSpectrum out;
+        extract_column(ctx, sd + c, se + c, kTileStride, nspat, lim_lo[col], lim_hi[col], bin, &out,
+                       crmask ? crmask + ((size_t)f * ndisp + col) * nspat : nullptr);
+        if (ctx.lane == 0) {
+            double* sp = spectra + (size_t)f * 4 * ndisp;
+            sp[col] = out.optimal;
+            sp[(size_t)ndisp + col] = out.optimal_err;
+            sp[(size_t)2 * ndisp + col] = out.aperture;
+            sp[(size_t)3 * ndisp + col] = out.aperture_err;
+            if (lo_idx) lo_idx[(size_t)f * ndisp + col] = out.lo;
+            if (hi_idx) hi_idx[(size_t)f * ndisp + col] = out.hi;
+        }
+    }
+}
+
+// float64 {0,1} quality frame -> uint8 (harvesters hand out float64, gmosio.py:50-52)
+__global__ void qual_pack_kernel(const double* __restrict__ q, size_t n, uint8_t* __restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (q[i] != 0.0) ? 1 : 0;
+}
+
+}  // namespace motes

@@ -1,123 +1,130 @@
-// libmotes_b200.so: CUDA kernels (sm_100a) and the C ABI declared in include/motes_b200.h.
+// libmotes_b200.so: stage launchers and the C ABI declared in include/motes_b200.h.
 #include "handle.cuh"
-#include "trf.cuh"
-#include "extract.cuh"
+#include "kernels.cuh"
 
 namespace motes {
 
-// ------------------------------------------------------------------------------------------
-// a3: one warp per Moffat fit, slab in shared memory, work handed out by an atomic counter.
-// ------------------------------------------------------------------------------------------
-constexpr int kFitMaxWarps = 8;
+// Work-area slots inside motes_handle::work
+enum WorkSlot { W_STATE = 0, W_F64, W_I32, W_U8, W_SORTED, W_RANKS, W_PROFILES, W_RNG, W_QUAL, W_HOSTOUT };
 
-__global__ void __launch_bounds__(kFitMaxWarps * 32)
-moffat_fit_kernel(const double* __restrict__ profiles, int nfit, int m, const double* __restrict__ alpha0,
-                  double* __restrict__ params, double* __restrict__ cost, int32_t* __restrict__ nfev,
-                  int32_t* __restrict__ njev, int32_t* __restrict__ status, unsigned int* work_counter) {
-    extern __shared__ __align__(16) double fit_smem[];
-    const int warp = threadIdx.x >> 5;
-    WarpCtx ctx{(int)(threadIdx.x & 31)};
-    const size_t per_warp = fit_scratch_doubles(m);
-    double* slab = fit_smem + per_warp * warp;
-    FitScratch ws;
-    ws.y = slab;
-    ws.unit = ws.y + m;
-    ws.a = ws.unit + m;
-    ws.w = ws.a + 7 * (size_t)m;
-    ws.v = ws.w + 36;
-    while (true) {
-        unsigned int f = 0;
-        if (ctx.lane == 0) f = atomicAdd(work_counter, 1u);
-        f = __shfl_sync(0xffffffffu, f, 0);
-        if (f >= (unsigned int)nfit) break;
-        FitResult r;
-        trf_fit_moffat(ctx, m, profiles + (size_t)f * m, alpha0[f], ws, &r);
-        if (ctx.lane == 0) {
-            for (int k = 0; k < kParams; ++k) params[(size_t)f * kParams + k] = r.x[k];
-            if (cost) cost[f] = r.cost;
-            if (nfev) nfev[f] = r.nfev;
-            if (njev) njev[f] = r.njev;
-            if (status) status[f] = r.status;
-        }
-        __syncwarp();
+// Device-side working set of one batch.  All pointers are carved out of handle scratch.
+struct Batch {
+    int F, nspat, ndisp, cap;
+    FrameState* st;
+    double *medprof, *fit0_params, *S, *V;
+    int32_t* fit0_status;
+    uint8_t* gap;
+    // two bin sets: [0] sky localisation, [1] extraction
+    int32_t* bins_i[2];
+    double* bins_snr[2];
+    int32_t* nbins[2];
+    int32_t* tmp_i;
+    double* tmp_snr;
+    double* profiles;
+    double *fit_params, *fit_cost;
+    int32_t *fit_nfev, *fit_njev, *fit_status;
+    double* params8[2];
+    double* table;
+    double* limits[2];
+    double* inner;
+    int32_t *n_sky, *n_good, *sky_flag;
+    double *sorted, *sky, *sky_err;
+    uint16_t* rank_of;
+    double* spectra;
+};
+
+struct Carver {
+    char* base;
+    size_t off = 0;
+    explicit Carver(void* p) : base(static_cast<char*>(p)) {}
+    template <class T>
+    T* take(size_t count) {
+        off = (off + 255) & ~size_t(255);
+        T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+        off += count * sizeof(T);
+        return p;
     }
+};
+
+static size_t carve_f64(Batch& b, void* base) {
+    Carver c(base);
+    const size_t F = b.F, ns = b.nspat, nd = b.ndisp, cap = b.cap;
+    b.medprof = c.take<double>(F * ns);
+    b.fit0_params = c.take<double>(F * kParams);
+    b.S = c.take<double>(F * nd);
+    b.V = c.take<double>(F * nd);
+    for (int k = 0; k < 2; ++k) b.bins_snr[k] = c.take<double>(F * cap);
+    b.tmp_snr = c.take<double>(F * cap);
+    b.fit_params = c.take<double>(F * cap * kParams);
+    b.fit_cost = c.take<double>(F * cap);
+    for (int k = 0; k < 2; ++k) b.params8[k] = c.take<double>(F * cap * 8);
+    b.table = c.take<double>(F * 4 * cap);
+    for (int k = 0; k < 2; ++k) b.limits[k] = c.take<double>(F * 2 * nd);
+    b.inner = c.take<double>(F * 2 * (nd + 2));
+    b.sky = c.take<double>(F * nd);
+    b.sky_err = c.take<double>(F * nd);
+    b.spectra = c.take<double>(F * 4 * nd);
+    return c.off + 256;
 }
 
-// ------------------------------------------------------------------------------------------
-// a10: extraction.  A CTA stages a tile of kExtCols consecutive columns (all nspat rows of data
-// and errs) through shared memory with coalesced row-segment loads, then each warp extracts
-// columns of the tile.  Row stride in shared memory is kExtCols+1 doubles (odd -> no bank
-// conflicts when a warp walks down a column).
-// ------------------------------------------------------------------------------------------
-constexpr int kExtCols = 16;
-constexpr int kExtStride = kExtCols + 1;
-constexpr int kExtThreads = 256;
-
-__global__ void __launch_bounds__(kExtThreads)
-optimal_extract_kernel(double* __restrict__ data, const double* __restrict__ errs, int nspat, int ndisp,
-                       const double* __restrict__ lim_lo, const double* __restrict__ lim_hi,
-                       const double* __restrict__ bin_params, int nbins, int wavelength_start,
-                       double* __restrict__ spectra, int32_t* __restrict__ lo_idx, int32_t* __restrict__ hi_idx,
-                       uint8_t* __restrict__ crmask) {
-    extern __shared__ __align__(16) double ext_smem[];
-    double* sd = ext_smem;
-    double* se = ext_smem + (size_t)nspat * kExtStride;
-    const int col0 = blockIdx.x * kExtCols;
-    const int ncols = min(kExtCols, ndisp - col0);
-    // stage + scrub (extraction.py:31-34, 86)
-    for (int idx = threadIdx.x; idx < nspat * kExtCols; idx += blockDim.x) {
-        int row = idx / kExtCols, c = idx % kExtCols;
-        if (c < ncols) {
-            size_t g = (size_t)row * ndisp + col0 + c;
-            double d = data[g];
-            double e = fabs(errs[g]);
-            if (!is_finite(e)) e = 0.0;
-            if (!is_finite(d)) { d = 0.0; data[g] = 0.0; }
-            sd[row * kExtStride + c] = d;
-            se[row * kExtStride + c] = e;
-        }
-    }
-    __syncthreads();
-    const int warp = threadIdx.x >> 5;
-    WarpCtx ctx{(int)(threadIdx.x & 31)};
-    for (int c = warp; c < ncols; c += kExtThreads / 32) {
-        int col = col0 + c;
-        // the bin whose parameters the reference holds when it reaches this column
-        // (extraction.py:104-112): last bin b with first_col(b) <= col, stepping only through
-        // consecutive bins; bins tile the axis, so that is the bin containing the column.
-        int which = -1;
-        {
-            int lo_b = 0, hi_b = nbins - 1;
-            double key = (double)(col + wavelength_start);
-            while (lo_b <= hi_b) {
-                int mid = (lo_b + hi_b) >> 1;
-                if (bin_params[(size_t)mid * 8 + 6] <= key) { which = mid; lo_b = mid + 1; }
-                else hi_b = mid - 1;
-            }
-        }
-        double zero_bin[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        const double* bin = (which >= 0) ? bin_params + (size_t)which * 8 : zero_bin;
-        ColumnSpectrum out;
-        extract_column(ctx, sd + c, se + c, kExtStride, nspat, lim_lo[col], lim_hi[col], bin, &out,
-                       crmask ? crmask + (size_t)col * nspat : nullptr);
-        if (ctx.lane == 0) {
-            spectra[col] = out.optimal;
-            spectra[(size_t)ndisp + col] = out.optimal_err;
-            spectra[(size_t)2 * ndisp + col] = out.aperture;
-            spectra[(size_t)3 * ndisp + col] = out.aperture_err;
-            if (lo_idx) lo_idx[col] = out.lo;
-            if (hi_idx) hi_idx[col] = out.hi;
-        }
-    }
+static size_t carve_i32(Batch& b, void* base) {
+    Carver c(base);
+    const size_t F = b.F, nd = b.ndisp, cap = b.cap;
+    b.fit0_status = c.take<int32_t>(F);
+    for (int k = 0; k < 2; ++k) b.bins_i[k] = c.take<int32_t>(F * 2 * cap);
+    for (int k = 0; k < 2; ++k) b.nbins[k] = c.take<int32_t>(F);
+    b.tmp_i = c.take<int32_t>(F * 2 * cap);
+    b.fit_nfev = c.take<int32_t>(F * cap);
+    b.fit_njev = c.take<int32_t>(F * cap);
+    b.fit_status = c.take<int32_t>(F * cap);
+    b.n_sky = c.take<int32_t>(F * nd);
+    b.n_good = c.take<int32_t>(F * nd);
+    b.sky_flag = c.take<int32_t>(F * nd);
+    return c.off + 256;
 }
 
-// ------------------------------------------------------------------------------------------
-// launch helpers
-// ------------------------------------------------------------------------------------------
-static int launch_fit(motes_handle* h, const double* profiles, int nfit, int m, const double* alpha0,
-                      double* params, double* cost, int32_t* nfev, int32_t* njev, int32_t* status) {
-    if (nfit <= 0) return MOTES_OK;
-    size_t per_warp = fit_scratch_doubles(m) * sizeof(double);
+static int make_batch(motes_handle* h, Batch& b, int F, int nspat, int ndisp, int cap, bool need_sky) {
+    b = Batch();
+    b.F = F; b.nspat = nspat; b.ndisp = ndisp; b.cap = cap;
+    MOTES_TRY(h->work[W_STATE].ensure(sizeof(FrameState) * (size_t)F));
+    b.st = h->work[W_STATE].as<FrameState>();
+    MOTES_TRY(h->work[W_F64].ensure(carve_f64(b, nullptr)));
+    carve_f64(b, h->work[W_F64].ptr);
+    MOTES_TRY(h->work[W_I32].ensure(carve_i32(b, nullptr)));
+    carve_i32(b, h->work[W_I32].ptr);
+    MOTES_TRY(h->work[W_U8].ensure((size_t)F * ndisp + 256));
+    b.gap = h->work[W_U8].as<uint8_t>();
+    MOTES_TRY(h->work[W_PROFILES].ensure((size_t)F * cap * nspat * sizeof(double)));
+    b.profiles = h->work[W_PROFILES].as<double>();
+    if (need_sky) {
+        MOTES_TRY(h->work[W_SORTED].ensure((size_t)F * ndisp * nspat * sizeof(double)));
+        b.sorted = h->work[W_SORTED].as<double>();
+        MOTES_TRY(h->work[W_RANKS].ensure((size_t)F * ndisp * nspat * sizeof(uint16_t)));
+        b.rank_of = h->work[W_RANKS].as<uint16_t>();
+    }
+    return MOTES_OK;
+}
+
+#define MOTES_LAUNCHED(h)               \
+    do {                                \
+        MOTES_CUDA(cudaGetLastError()); \
+        (h)->launches += 1;             \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------ stages
+static int stage_row_median(motes_handle* h, const double* data, size_t frame_stride, int F, int nspat, int ndisp,
+                            double* out) {
+    size_t smem = (size_t)ndisp * 8 + 256 * 4 + 32;
+    if (smem > h->smem_optin) return fail_arg("dispersion axis too long for the shared-memory row median");
+    MOTES_CUDA(cudaFuncSetAttribute(row_median_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    row_median_kernel<<<dim3(nspat, F), 256, smem, h->stream>>>(data, frame_stride, nspat, ndisp, out);
+    MOTES_LAUNCHED(h);
+    return MOTES_OK;
+}
+
+static int stage_fit(motes_handle* h, const FitBatch& fb) {
+    if (fb.nframes <= 0 || fb.bound <= 0) return MOTES_OK;
+    size_t per_warp = fit_scratch_doubles(fb.m) * sizeof(double);
     size_t budget = h->smem_optin > 2048 ? h->smem_optin - 1024 : h->smem_optin;
     int warps = (int)(budget / per_warp);
     if (warps < 1) return fail_arg("nspat too large for the shared-memory fit slab");
@@ -127,31 +134,125 @@ static int launch_fit(motes_handle* h, const double* profiles, int nfit, int m, 
     int ctas_per_sm = (int)(budget / smem);
     if (ctas_per_sm < 1) ctas_per_sm = 1;
     if (ctas_per_sm > 4) ctas_per_sm = 4;
-    int grid = h->sm_count * ctas_per_sm;
-    int needed = (nfit + warps - 1) / warps;
+    long long items = (long long)fb.nframes * fb.bound;
+    long long grid = (long long)h->sm_count * ctas_per_sm;
+    long long needed = (items + warps - 1) / warps;
     if (grid > needed) grid = needed;
     MOTES_TRY(h->counters.ensure(256));
     MOTES_CUDA(cudaMemsetAsync(h->counters.ptr, 0, 256, h->stream));
-    moffat_fit_kernel<<<grid, warps * 32, smem, h->stream>>>(profiles, nfit, m, alpha0, params, cost, nfev,
-                                                             njev, status, h->counters.as<unsigned int>());
-    MOTES_CUDA(cudaGetLastError());
-    h->launches += 1;
+    moffat_fit_kernel<<<(int)grid, warps * 32, smem, h->stream>>>(fb, h->counters.as<unsigned int>());
+    MOTES_LAUNCHED(h);
     return MOTES_OK;
 }
 
-static int launch_extract(motes_handle* h, double* data, const double* errs, int nspat, int ndisp,
-                          const double* lim_lo, const double* lim_hi, const double* bin_params, int nbins,
-                          int wavelength_start, double* spectra, int32_t* lo_idx, int32_t* hi_idx,
-                          uint8_t* crmask) {
-    size_t smem = (size_t)2 * nspat * kExtStride * sizeof(double);
+// median profile -> scale -> fit -> FWHM / binning rows  (core.py:80-100)
+static int stage_median_fit(motes_handle* h, Batch& b, const double* data, size_t frame_stride) {
+    MOTES_TRY(stage_row_median(h, data, frame_stride, b.F, b.nspat, b.ndisp, b.medprof));
+    frame_prep_kernel<<<b.F, 32, 0, h->stream>>>(b.medprof, b.nspat, b.st);
+    MOTES_LAUNCHED(h);
+    FitBatch fb{};
+    fb.profiles = b.medprof; fb.m = b.nspat; fb.nframes = b.F; fb.bound = 1; fb.cap = 1; fb.nbins = nullptr;
+    fb.alpha0 = &b.st->alpha0_first; fb.alpha0_frame_stride = sizeof(FrameState);
+    fb.scale = &b.st->scale; fb.scale_frame_stride = sizeof(FrameState);
+    fb.params = b.fit0_params; fb.status = b.fit0_status;
+    MOTES_TRY(stage_fit(h, fb));
+    frame_post_kernel<<<(b.F + 127) / 128, 128, 0, h->stream>>>(b.F, b.fit0_params, b.fit0_status, b.st);
+    MOTES_LAUNCHED(h);
+    return MOTES_OK;
+}
+
+static int stage_column_stats(motes_handle* h, Batch& b, const double* data, const double* errs, size_t frame_stride) {
+    column_stats_kernel<<<dim3((b.ndisp + 127) / 128, b.F), 128, 0, h->stream>>>(data, errs, frame_stride, b.nspat,
+                                                                                b.ndisp, b.st, b.S, b.V, b.gap);
+    MOTES_LAUNCHED(h);
+    return MOTES_OK;
+}
+
+static int stage_bins(motes_handle* h, Batch& b, const uint8_t* qual, size_t qual_stride, double snr_limit,
+                      double min_cols, int set) {
+    int threads = ((b.nspat + 31) / 32) * 32;
+    if (threads > 1024) threads = 1024;
+    size_t smem = (size_t)b.nspat * sizeof(int);
+    bins_kernel<<<b.F, threads, smem, h->stream>>>(qual, qual_stride, b.S, b.V, b.nspat, b.ndisp, snr_limit, min_cols,
+                                                   b.cap, b.bins_i[set], b.bins_snr[set], b.tmp_i, b.tmp_snr,
+                                                   b.nbins[set]);
+    MOTES_LAUNCHED(h);
+    return MOTES_OK;
+}
+
+static int stage_bin_profiles(motes_handle* h, Batch& b, const double* data, size_t frame_stride, int set) {
+    long long items = (long long)b.cap * b.nspat;
+    int gx = (int)((items + kProfWarps - 1) / kProfWarps);
+    bin_profile_kernel<<<dim3(gx, b.F), kProfWarps * 32, 0, h->stream>>>(data, frame_stride, b.nspat, b.ndisp, b.gap,
+                                                                         b.bins_i[set], b.nbins[set], b.cap, b.profiles);
+    MOTES_LAUNCHED(h);
+    return MOTES_OK;
+}
+
+// bins -> profiles -> fits -> limit table -> per-pixel limits  (sky.py:96-144 / core.py:200-252)
+static int stage_localise(motes_handle* h, Batch& b, const double* data, const double* errs, size_t frame_stride,
+                          const uint8_t* qual, size_t qual_stride, double snr_limit, const motes_params& p, int set) {
+    MOTES_TRY(stage_column_stats(h, b, data, errs, frame_stride));
+    MOTES_TRY(stage_bins(h, b, qual, qual_stride, snr_limit, p.minimum_column_limit, set));
+    MOTES_TRY(stage_bin_profiles(h, b, data, frame_stride, set));
+    FitBatch fb{};
+    fb.profiles = b.profiles; fb.m = b.nspat; fb.nframes = b.F; fb.bound = b.cap; fb.cap = b.cap;
+    fb.nbins = b.nbins[set];
+    fb.alpha0 = &b.st->alpha0_bins; fb.alpha0_frame_stride = sizeof(FrameState);
+    fb.scale = &b.st->scale; fb.scale_frame_stride = sizeof(FrameState);
+    fb.params = b.fit_params; fb.cost = b.fit_cost; fb.nfev = b.fit_nfev; fb.njev = b.fit_njev; fb.status = b.fit_status;
+    MOTES_TRY(stage_fit(h, fb));
+    int items = b.F * b.cap;
+    bin_post_kernel<<<(items + 127) / 128, 128, 0, h->stream>>>(b.F, b.cap, b.cap, b.nbins[set], b.bins_i[set],
+                                                                b.fit_params, b.fit_status, b.st, p.sky_fwhm_multiplier,
+                                                                p.wavelength_start, b.params8[set], b.table);
+    MOTES_LAUNCHED(h);
+    limits_kernel<<<b.F, 256, 0, h->stream>>>(b.table, b.cap, b.nbins[set], b.ndisp, b.limits[set], b.inner);
+    MOTES_LAUNCHED(h);
+    return MOTES_OK;
+}
+
+static size_t sky_prepare_smem(int nspat) {
+    return (size_t)nspat * kTileStride * 8 + (size_t)kTileWarps * nspat * 8 + kTileWarps * 256 * 4 + kTileWarps * 8 +
+           (size_t)kTileWarps * nspat * 2 + 64;
+}
+static size_t sky_boot_smem(int nspat) {
+    return (size_t)kBootstrap * 8 + kMtN * 4 + 34 * 4 + 2 * 4 + (size_t)50 * nspat * 4 + (size_t)nspat * 2 + 64;
+}
+
+static int stage_sky(motes_handle* h, Batch& b, double* data, double* errs, size_t frame_stride, double* limits,
+                     const motes_params& p, uint32_t* rng) {
+    if (p.sky_order != 0) return fail_arg("sky_order > 0 (bootstrap polynomial sky) is not implemented on the device yet");
+    if (b.nspat > 65535) return fail_arg("nspat too large");
+    size_t smem = sky_prepare_smem(b.nspat);
+    if (smem > h->smem_optin || sky_boot_smem(b.nspat) > h->smem_optin)
+        return fail_arg("nspat too large for the shared-memory sky kernels");
+    MOTES_CUDA(cudaFuncSetAttribute(sky_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    sky_prepare_kernel<<<dim3((b.ndisp + kTileCols - 1) / kTileCols, b.F), kTileThreads, smem, h->stream>>>(
+        data, frame_stride, b.nspat, b.ndisp, limits, p.spatial_floor, b.n_sky, b.n_good, b.sky_flag, b.sorted,
+        b.rank_of, b.st);
+    MOTES_LAUNCHED(h);
+    smem = sky_boot_smem(b.nspat);
+    MOTES_CUDA(cudaFuncSetAttribute(sky_bootstrap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    sky_bootstrap_kernel<<<b.F, kBootThreads, smem, h->stream>>>(rng, b.nspat, b.ndisp, b.n_good, b.sky_flag, b.sorted,
+                                                                 b.rank_of, b.sky, b.sky_err, b.st);
+    MOTES_LAUNCHED(h);
+    sky_apply_kernel<<<dim3((b.ndisp + 127) / 128, b.F), 128, 0, h->stream>>>(data, errs, frame_stride, b.nspat, b.ndisp,
+                                                                             b.sky_flag, b.sky, b.sky_err, b.st);
+    MOTES_LAUNCHED(h);
+    return MOTES_OK;
+}
+
+static int stage_extract(motes_handle* h, double* data, const double* errs, size_t frame_stride, int F, int nspat,
+                         int ndisp, const double* limits, const double* bin_params, const int32_t* nbins, int cap,
+                         int wavelength_start, double* spectra, int32_t* lo_idx, int32_t* hi_idx, uint8_t* crmask) {
+    size_t smem = (size_t)2 * nspat * kTileStride * sizeof(double);
     if (smem > h->smem_optin) return fail_arg("nspat too large for the extraction tile");
     MOTES_CUDA(cudaFuncSetAttribute(optimal_extract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int grid = (ndisp + kExtCols - 1) / kExtCols;
-    optimal_extract_kernel<<<grid, kExtThreads, smem, h->stream>>>(data, errs, nspat, ndisp, lim_lo, lim_hi,
-                                                                   bin_params, nbins, wavelength_start, spectra,
-                                                                   lo_idx, hi_idx, crmask);
-    MOTES_CUDA(cudaGetLastError());
-    h->launches += 1;
+    optimal_extract_kernel<<<dim3((ndisp + kTileCols - 1) / kTileCols, F), kTileThreads, smem, h->stream>>>(
+        data, errs, frame_stride, nspat, ndisp, limits, bin_params, nbins, cap, wavelength_start, spectra, lo_idx,
+        hi_idx, crmask);
+    MOTES_LAUNCHED(h);
     return MOTES_OK;
 }
 
@@ -164,8 +265,39 @@ static int upload(motes_handle* h, Scratch& s, const T* host, size_t count, T** 
 }
 template <class T>
 static int download(motes_handle* h, T* host, const T* dev, size_t count) {
-    if (host && count) MOTES_CUDA(cudaMemcpyAsync(host, dev, count * sizeof(T), cudaMemcpyDeviceToHost, h->stream));
+    if (host && dev && count) MOTES_CUDA(cudaMemcpyAsync(host, dev, count * sizeof(T), cudaMemcpyDeviceToHost, h->stream));
     return MOTES_OK;
+}
+template <class T>
+static int copy_dd(motes_handle* h, T* dst, const T* src, size_t count) {
+    if (dst && src && count) MOTES_CUDA(cudaMemcpyAsync(dst, src, count * sizeof(T), cudaMemcpyDeviceToDevice, h->stream));
+    return MOTES_OK;
+}
+
+// The whole path on device-resident frames.  `emit` copies results into the caller's block
+// (device-to-device for the _dev entry point, device-to-host for _host).
+template <class Emit>
+static int run_frames_core(motes_handle* h, Batch& b, double* data, double* errs, const uint8_t* qual,
+                           const motes_params& p, const double* seeing_dev, const double* pixres_dev, uint32_t* rng,
+                           Emit emit) {
+    const size_t frame_stride = (size_t)b.nspat * b.ndisp;
+    // seed FrameState with seeing / pixres
+    MOTES_CUDA(cudaMemsetAsync(b.st, 0, sizeof(FrameState) * (size_t)b.F, h->stream));
+    MOTES_CUDA(cudaMemcpy2DAsync(&b.st->seeing, sizeof(FrameState), seeing_dev, sizeof(double), sizeof(double), b.F,
+                                 cudaMemcpyDeviceToDevice, h->stream));
+    MOTES_CUDA(cudaMemcpy2DAsync(&b.st->pixres, sizeof(FrameState), pixres_dev, sizeof(double), sizeof(double), b.F,
+                                 cudaMemcpyDeviceToDevice, h->stream));
+    MOTES_TRY(stage_median_fit(h, b, data, frame_stride));
+    if (p.subtract_sky) {
+        MOTES_TRY(stage_localise(h, b, data, errs, frame_stride, qual, frame_stride, p.sky_snr_limit, p, 0));
+        MOTES_TRY(stage_sky(h, b, data, errs, frame_stride, b.limits[0], p, rng));
+    } else {
+        MOTES_CUDA(cudaMemsetAsync(b.nbins[0], 0, sizeof(int32_t) * (size_t)b.F, h->stream));
+    }
+    MOTES_TRY(stage_localise(h, b, data, errs, frame_stride, qual, frame_stride, p.extraction_snr_limit, p, 1));
+    MOTES_TRY(stage_extract(h, data, errs, frame_stride, b.F, b.nspat, b.ndisp, b.limits[1], b.params8[1], b.nbins[1],
+                            b.cap, p.wavelength_start, b.spectra, nullptr, nullptr, nullptr));
+    return emit();
 }
 
 }  // namespace motes
@@ -178,7 +310,7 @@ using namespace motes;
 extern "C" {
 
 const char* motes_last_error(void) { return last_error_string().c_str(); }
-const char* motes_version(void) { return "motes_b200 0.1 (sm_100a)"; }
+const char* motes_version(void) { return "motes_b200 0.2 (sm_100a)"; }
 
 int motes_create(int device, motes_handle** out) {
     if (!out) return fail_arg("motes_create: out is NULL");
@@ -233,18 +365,156 @@ int motes_synchronize(motes_handle* h) {
 
 long long motes_launch_count(motes_handle* h) { return h ? h->launches : 0; }
 
-int motes_moffat_fit_batch_dev(motes_handle* h, const double* profiles, int nfit, int nspat,
-                               const double* alpha0, double* params, double* cost, int32_t* nfev,
-                               int32_t* njev, int32_t* status) {
+int motes_bin_capacity(int ndisp, double minimum_column_limit) {
+    if (ndisp < 1) return 0;
+    if (!(minimum_column_limit >= 1.0)) return ndisp;
+    long long cap = (long long)(ndisp / (floor(minimum_column_limit) + 1.0)) + 2;
+    return (int)(cap < ndisp ? cap : ndisp);
+}
+
+int motes_seed_states(const uint32_t* seeds, int nframes, uint32_t* states) {
+    if (!seeds || !states || nframes < 0) return fail_arg("motes_seed_states: bad argument");
+    for (int f = 0; f < nframes; ++f) {
+        mt_seed(states + (size_t)f * 625, seeds[f]);
+        states[(size_t)f * 625 + 624] = kMtN;
+    }
+    return MOTES_OK;
+}
+
+int motes_qual_pack_dev(motes_handle* h, const double* qual, size_t count, uint8_t* out) {
+    if (!h || !qual || !out) return fail_arg("motes_qual_pack_dev: null argument");
+    MOTES_CUDA(cudaSetDevice(h->device));
+    if (count == 0) return MOTES_OK;
+    qual_pack_kernel<<<(unsigned)((count + 255) / 256), 256, 0, h->stream>>>(qual, count, out);
+    MOTES_LAUNCHED(h);
+    return MOTES_OK;
+}
+
+static int check_run_args(motes_handle* h, const void* data, const void* errs, const void* qual, int nframes, int nspat,
+                          int ndisp, int cap, const motes_params* p, const void* seeing, const void* pixres,
+                          const void* rng, const motes_outputs* out) {
+    if (!h || !data || !errs || !qual || !p || !seeing || !pixres || !out) return fail_arg("motes_run_frames: null argument");
+    if (nframes < 1 || nspat < 10 || ndisp < 2) return fail_arg("motes_run_frames: bad size");
+    if (p->subtract_sky && !rng) return fail_arg("motes_run_frames: rng_states required when subtract_sky is set");
+    if (cap < motes_bin_capacity(ndisp, p->minimum_column_limit)) return fail_arg("motes_run_frames: cap below motes_bin_capacity()");
+    return MOTES_OK;
+}
+
+int motes_run_frames_dev(motes_handle* h, double* data, double* errs, const uint8_t* qual, int nframes, int nspat,
+                         int ndisp, int cap, const motes_params* params, const double* seeing, const double* pixres,
+                         uint32_t* rng_states, const motes_outputs* out) {
+    MOTES_TRY(check_run_args(h, data, errs, qual, nframes, nspat, ndisp, cap, params, seeing, pixres, rng_states, out));
+    MOTES_CUDA(cudaSetDevice(h->device));
+    Batch b;
+    MOTES_TRY(make_batch(h, b, nframes, nspat, ndisp, cap, params->subtract_sky != 0));
+    const motes_params p = *params;
+    const motes_outputs o = *out;
+    auto emit = [&]() -> int {
+        const size_t F = b.F, nd = b.ndisp, cp = b.cap;
+        MOTES_TRY(copy_dd(h, o.spectra, b.spectra, F * 4 * nd));
+        MOTES_TRY(copy_dd(h, o.ext_limits, b.limits[1], F * 2 * nd));
+        MOTES_TRY(copy_dd(h, o.ext_params, b.params8[1], F * cp * 8));
+        MOTES_TRY(copy_dd(h, o.ext_bins, b.bins_i[1], F * cp * 2));
+        MOTES_TRY(copy_dd(h, o.ext_bin_snr, b.bins_snr[1], F * cp));
+        MOTES_TRY(copy_dd(h, o.n_ext_bins, b.nbins[1], F));
+        MOTES_TRY(copy_dd(h, o.n_sky_bins, b.nbins[0], F));
+        if (p.subtract_sky) {
+            MOTES_TRY(copy_dd(h, o.sky_limits, b.limits[0], F * 2 * nd));
+            MOTES_TRY(copy_dd(h, o.sky_params, b.params8[0], F * cp * 8));
+            MOTES_TRY(copy_dd(h, o.sky_bins, b.bins_i[0], F * cp * 2));
+            MOTES_TRY(copy_dd(h, o.sky_bin_snr, b.bins_snr[0], F * cp));
+            MOTES_TRY(copy_dd(h, o.sky_model, b.sky, F * nd));
+            MOTES_TRY(copy_dd(h, o.sky_uncertainty, b.sky_err, F * nd));
+            MOTES_TRY(copy_dd(h, o.sky_flag, b.sky_flag, F * nd));
+        }
+        if (o.median_params) MOTES_CUDA(cudaMemcpy2DAsync(o.median_params, 6 * sizeof(double), b.st->median_params, sizeof(FrameState), 6 * sizeof(double), F, cudaMemcpyDeviceToDevice, h->stream));
+        if (o.scale) MOTES_CUDA(cudaMemcpy2DAsync(o.scale, sizeof(double), &b.st->scale, sizeof(FrameState), sizeof(double), F, cudaMemcpyDeviceToDevice, h->stream));
+        if (o.seeing_px) MOTES_CUDA(cudaMemcpy2DAsync(o.seeing_px, sizeof(double), &b.st->seeing_px, sizeof(FrameState), sizeof(double), F, cudaMemcpyDeviceToDevice, h->stream));
+        if (o.frame_status) MOTES_CUDA(cudaMemcpy2DAsync(o.frame_status, sizeof(int32_t), &b.st->status, sizeof(FrameState), sizeof(int32_t), F, cudaMemcpyDeviceToDevice, h->stream));
+        return MOTES_OK;
+    };
+    return run_frames_core(h, b, data, errs, qual, p, seeing, pixres, rng_states, emit);
+}
+
+int motes_run_frames_host(motes_handle* h, double* data, double* errs, const uint8_t* qual, int nframes, int nspat,
+                          int ndisp, int cap, const motes_params* params, const double* seeing, const double* pixres,
+                          uint32_t* rng_states, int copy_back, const motes_outputs* out) {
+    MOTES_TRY(check_run_args(h, data, errs, qual, nframes, nspat, ndisp, cap, params, seeing, pixres, rng_states, out));
+    MOTES_CUDA(cudaSetDevice(h->device));
+    Batch b;
+    MOTES_TRY(make_batch(h, b, nframes, nspat, ndisp, cap, params->subtract_sky != 0));
+    const motes_params p = *params;
+    const motes_outputs o = *out;
+    const size_t npix = (size_t)nframes * nspat * ndisp;
+    double *d_data, *d_errs, *d_seeing, *d_pixres;
+    uint8_t* d_qual;
+    uint32_t* d_rng = nullptr;
+    MOTES_TRY(upload(h, h->stage[0], data, npix, &d_data));
+    MOTES_TRY(upload(h, h->stage[1], errs, npix, &d_errs));
+    MOTES_TRY(upload(h, h->stage[2], qual, npix, &d_qual));
+    MOTES_TRY(upload(h, h->stage[3], seeing, (size_t)nframes, &d_seeing));
+    MOTES_TRY(upload(h, h->stage[4], pixres, (size_t)nframes, &d_pixres));
+    if (rng_states) MOTES_TRY(upload(h, h->stage[5], rng_states, (size_t)nframes * 625, &d_rng));
+    auto emit = [&]() -> int {
+        const size_t F = b.F, nd = b.ndisp, cp = b.cap;
+        MOTES_TRY(download(h, o.spectra, b.spectra, F * 4 * nd));
+        MOTES_TRY(download(h, o.ext_limits, b.limits[1], F * 2 * nd));
+        MOTES_TRY(download(h, o.ext_params, b.params8[1], F * cp * 8));
+        MOTES_TRY(download(h, o.ext_bins, b.bins_i[1], F * cp * 2));
+        MOTES_TRY(download(h, o.ext_bin_snr, b.bins_snr[1], F * cp));
+        MOTES_TRY(download(h, o.n_ext_bins, b.nbins[1], F));
+        MOTES_TRY(download(h, o.n_sky_bins, b.nbins[0], F));
+        if (p.subtract_sky) {
+            MOTES_TRY(download(h, o.sky_limits, b.limits[0], F * 2 * nd));
+            MOTES_TRY(download(h, o.sky_params, b.params8[0], F * cp * 8));
+            MOTES_TRY(download(h, o.sky_bins, b.bins_i[0], F * cp * 2));
+            MOTES_TRY(download(h, o.sky_bin_snr, b.bins_snr[0], F * cp));
+            MOTES_TRY(download(h, o.sky_model, b.sky, F * nd));
+            MOTES_TRY(download(h, o.sky_uncertainty, b.sky_err, F * nd));
+            MOTES_TRY(download(h, o.sky_flag, b.sky_flag, F * nd));
+            MOTES_TRY(download(h, rng_states, d_rng, F * 625));
+        }
+        if (o.median_params) MOTES_CUDA(cudaMemcpy2DAsync(o.median_params, 6 * sizeof(double), b.st->median_params, sizeof(FrameState), 6 * sizeof(double), F, cudaMemcpyDeviceToHost, h->stream));
+        if (o.scale) MOTES_CUDA(cudaMemcpy2DAsync(o.scale, sizeof(double), &b.st->scale, sizeof(FrameState), sizeof(double), F, cudaMemcpyDeviceToHost, h->stream));
+        if (o.seeing_px) MOTES_CUDA(cudaMemcpy2DAsync(o.seeing_px, sizeof(double), &b.st->seeing_px, sizeof(FrameState), sizeof(double), F, cudaMemcpyDeviceToHost, h->stream));
+        if (o.frame_status) MOTES_CUDA(cudaMemcpy2DAsync(o.frame_status, sizeof(int32_t), &b.st->status, sizeof(FrameState), sizeof(int32_t), F, cudaMemcpyDeviceToHost, h->stream));
+        if (copy_back) {
+            MOTES_TRY(download(h, data, d_data, npix));
+            MOTES_TRY(download(h, errs, d_errs, npix));
+        }
+        return MOTES_OK;
+    };
+    MOTES_TRY(run_frames_core(h, b, d_data, d_errs, d_qual, p, d_seeing, d_pixres, d_rng, emit));
+    MOTES_CUDA(cudaStreamSynchronize(h->stream));
+    return MOTES_OK;
+}
+
+// ------------------------------------------------------------------------------------------ stage entry points
+int motes_row_median_host(motes_handle* h, const double* data, int nspat, int ndisp, double* out) {
+    if (!h || !data || !out || nspat < 1 || ndisp < 1) return fail_arg("motes_row_median: bad argument");
+    MOTES_CUDA(cudaSetDevice(h->device));
+    double *d_data, *d_out;
+    MOTES_TRY(upload(h, h->stage[0], data, (size_t)nspat * ndisp, &d_data));
+    MOTES_TRY(upload<double>(h, h->stage[1], nullptr, (size_t)nspat, &d_out));
+    MOTES_TRY(stage_row_median(h, d_data, (size_t)nspat * ndisp, 1, nspat, ndisp, d_out));
+    MOTES_TRY(download(h, out, d_out, (size_t)nspat));
+    MOTES_CUDA(cudaStreamSynchronize(h->stream));
+    return MOTES_OK;
+}
+
+int motes_moffat_fit_batch_dev(motes_handle* h, const double* profiles, int nfit, int nspat, const double* alpha0,
+                               double* params, double* cost, int32_t* nfev, int32_t* njev, int32_t* status) {
     if (!h || !profiles || !alpha0 || !params) return fail_arg("motes_moffat_fit_batch: null argument");
     if (nfit < 0 || nspat < 1) return fail_arg("motes_moffat_fit_batch: bad size");
     MOTES_CUDA(cudaSetDevice(h->device));
-    return launch_fit(h, profiles, nfit, nspat, alpha0, params, cost, nfev, njev, status);
+    FitBatch fb{};
+    fb.profiles = profiles; fb.m = nspat; fb.nframes = 1; fb.bound = nfit; fb.cap = nfit; fb.alpha0 = alpha0;
+    fb.params = params; fb.cost = cost; fb.nfev = nfev; fb.njev = njev; fb.status = status;
+    return stage_fit(h, fb);
 }
 
-int motes_moffat_fit_batch_host(motes_handle* h, const double* profiles, int nfit, int nspat,
-                                const double* alpha0, double* params, double* cost, int32_t* nfev,
-                                int32_t* njev, int32_t* status) {
+int motes_moffat_fit_batch_host(motes_handle* h, const double* profiles, int nfit, int nspat, const double* alpha0,
+                                double* params, double* cost, int32_t* nfev, int32_t* njev, int32_t* status) {
     if (!h || !profiles || !alpha0 || !params) return fail_arg("motes_moffat_fit_batch: null argument");
     if (nfit < 0 || nspat < 1) return fail_arg("motes_moffat_fit_batch: bad size");
     if (nfit == 0) return MOTES_OK;
@@ -256,7 +526,8 @@ int motes_moffat_fit_batch_host(motes_handle* h, const double* profiles, int nfi
     MOTES_TRY(upload<double>(h, h->stage[2], nullptr, (size_t)nfit * kParams, &d_par));
     MOTES_TRY(upload<double>(h, h->stage[3], nullptr, (size_t)nfit, &d_cost));
     MOTES_TRY(upload<int32_t>(h, h->stage[4], nullptr, (size_t)nfit * 3, &d_int));
-    MOTES_TRY(launch_fit(h, d_prof, nfit, nspat, d_a0, d_par, d_cost, d_int, d_int + nfit, d_int + 2 * (size_t)nfit));
+    MOTES_TRY(motes_moffat_fit_batch_dev(h, d_prof, nfit, nspat, d_a0, d_par, d_cost, d_int, d_int + nfit,
+                                         d_int + 2 * (size_t)nfit));
     MOTES_TRY(download(h, params, d_par, (size_t)nfit * kParams));
     MOTES_TRY(download(h, cost, d_cost, (size_t)nfit));
     MOTES_TRY(download(h, nfev, d_int, (size_t)nfit));
@@ -266,28 +537,139 @@ int motes_moffat_fit_batch_host(motes_handle* h, const double* profiles, int nfi
     return MOTES_OK;
 }
 
+int motes_get_bins_host(motes_handle* h, const double* data, const double* errs, const uint8_t* qual, int nspat,
+                        int ndisp, int row_lo, int row_hi, double snr_limit, double minimum_column_limit, int cap,
+                        int32_t* bins, double* snr, int32_t* nbins, uint8_t* gap) {
+    if (!h || !data || !errs || !qual || !bins || !snr || !nbins) return fail_arg("motes_get_bins: null argument");
+    if (nspat < 1 || ndisp < 1) return fail_arg("motes_get_bins: bad size");
+    if (cap < motes_bin_capacity(ndisp, minimum_column_limit)) return fail_arg("motes_get_bins: cap below motes_bin_capacity()");
+    MOTES_CUDA(cudaSetDevice(h->device));
+    const size_t npix = (size_t)nspat * ndisp;
+    Batch b;
+    MOTES_TRY(make_batch(h, b, 1, nspat, ndisp, cap, false));
+    double *d_data, *d_errs;
+    uint8_t* d_qual;
+    MOTES_TRY(upload(h, h->stage[0], data, npix, &d_data));
+    MOTES_TRY(upload(h, h->stage[1], errs, npix, &d_errs));
+    MOTES_TRY(upload(h, h->stage[2], qual, npix, &d_qual));
+    FrameState st{};
+    st.row_lo = row_lo;
+    st.row_hi = row_hi;
+    MOTES_CUDA(cudaMemcpyAsync(b.st, &st, sizeof(st), cudaMemcpyHostToDevice, h->stream));
+    MOTES_TRY(stage_column_stats(h, b, d_data, d_errs, npix));
+    MOTES_TRY(stage_bins(h, b, d_qual, npix, snr_limit, minimum_column_limit, 0));
+    MOTES_TRY(download(h, nbins, b.nbins[0], 1));
+    MOTES_TRY(download(h, bins, b.bins_i[0], (size_t)2 * cap));
+    MOTES_TRY(download(h, snr, b.bins_snr[0], (size_t)cap));
+    MOTES_TRY(download(h, gap, b.gap, (size_t)ndisp));
+    MOTES_CUDA(cudaStreamSynchronize(h->stream));
+    return MOTES_OK;
+}
+
+int motes_bin_profiles_host(motes_handle* h, const double* data, int nspat, int ndisp, const int32_t* bins, int nbins,
+                            double* profiles) {
+    if (!h || !data || !bins || !profiles) return fail_arg("motes_bin_profiles: null argument");
+    if (nspat < 1 || ndisp < 1 || nbins < 1) return fail_arg("motes_bin_profiles: bad size");
+    MOTES_CUDA(cudaSetDevice(h->device));
+    const size_t npix = (size_t)nspat * ndisp;
+    Batch b;
+    MOTES_TRY(make_batch(h, b, 1, nspat, ndisp, nbins, false));
+    double* d_data;
+    MOTES_TRY(upload(h, h->stage[0], data, npix, &d_data));
+    FrameState st{};
+    MOTES_CUDA(cudaMemcpyAsync(b.st, &st, sizeof(st), cudaMemcpyHostToDevice, h->stream));
+    MOTES_TRY(stage_column_stats(h, b, d_data, d_data, npix));   // only the chip-gap flags are used
+    MOTES_CUDA(cudaMemcpyAsync(b.bins_i[0], bins, sizeof(int32_t) * 2 * (size_t)nbins, cudaMemcpyHostToDevice, h->stream));
+    int32_t nb = nbins;
+    MOTES_CUDA(cudaMemcpyAsync(b.nbins[0], &nb, sizeof(nb), cudaMemcpyHostToDevice, h->stream));
+    MOTES_TRY(stage_bin_profiles(h, b, d_data, npix, 0));
+    MOTES_TRY(download(h, profiles, b.profiles, (size_t)nbins * nspat));
+    MOTES_CUDA(cudaStreamSynchronize(h->stream));
+    return MOTES_OK;
+}
+
+int motes_interp_limits_host(motes_handle* h, const double* table, int nbins, int ndisp, double* lim_lo, double* lim_hi) {
+    if (!h || !table || !lim_lo || !lim_hi || nbins < 1 || ndisp < 1) return fail_arg("motes_interp_limits: bad argument");
+    MOTES_CUDA(cudaSetDevice(h->device));
+    Batch b;
+    MOTES_TRY(make_batch(h, b, 1, 16, ndisp, nbins, false));
+    MOTES_CUDA(cudaMemcpyAsync(b.table, table, sizeof(double) * 4 * (size_t)nbins, cudaMemcpyHostToDevice, h->stream));
+    int32_t nb = nbins;
+    MOTES_CUDA(cudaMemcpyAsync(b.nbins[0], &nb, sizeof(nb), cudaMemcpyHostToDevice, h->stream));
+    limits_kernel<<<1, 256, 0, h->stream>>>(b.table, nbins, b.nbins[0], ndisp, b.limits[0], b.inner);
+    MOTES_LAUNCHED(h);
+    MOTES_TRY(download(h, lim_lo, b.limits[0], (size_t)ndisp));
+    MOTES_TRY(download(h, lim_hi, b.limits[0] + ndisp, (size_t)ndisp));
+    MOTES_CUDA(cudaStreamSynchronize(h->stream));
+    return MOTES_OK;
+}
+
+int motes_sky_subtract_host(motes_handle* h, double* data, double* errs, int nspat, int ndisp, double* lim_lo,
+                            double* lim_hi, int spatial_floor, int sky_order, uint32_t* rng_state, double* sky,
+                            double* sky_err, int32_t* flag, int32_t* n_sky, int32_t* n_good) {
+    if (!h || !data || !errs || !lim_lo || !lim_hi || !rng_state) return fail_arg("motes_sky_subtract: null argument");
+    if (nspat < 1 || ndisp < 1) return fail_arg("motes_sky_subtract: bad size");
+    MOTES_CUDA(cudaSetDevice(h->device));
+    const size_t npix = (size_t)nspat * ndisp;
+    Batch b;
+    MOTES_TRY(make_batch(h, b, 1, nspat, ndisp, 1, true));
+    double *d_data, *d_errs;
+    uint32_t* d_rng;
+    MOTES_TRY(upload(h, h->stage[0], data, npix, &d_data));
+    MOTES_TRY(upload(h, h->stage[1], errs, npix, &d_errs));
+    MOTES_TRY(upload(h, h->stage[5], rng_state, (size_t)625, &d_rng));
+    MOTES_CUDA(cudaMemcpyAsync(b.limits[0], lim_lo, sizeof(double) * ndisp, cudaMemcpyHostToDevice, h->stream));
+    MOTES_CUDA(cudaMemcpyAsync(b.limits[0] + ndisp, lim_hi, sizeof(double) * ndisp, cudaMemcpyHostToDevice, h->stream));
+    FrameState st{};
+    MOTES_CUDA(cudaMemcpyAsync(b.st, &st, sizeof(st), cudaMemcpyHostToDevice, h->stream));
+    motes_params p{};
+    p.sky_order = sky_order;
+    p.spatial_floor = spatial_floor;
+    MOTES_TRY(stage_sky(h, b, d_data, d_errs, npix, b.limits[0], p, d_rng));
+    MOTES_CUDA(cudaMemcpyAsync(&st, b.st, sizeof(st), cudaMemcpyDeviceToHost, h->stream));
+    MOTES_TRY(download(h, lim_lo, b.limits[0], (size_t)ndisp));
+    MOTES_TRY(download(h, lim_hi, b.limits[0] + ndisp, (size_t)ndisp));
+    MOTES_TRY(download(h, n_sky, b.n_sky, (size_t)ndisp));
+    MOTES_TRY(download(h, n_good, b.n_good, (size_t)ndisp));
+    MOTES_TRY(download(h, flag, b.sky_flag, (size_t)ndisp));
+    MOTES_CUDA(cudaStreamSynchronize(h->stream));
+    if (st.status == MOTES_E_NOSKY) {
+        last_error_string() = "No pixels contained inside sky region.";
+        return MOTES_E_NOSKY;
+    }
+    MOTES_TRY(download(h, data, d_data, npix));
+    MOTES_TRY(download(h, errs, d_errs, npix));
+    MOTES_TRY(download(h, sky, b.sky, (size_t)ndisp));
+    MOTES_TRY(download(h, sky_err, b.sky_err, (size_t)ndisp));
+    MOTES_TRY(download(h, rng_state, d_rng, (size_t)625));
+    MOTES_CUDA(cudaStreamSynchronize(h->stream));
+    return MOTES_OK;
+}
+
 int motes_optimal_extract_host(motes_handle* h, double* data, const double* errs, int nspat, int ndisp,
-                               const double* lim_lo, const double* lim_hi, const double* bin_params,
-                               int nbins, int wavelength_start, double* spectra, int32_t* lo_idx,
-                               int32_t* hi_idx, uint8_t* crmask) {
+                               const double* lim_lo, const double* lim_hi, const double* bin_params, int nbins,
+                               int wavelength_start, double* spectra, int32_t* lo_idx, int32_t* hi_idx, uint8_t* crmask) {
     if (!h || !data || !errs || !lim_lo || !lim_hi || !bin_params || !spectra)
         return fail_arg("motes_optimal_extract: null argument");
     if (nspat < 1 || ndisp < 1 || nbins < 0) return fail_arg("motes_optimal_extract: bad size");
     MOTES_CUDA(cudaSetDevice(h->device));
     size_t npix = (size_t)nspat * ndisp;
-    double *d_data, *d_errs, *d_lo, *d_hi, *d_bins, *d_spec;
+    double *d_data, *d_errs, *d_lim, *d_bins, *d_spec;
     int32_t* d_idx;
     uint8_t* d_mask;
     MOTES_TRY(upload(h, h->stage[0], data, npix, &d_data));
     MOTES_TRY(upload(h, h->stage[1], errs, npix, &d_errs));
-    MOTES_TRY(upload(h, h->stage[2], lim_lo, (size_t)ndisp, &d_lo));
-    MOTES_TRY(upload(h, h->stage[3], lim_hi, (size_t)ndisp, &d_hi));
+    MOTES_TRY(upload<double>(h, h->stage[2], nullptr, (size_t)2 * ndisp, &d_lim));
+    MOTES_CUDA(cudaMemcpyAsync(d_lim, lim_lo, sizeof(double) * ndisp, cudaMemcpyHostToDevice, h->stream));
+    MOTES_CUDA(cudaMemcpyAsync(d_lim + ndisp, lim_hi, sizeof(double) * ndisp, cudaMemcpyHostToDevice, h->stream));
     MOTES_TRY(upload(h, h->stage[4], bin_params, (size_t)nbins * 8, &d_bins));
     MOTES_TRY(upload<double>(h, h->stage[5], nullptr, (size_t)4 * ndisp, &d_spec));
-    MOTES_TRY(upload<int32_t>(h, h->stage[6], nullptr, (size_t)2 * ndisp, &d_idx));
+    MOTES_TRY(upload<int32_t>(h, h->stage[6], nullptr, (size_t)2 * ndisp + 1, &d_idx));
     MOTES_TRY(upload<uint8_t>(h, h->stage[7], nullptr, crmask ? npix : 0, &d_mask));
-    MOTES_TRY(launch_extract(h, d_data, d_errs, nspat, ndisp, d_lo, d_hi, d_bins, nbins, wavelength_start, d_spec,
-                             d_idx, d_idx + ndisp, crmask ? d_mask : nullptr));
+    int32_t nb = nbins;
+    MOTES_CUDA(cudaMemcpyAsync(d_idx + 2 * (size_t)ndisp, &nb, sizeof(nb), cudaMemcpyHostToDevice, h->stream));
+    MOTES_TRY(stage_extract(h, d_data, d_errs, npix, 1, nspat, ndisp, d_lim, d_bins, d_idx + 2 * (size_t)ndisp, nbins,
+                            wavelength_start, d_spec, d_idx, d_idx + ndisp, crmask ? d_mask : nullptr));
     MOTES_TRY(download(h, data, d_data, npix));
     MOTES_TRY(download(h, spectra, d_spec, (size_t)4 * ndisp));
     MOTES_TRY(download(h, lo_idx, d_idx, (size_t)ndisp));

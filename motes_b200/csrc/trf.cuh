@@ -422,9 +422,11 @@ MOTES_HD void fd_jacobian(const Ctx& ctx, int m, const double* y, const double* 
     ctx.sync();
 }
 
-// The fit.  `profile` may live anywhere readable (global or shared); alpha0 = seeing / pixel_resolution.
+// The fit.  `profile` may live anywhere readable (global or shared); the fitted data are
+// profile[i] * scale (tracing.py:441,513: the caller's data_scaling_factor; pass 1.0 for none);
+// alpha0 = seeing / pixel_resolution.
 template <class Ctx>
-MOTES_HD void trf_fit_moffat(const Ctx& ctx, int m, const double* profile, double alpha0,
+MOTES_HD void trf_fit_moffat(const Ctx& ctx, int m, const double* profile, double scale, double alpha0,
                              const FitScratch& ws, FitResult* res) {
     using namespace trf_detail;
     constexpr int n = kParams;
@@ -436,7 +438,7 @@ MOTES_HD void trf_fit_moffat(const Ctx& ctx, int m, const double* profile, doubl
     double top1 = -INFINITY, top2 = -INFINITY, top3 = -INFINITY;
     int peak = 0, n_nan = 0;
     bool peak_nan = false;
-    for (int i = ctx.lane; i < m; i += Ctx::kLanes) y[i] = profile[i];
+    for (int i = ctx.lane; i < m; i += Ctx::kLanes) y[i] = profile[i] * scale;
     ctx.sync();
     for (int i = 0; i < m; ++i) {
         double val = y[i];

@@ -17,7 +17,7 @@ extern "C" int hostsim_fit_batch(const double* profiles, int nfit, int m, const 
     motes::SeqCtx ctx;
     for (int f = 0; f < nfit; ++f) {
         motes::FitResult r;
-        motes::trf_fit_moffat(ctx, m, profiles + (size_t)f * m, alpha0[f], ws, &r);
+        motes::trf_fit_moffat(ctx, m, profiles + (size_t)f * m, 1.0, alpha0[f], ws, &r);
         std::memcpy(params + 6 * (size_t)f, r.x, sizeof(r.x));
         cost[f] = r.cost;
         nfev[f] = r.nfev;
@@ -26,3 +26,77 @@ extern "C" int hostsim_fit_batch(const double* profiles, int nfit, int m, const 
     }
     return 0;
 }
+
+#include "../../motes_b200/csrc/bins.cuh"
+#include "../../motes_b200/csrc/limits.cuh"
+#include "../../motes_b200/csrc/extract.cuh"
+
+extern "C" int hostsim_snr_bins(const double* data, const double* errs, const uint8_t* qual, int nspat, int ndisp,
+                                int row_lo, int row_hi, double snr_limit, double min_cols, int32_t* bins_i,
+                                double* bins_snr, uint8_t* gap) {
+    std::vector<double> S(ndisp), V(ndisp), tmp_snr(ndisp);
+    std::vector<int32_t> tmp_i(2 * (size_t)ndisp);
+    std::vector<int> counts(nspat);
+    for (int c = 0; c < ndisp; ++c) {
+        motes::ColumnStats st = motes::column_stats(data, errs, nspat, ndisp, c, row_lo, row_hi);
+        S[c] = st.sum_data;
+        V[c] = st.sum_var;
+        gap[c] = st.gap;
+    }
+    motes::SeqScope sc;
+    return motes::snr_bins_scan(sc, qual, S.data(), V.data(), nspat, ndisp, snr_limit, min_cols, counts.data(),
+                                bins_i, bins_snr, tmp_i.data(), tmp_snr.data());
+}
+
+extern "C" int hostsim_interp_limits(const double* table, int nb, int ndisp, double* out_lo, double* out_hi) {
+    std::vector<double> inner(2 * ((size_t)ndisp + 2));
+    std::vector<unsigned long long> keys(256);
+    uint32_t hist[256];
+    unsigned long long cell;
+    int icell;
+    motes::SeqScope sc;
+    motes::interpolate_limits(sc, table, nb, nb, ndisp, out_lo, out_hi, inner.data(), keys.data(), hist, &cell, &icell);
+    return 0;
+}
+
+extern "C" double hostsim_median(const double* v, int n) {
+    std::vector<unsigned long long> keys(n);
+    for (int i = 0; i < n; ++i) keys[i] = motes::key_of(v[i]);
+    uint32_t hist[256];
+    unsigned long long cell;
+    motes::SeqScope sc;
+    return motes::median_of_keys(sc, keys.data(), n, hist, &cell);
+}
+
+#include "../../motes_b200/csrc/sky.cuh"
+
+// Order-0 sky subtraction of one frame with numpy's RandomState (624-word key + position) as input/output.
+extern "C" int hostsim_sky_median(double* data, double* errs, int nspat, int ndisp, double* lim_lo, double* lim_hi,
+                                  int spatial_floor, uint32_t* mt, int* pos, double* sky, double* sky_err,
+                                  int32_t* n_sky, int32_t* n_good, int32_t* flag) {
+    motes::SeqScope sc;
+    std::vector<double> sorted((size_t)ndisp * nspat), column(nspat);
+    std::vector<uint16_t> rank_of((size_t)ndisp * nspat), good_row((size_t)nspat);
+    std::vector<unsigned long long> keys(nspat);
+    uint32_t hist[256];
+    unsigned long long cell;
+    int icell;
+    for (int c = 0; c < ndisp; ++c) {
+        for (int r = 0; r < nspat; ++r) column[r] = data[(size_t)r * ndisp + c];
+        motes::sky_prepare_column(sc, column.data(), 1, nspat, lim_lo + c, lim_hi + c, spatial_floor, n_sky + c,
+                                  n_good + c, flag + c, sorted.data() + (size_t)c * nspat,
+                                  rank_of.data() + (size_t)c * nspat, good_row.data(), keys.data(), hist, &cell, &icell);
+        if (flag[c] == motes::kSkyNoPixels) return -4;
+    }
+    std::vector<uint32_t> bhist(50 * (size_t)nspat);
+    std::vector<uint16_t> ranks(nspat);
+    double meds[100];
+    uint32_t scan[33];
+    int ctl[2];
+    motes::sky_bootstrap_frame(sc, mt, pos, ndisp, n_good, flag, sorted.data(), rank_of.data(), (size_t)nspat, sky,
+                               sky_err, bhist.data(), ranks.data(), meds, scan, ctl);
+    for (int c = 0; c < ndisp; ++c) motes::sky_apply_column(data, errs, nspat, ndisp, c, flag[c], sky[c], sky_err[c]);
+    return 0;
+}
+
+extern "C" void hostsim_mt_seed(uint32_t* mt, uint32_t seed) { motes::mt_seed(mt, seed); }
