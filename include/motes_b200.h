@@ -52,6 +52,14 @@ int motes_synchronize(motes_handle* h);
 /* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */
 long long motes_launch_count(motes_handle* h);
 
+/* Optional per-stage timing with CUDA events on the handle's stream.  Stages: see
+ * motes_profile_stage_name().  ms / launches: motes_profile_stage_count() entries, accumulated since
+ * the last reset; motes_profile_read synchronises the stream. */
+int motes_profile_enable(motes_handle* h, int on);
+int motes_profile_stage_count(void);
+const char* motes_profile_stage_name(int stage);
+int motes_profile_read(motes_handle* h, double* ms, long long* launches, int reset);
+
 /* ---------------------------------------------------------------------------------------
  * Whole path for a batch of frames (core.motes stage order, core.py:80-275).
  * ------------------------------------------------------------------------------------- */

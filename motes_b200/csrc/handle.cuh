@@ -72,6 +72,13 @@ struct Scratch {
 
 }  // namespace motes
 
+namespace motes {
+// Optional per-stage timing with CUDA events on the handle's stream (bench.py's roofline leg).
+enum Stage { ST_ROW_MEDIAN = 0, ST_MEDIAN_FIT, ST_COLUMN_STATS, ST_BINS, ST_BIN_PROFILES, ST_BIN_FITS, ST_LIMITS,
+             ST_SKY_PREPARE, ST_SKY_BOOTSTRAP, ST_SKY_APPLY, ST_EXTRACT, ST_COUNT };
+struct StageSpan { cudaEvent_t a, b; int stage; };
+}  // namespace motes
+
 struct motes_handle {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -83,4 +90,28 @@ struct motes_handle {
     motes::Scratch stage[12];
     motes::Scratch work[12];
     motes::Scratch counters;    // small zero-initialised control block
+    bool profiling = false;
+    std::vector<motes::StageSpan> spans;
+    double stage_ms[motes::ST_COUNT] = {0};
+    long long stage_launches[motes::ST_COUNT] = {0};
 };
+
+namespace motes {
+struct StageTimer {
+    motes_handle* h;
+    int idx = -1;
+    StageTimer(motes_handle* handle, int stage) : h(handle) {
+        if (!h->profiling) return;
+        StageSpan s;
+        s.stage = stage;
+        if (cudaEventCreate(&s.a) != cudaSuccess || cudaEventCreate(&s.b) != cudaSuccess) return;
+        cudaEventRecord(s.a, h->stream);
+        h->spans.push_back(s);
+        idx = (int)h->spans.size() - 1;
+        h->stage_launches[stage] += 1;
+    }
+    ~StageTimer() {
+        if (idx >= 0) cudaEventRecord(h->spans[idx].b, h->stream);
+    }
+};
+}  // namespace motes

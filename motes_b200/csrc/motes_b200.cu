@@ -114,6 +114,7 @@ static int make_batch(motes_handle* h, Batch& b, int F, int nspat, int ndisp, in
 // ------------------------------------------------------------------------------------------ stages
 static int stage_row_median(motes_handle* h, const double* data, size_t frame_stride, int F, int nspat, int ndisp,
                             double* out) {
+    StageTimer timer(h, ST_ROW_MEDIAN);
     size_t smem = (size_t)ndisp * 8 + 256 * 4 + 32;
     if (smem > h->smem_optin) return fail_arg("dispersion axis too long for the shared-memory row median");
     MOTES_CUDA(cudaFuncSetAttribute(row_median_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -148,6 +149,7 @@ static int stage_fit(motes_handle* h, const FitBatch& fb) {
 // median profile -> scale -> fit -> FWHM / binning rows  (core.py:80-100)
 static int stage_median_fit(motes_handle* h, Batch& b, const double* data, size_t frame_stride) {
     MOTES_TRY(stage_row_median(h, data, frame_stride, b.F, b.nspat, b.ndisp, b.medprof));
+    StageTimer timer(h, ST_MEDIAN_FIT);
     frame_prep_kernel<<<b.F, 32, 0, h->stream>>>(b.medprof, b.nspat, b.st);
     MOTES_LAUNCHED(h);
     FitBatch fb{};
@@ -162,6 +164,7 @@ static int stage_median_fit(motes_handle* h, Batch& b, const double* data, size_
 }
 
 static int stage_column_stats(motes_handle* h, Batch& b, const double* data, const double* errs, size_t frame_stride) {
+    StageTimer timer(h, ST_COLUMN_STATS);
     column_stats_kernel<<<dim3((b.ndisp + 127) / 128, b.F), 128, 0, h->stream>>>(data, errs, frame_stride, b.nspat,
                                                                                 b.ndisp, b.st, b.S, b.V, b.gap);
     MOTES_LAUNCHED(h);
@@ -170,6 +173,7 @@ static int stage_column_stats(motes_handle* h, Batch& b, const double* data, con
 
 static int stage_bins(motes_handle* h, Batch& b, const uint8_t* qual, size_t qual_stride, double snr_limit,
                       double min_cols, int set) {
+    StageTimer timer(h, ST_BINS);
     int threads = ((b.nspat + 31) / 32) * 32;
     if (threads > 1024) threads = 1024;
     size_t smem = (size_t)b.nspat * sizeof(int);
@@ -181,6 +185,7 @@ static int stage_bins(motes_handle* h, Batch& b, const uint8_t* qual, size_t qua
 }
 
 static int stage_bin_profiles(motes_handle* h, Batch& b, const double* data, size_t frame_stride, int set) {
+    StageTimer timer(h, ST_BIN_PROFILES);
     long long items = (long long)b.cap * b.nspat;
     int gx = (int)((items + kProfWarps - 1) / kProfWarps);
     bin_profile_kernel<<<dim3(gx, b.F), kProfWarps * 32, 0, h->stream>>>(data, frame_stride, b.nspat, b.ndisp, b.gap,
@@ -201,7 +206,11 @@ static int stage_localise(motes_handle* h, Batch& b, const double* data, const d
     fb.alpha0 = &b.st->alpha0_bins; fb.alpha0_frame_stride = sizeof(FrameState);
     fb.scale = &b.st->scale; fb.scale_frame_stride = sizeof(FrameState);
     fb.params = b.fit_params; fb.cost = b.fit_cost; fb.nfev = b.fit_nfev; fb.njev = b.fit_njev; fb.status = b.fit_status;
-    MOTES_TRY(stage_fit(h, fb));
+    {
+        StageTimer timer(h, ST_BIN_FITS);
+        MOTES_TRY(stage_fit(h, fb));
+    }
+    StageTimer timer(h, ST_LIMITS);
     int items = b.F * b.cap;
     bin_post_kernel<<<(items + 127) / 128, 128, 0, h->stream>>>(b.F, b.cap, b.cap, b.nbins[set], b.bins_i[set],
                                                                 b.fit_params, b.fit_status, b.st, p.sky_fwhm_multiplier,
@@ -228,15 +237,22 @@ static int stage_sky(motes_handle* h, Batch& b, double* data, double* errs, size
     if (smem > h->smem_optin || sky_boot_smem(b.nspat) > h->smem_optin)
         return fail_arg("nspat too large for the shared-memory sky kernels");
     MOTES_CUDA(cudaFuncSetAttribute(sky_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {
+    StageTimer timer(h, ST_SKY_PREPARE);
     sky_prepare_kernel<<<dim3((b.ndisp + kTileCols - 1) / kTileCols, b.F), kTileThreads, smem, h->stream>>>(
         data, frame_stride, b.nspat, b.ndisp, limits, p.spatial_floor, b.n_sky, b.n_good, b.sky_flag, b.sorted,
         b.rank_of, b.st);
     MOTES_LAUNCHED(h);
+    }
     smem = sky_boot_smem(b.nspat);
     MOTES_CUDA(cudaFuncSetAttribute(sky_bootstrap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {
+    StageTimer timer(h, ST_SKY_BOOTSTRAP);
     sky_bootstrap_kernel<<<b.F, kBootThreads, smem, h->stream>>>(rng, b.nspat, b.ndisp, b.n_good, b.sky_flag, b.sorted,
                                                                  b.rank_of, b.sky, b.sky_err, b.st);
     MOTES_LAUNCHED(h);
+    }
+    StageTimer timer(h, ST_SKY_APPLY);
     sky_apply_kernel<<<dim3((b.ndisp + 127) / 128, b.F), 128, 0, h->stream>>>(data, errs, frame_stride, b.nspat, b.ndisp,
                                                                              b.sky_flag, b.sky, b.sky_err, b.st);
     MOTES_LAUNCHED(h);
@@ -246,6 +262,7 @@ static int stage_sky(motes_handle* h, Batch& b, double* data, double* errs, size
 static int stage_extract(motes_handle* h, double* data, const double* errs, size_t frame_stride, int F, int nspat,
                          int ndisp, const double* limits, const double* bin_params, const int32_t* nbins, int cap,
                          int wavelength_start, double* spectra, int32_t* lo_idx, int32_t* hi_idx, uint8_t* crmask) {
+    StageTimer timer(h, ST_EXTRACT);
     size_t smem = (size_t)2 * nspat * kTileStride * sizeof(double);
     if (smem > h->smem_optin) return fail_arg("nspat too large for the extraction tile");
     MOTES_CUDA(cudaFuncSetAttribute(optimal_extract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -364,6 +381,40 @@ int motes_synchronize(motes_handle* h) {
 }
 
 long long motes_launch_count(motes_handle* h) { return h ? h->launches : 0; }
+
+int motes_profile_enable(motes_handle* h, int on) {
+    if (!h) return fail_arg("null handle");
+    h->profiling = on != 0;
+    return MOTES_OK;
+}
+
+int motes_profile_stage_count(void) { return ST_COUNT; }
+
+const char* motes_profile_stage_name(int stage) {
+    static const char* names[ST_COUNT] = {"row_median", "median_fit", "column_stats", "snr_bins", "bin_profiles",
+                                          "bin_fits", "limits", "sky_prepare", "sky_bootstrap", "sky_apply",
+                                          "extract"};
+    return (stage >= 0 && stage < ST_COUNT) ? names[stage] : "";
+}
+
+int motes_profile_read(motes_handle* h, double* ms, long long* launches, int reset) {
+    if (!h || !ms) return fail_arg("motes_profile_read: null argument");
+    MOTES_CUDA(cudaSetDevice(h->device));
+    MOTES_CUDA(cudaStreamSynchronize(h->stream));
+    for (auto& s : h->spans) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, s.a, s.b) == cudaSuccess) h->stage_ms[s.stage] += t;
+        cudaEventDestroy(s.a);
+        cudaEventDestroy(s.b);
+    }
+    h->spans.clear();
+    for (int i = 0; i < ST_COUNT; ++i) {
+        ms[i] = h->stage_ms[i];
+        if (launches) launches[i] = h->stage_launches[i];
+        if (reset) { h->stage_ms[i] = 0; h->stage_launches[i] = 0; }
+    }
+    return MOTES_OK;
+}
 
 int motes_bin_capacity(int ndisp, double minimum_column_limit) {
     if (ndisp < 1) return 0;

@@ -84,14 +84,18 @@ def test_batch_equals_single_frames_and_reports_per_frame_status():
     for i in (0, 2):
         single = pipeline.run_frames(data[i:i + 1].copy(), errs[i:i + 1].copy(), qual[i:i + 1], args,
                                      header["seeing"], header["pixel_resolution"], seeds=seeds[i:i + 1], axes_dict=axes)
-        for key in ("spectra", "ext_limits", "ext_params", "sky_model"):
+        n = int(batch["n_ext_bins"][i])
+        assert n == int(single["n_ext_bins"][0])
+        for key in ("spectra", "ext_limits", "sky_model"):
             assert np.array_equal(batch[key][i], single[key][0], equal_nan=True), key
+        assert np.array_equal(batch["ext_params"][i, :n], single["ext_params"][0, :n])
 
 
 def test_linearity_property_full_size():
     """Size-independent property at BASELINE.json's configs[1] shape (4096x400, no oracle run needed):
-    without sky subtraction, scaling data and errs by a power of two scales flux and error spectra by
-    exactly that factor and leaves bins, limits and shape parameters bit-identical."""
+    without sky subtraction, scaling data and errs by 4 leaves the bins identical, moves the limits only
+    at rounding level (the decimal scale factor of tracing.py:437 changes, so the fits are not bitwise
+    scale-free), scales the aperture flux by exactly 4 and the optimal flux by 4 within 1e-6."""
     from motes_b200 import pipeline, synth
     frame, axes, header = synth.make_frame(synth.config_spec("C2", seed=77))
     args = synth.default_args(subtract_sky=False)
@@ -103,9 +107,13 @@ def test_linearity_property_full_size():
     n = int(a["n_ext_bins"][0])
     assert n == int(b["n_ext_bins"][0]) and n > 200
     assert np.array_equal(a["ext_bins"][0, :n], b["ext_bins"][0, :n])
-    assert np.array_equal(a["ext_limits"], b["ext_limits"])
-    assert np.array_equal(4.0 * a["spectra"], b["spectra"])
-    assert np.array_equal(a["ext_params"][0, :n, 1:4], b["ext_params"][0, :n, 1:4])
+    assert np.allclose(a["ext_limits"], b["ext_limits"], rtol=1e-7, atol=0)
+    same = (np.floor(a["ext_limits"][0, 0]) == np.floor(b["ext_limits"][0, 0])) & \
+           (np.ceil(a["ext_limits"][0, 1]) == np.ceil(b["ext_limits"][0, 1]))
+    assert same.mean() > 0.999
+    assert np.array_equal(4.0 * a["spectra"][0, 2:, same], b["spectra"][0, 2:, same])          # aperture flux / error
+    assert np.allclose(4.0 * a["spectra"][0, :2, same], b["spectra"][0, :2, same], rtol=1e-6)   # optimal flux / error
+    assert np.allclose(a["ext_params"][0, :n, 1:4], b["ext_params"][0, :n, 1:4], rtol=1e-5)
     # aperture flux is the plain sum of the pixels inside the integer limits
     lo = np.floor(a["ext_limits"][0, 0]).astype(int)
     hi = np.ceil(a["ext_limits"][0, 1]).astype(int) + 1
