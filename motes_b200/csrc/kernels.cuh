@@ -138,12 +138,16 @@ bins_kernel(const uint8_t* __restrict__ qual, size_t qual_stride, const double* 
 }
 
 // a6 (first half): median spatial profile of every bin, leaving out chip-gap columns
-// (tracing.py:505-507).  One warp per (frame, bin, row); keys are read straight from the frame.
+// (tracing.py:505-507).  One warp per (frame, bin, row).  Bins of up to kProfStage columns are
+// staged in shared memory and the median is found by rank counting (w^2/32 compares per lane:
+// 8 for the usual 16-column bins); wider bins fall back to radix selection straight from the frame.
 constexpr int kProfWarps = 8;
+constexpr int kProfStage = 512;
 __global__ void __launch_bounds__(kProfWarps * 32)
 bin_profile_kernel(const double* __restrict__ data, size_t frame_stride, int nspat, int ndisp,
                    const uint8_t* __restrict__ gap, const int32_t* __restrict__ bins_i, const int32_t* __restrict__ nbins,
                    int cap, double* __restrict__ profiles /* [F][cap][nspat] */) {
+    __shared__ unsigned long long staged[kProfWarps][kProfStage];
     __shared__ uint32_t hist_all[kProfWarps][256];
     __shared__ unsigned long long cells[kProfWarps];
     const int warp = threadIdx.x >> 5;
@@ -160,10 +164,39 @@ bin_profile_kernel(const double* __restrict__ data, size_t frame_stride, int nsp
         __device__ unsigned long long operator()(int i) const { return g[i] ? kKeyExcluded : key_or_excluded(p[i]); }
     };
     BinKeys keys{data + (size_t)f * frame_stride + (size_t)row * ndisp + first, gap + (size_t)f * ndisp + first};
-    int valid = 0;
-    for (int i = sc.tid; i < w; i += 32) valid += (keys(i) != kKeyExcluded);
-    int n_valid = sc.isum(valid, nullptr);
-    double med = median_of(sc, keys, w, n_valid, hist_all[warp], &cells[warp]);
+    double med;
+    if (w <= kProfStage) {
+        unsigned long long* sk = staged[warp];
+        int valid = 0;
+        for (int i = sc.tid; i < w; i += 32) {
+            unsigned long long k = keys(i);
+            sk[i] = k;
+            valid += (k != kKeyExcluded);
+        }
+        const int n = sc.isum(valid, nullptr);
+        __syncwarp();
+        const int k1 = (n - 1) / 2, k2 = n / 2;
+        unsigned long long a1 = kKeyExcluded, a2 = kKeyExcluded;
+        for (int e = sc.tid; e < w; e += 32) {
+            const unsigned long long k = sk[e];
+            if (k == kKeyExcluded) continue;
+            int rank = 0;
+            for (int j = 0; j < w; ++j) {
+                const unsigned long long o = sk[j];
+                rank += (o < k) || (o == k && j < e);
+            }
+            if (rank == k1) a1 = k;
+            if (rank == k2) a2 = k;
+        }
+        a1 = sc.umin(a1, nullptr);
+        a2 = sc.umin(a2, nullptr);
+        med = (n <= 0) ? NAN : (k1 == k2 ? value_of(a1) : (value_of(a1) + value_of(a2)) * 0.5);
+    } else {
+        int valid = 0;
+        for (int i = sc.tid; i < w; i += 32) valid += (keys(i) != kKeyExcluded);
+        int n_valid = sc.isum(valid, nullptr);
+        med = median_of(sc, keys, w, n_valid, hist_all[warp], &cells[warp]);
+    }
     if (sc.tid == 0) profiles[((size_t)f * cap + b) * nspat + row] = med;
 }
 
@@ -196,13 +229,7 @@ moffat_fit_kernel(FitBatch fb, unsigned int* work_counter) {
     WarpCtx ctx{(int)(threadIdx.x & 31)};
     const int m = fb.m;
     const size_t per_warp = fit_scratch_doubles(m);
-    double* slab = fit_smem + per_warp * warp;
-    FitScratch ws;
-    ws.y = slab;
-    ws.unit = ws.y + m;
-    ws.a = ws.unit + m;
-    ws.w = ws.a + 7 * (size_t)m;
-    ws.v = ws.w + 36;
+    FitScratch ws = carve_fit_scratch(fit_smem + per_warp * warp, m);
     const unsigned int total = (unsigned int)fb.nframes * (unsigned int)fb.bound;
     while (true) {
         unsigned int item = 0;
@@ -332,7 +359,7 @@ sky_prepare_kernel(const double* __restrict__ data, size_t frame_stride, int nsp
 }
 
 // One CTA per frame walks the columns in order and consumes the frame's MT19937 stream.
-constexpr int kBootThreads = 640;     // >= 624: one pass of the CTA covers a whole block of outputs
+constexpr int kBootThreads = 256;     // >= 227: one thread per word of a generator sweep
 
 __global__ void __launch_bounds__(kBootThreads)
 sky_bootstrap_kernel(uint32_t* __restrict__ rng /* [F][625]: 624 state words + position */, int nspat, int ndisp,
@@ -340,29 +367,20 @@ sky_bootstrap_kernel(uint32_t* __restrict__ rng /* [F][625]: 624 state words + p
                      const double* __restrict__ sorted, const uint16_t* __restrict__ rank_of,
                      double* __restrict__ sky, double* __restrict__ sky_err, const FrameState* __restrict__ st) {
     extern __shared__ __align__(16) unsigned char sb_smem[];
-    double* meds = reinterpret_cast<double*>(sb_smem);
-    uint32_t* mt = reinterpret_cast<uint32_t*>(meds + kBootstrap);
-    uint32_t* scan = mt + kMtN;
-    int* ctl = reinterpret_cast<int*>(scan + 34);
-    uint32_t* hist = reinterpret_cast<uint32_t*>(ctl + 2);
-    uint16_t* ranks = reinterpret_cast<uint16_t*>(hist + (size_t)50 * nspat);
+    BootShared sh;
+    sh.meds = reinterpret_cast<double*>(sb_smem);
+    sh.sq = sh.meds + kBootstrap;
+    sh.ring = reinterpret_cast<uint32_t*>(sh.sq + kBootstrap);
+    sh.counts = sh.ring + kRing;
+    sh.ctl = reinterpret_cast<int*>(sh.counts + 64);
+    sh.hist = reinterpret_cast<uint32_t*>(sh.ctl + 4);
+    sh.ranks = reinterpret_cast<uint16_t*>(sh.hist + (size_t)kBootstrap * boot_row_words(nspat));
     BlockScope sc{(int)threadIdx.x};
     const int f = blockIdx.x;
-    uint32_t* state = rng + (size_t)f * 625;
-    for (int i = threadIdx.x; i < kMtN; i += blockDim.x) mt[i] = state[i];
-    if (threadIdx.x == 0) ctl[1] = (int)state[624];
-    __syncthreads();
-    int pos = ctl[1];
-    __syncthreads();
-    if (st[f].status == 0) {
-        const size_t base = (size_t)f * ndisp;
-        sky_bootstrap_frame(sc, mt, &pos, ndisp, n_good + base, flag + base, sorted + base * nspat,
-                            rank_of + base * nspat, (size_t)nspat, sky + base, sky_err + base, hist, ranks, meds,
-                            scan, ctl);
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < kMtN; i += blockDim.x) state[i] = mt[i];
-    if (threadIdx.x == 0) state[624] = (uint32_t)pos;
+    if (st[f].status != 0) return;
+    const size_t base = (size_t)f * ndisp;
+    sky_bootstrap_frame(sc, rng + (size_t)f * 625, ndisp, n_good + base, flag + base, sorted + base * nspat,
+                        rank_of + base * nspat, (size_t)nspat, sky + base, sky_err + base, sh);
 }
 
 __global__ void __launch_bounds__(128)

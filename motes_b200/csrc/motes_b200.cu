@@ -226,7 +226,8 @@ static size_t sky_prepare_smem(int nspat) {
            (size_t)kTileWarps * nspat * 2 + 64;
 }
 static size_t sky_boot_smem(int nspat) {
-    return (size_t)kBootstrap * 8 + kMtN * 4 + 34 * 4 + 2 * 4 + (size_t)50 * nspat * 4 + (size_t)nspat * 2 + 64;
+    return (size_t)2 * kBootstrap * 8 + kRing * 4 + 64 * 4 + 4 * 4 + (size_t)kBootstrap * boot_row_words(nspat) * 4 +
+           (size_t)nspat * 2 + 64;
 }
 
 static int stage_sky(motes_handle* h, Batch& b, double* data, double* errs, size_t frame_stride, double* limits,

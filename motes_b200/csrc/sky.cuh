@@ -150,18 +150,71 @@ MOTES_HD void sky_prepare_column(const Scope& sc, const double* col, int st, int
 }
 
 // ---- 2. bootstrap over the columns of one frame ---------------------------------------------
-// mt / pos: the generator (624 shared words + position, numpy's RandomState layout).
-// Per column c (stride `cs` between columns in sorted / rank_of):
-//   flag != modelled -> nothing drawn; n_good == 0 -> NaN; n_good == 1 -> no draws (numpy's
-//   masked rejection with range 0 consumes none).
-// hist: 50 * max_good shared words (100 16-bit counters per rank); ranks: max_good shared uint16;
-// meds: 100 shared doubles; scan: 33 shared words; ctl: 2 shared ints.
+// The generator is kept as a ring of the last 1024 state words indexed by absolute stream
+// position n (slot n & 1023): word n = mix(word n-624, word n-623, word n-397+... i.e. n-227),
+// so any 227 consecutive new words are independent of each other and are produced by one
+// parallel sweep.  A numpy RandomState (624 words + position) maps to words [0, 624) with
+// `used` = position, and back (the block of 624 that holds the last consumed word).
+//
+// One loop iteration = one barrier: every thread (a) produces a word of the next sweep and
+// (b) tests one pending output of the current column; after the barrier the per-warp accept
+// counts give every accepted draw its ordinal k in the stream order, hence its bootstrap sample
+// k % 100 (np.random.choice fills its (n, 100) index array row-major), and the draw is counted
+// into that sample's rank histogram.
+constexpr int kRing = 1024;
+constexpr int kSweep = kMtN - kMtM;      // 227
+
+struct BootShared {
+    uint32_t* ring;      // kRing words
+    uint32_t* counts;    // 2 x 32 per-warp accept counts (double buffered)
+    int* ctl;            // 4 ints
+    uint32_t* hist;      // 100 rows x row_words: 16-bit counters, sample-major
+    uint16_t* ranks;     // max_good
+    double* meds;        // 100
+    double* sq;          // 100
+};
+
+MOTES_HD int boot_row_words(int n) { return ((n + 1) / 2) | 1; }     // odd -> conflict-free row walks
+
+// sum of 100 doubles in numpy's order, cooperatively when a warp is available
 template <class Scope>
-MOTES_HD void sky_bootstrap_frame(const Scope& sc, uint32_t* mt, int* pos_io, int ncol, const int* n_good,
-                                  const int* flag, const double* sorted, const uint16_t* rank_of, size_t cs,
-                                  double* sky, double* sky_err, uint32_t* hist, uint16_t* ranks, double* meds,
-                                  uint32_t* scan, int* ctl) {
-    int pos = *pos_io;
+MOTES_HD double numpy_sum100(const Scope& sc, const double* a) {
+#if defined(__CUDA_ARCH__)
+    if (sc.size() >= 32) {
+        double res = 0.0;
+        if (sc.tid < 32) {
+            int lane = sc.tid;
+            double v = 0.0;
+            if (lane < 8) {
+                v = a[lane];
+                for (int i = 1; i < 12; ++i) v += a[8 * i + lane];
+            }
+            double t = v + __shfl_down_sync(0xffffffffu, v, 1);
+            double u = t + __shfl_down_sync(0xffffffffu, t, 2);
+            double w = u + __shfl_down_sync(0xffffffffu, u, 4);
+            res = ((w + a[96]) + a[97]) + a[98];
+            res = res + a[99];
+        }
+        return res;            // valid in thread 0
+    }
+#endif
+    return numpy_sum(a, kBootstrap);
+}
+
+template <class Scope>
+MOTES_HD void sky_bootstrap_frame(const Scope& sc, uint32_t* state /* 625 words, in/out */, int ncol,
+                                  const int* n_good, const int* flag, const double* sorted,
+                                  const uint16_t* rank_of, size_t cs, double* sky, double* sky_err,
+                                  const BootShared& sh) {
+    uint32_t* ring = sh.ring;
+    for (int i = sc.tid; i < kMtN; i += sc.size()) ring[i] = state[i];
+    long long gen = kMtN;                 // words generated so far (absolute)
+    long long used = (long long)state[kMtN];
+    const long long origin_used = used;
+    sc.sync();
+    const int nwarps = (sc.size() + 31) / 32;
+    int parity = 0;
+
     for (int c = 0; c < ncol; ++c) {
         if (flag[c] != kSkyModelled) {
             if (sc.tid == 0) { sky[c] = 0.0; sky_err[c] = 0.0; }
@@ -174,66 +227,126 @@ MOTES_HD void sky_bootstrap_frame(const Scope& sc, uint32_t* mt, int* pos_io, in
             continue;
         }
         if (n > 1) {
-            for (int i = sc.tid; i < 50 * n; i += sc.size()) hist[i] = 0;
-            for (int i = sc.tid; i < n; i += sc.size()) ranks[i] = rank_of[(size_t)c * cs + i];
+            const int rw = boot_row_words(n);
+            for (int i = sc.tid; i < kBootstrap * rw; i += sc.size()) sh.hist[i] = 0;
+            for (int i = sc.tid; i < n; i += sc.size()) sh.ranks[i] = rank_of[(size_t)c * cs + i];
             sc.sync();
             const int need = n * kBootstrap;
             const uint32_t mask = rejection_mask((uint32_t)n);
             int have = 0;
             while (have < need) {
-                if (pos >= kMtN) { mt_twist(sc, mt); pos = 0; }
-                int i = pos + sc.tid;
+                // (a) keep at least one round of outputs ahead
+                const long long pending = gen - used;
+                const bool sweep = pending <= kSweep;
+                if (sweep) {
+                    for (int j = sc.tid; j < kSweep; j += sc.size()) {
+                        long long w = gen + j;
+                        ring[w & (kRing - 1)] = mt_mix(ring[(w - kMtN) & (kRing - 1)], ring[(w - kMtN + 1) & (kRing - 1)],
+                                                       ring[(w - kSweep) & (kRing - 1)]);
+                    }
+                }
+                // (b) test one pending output per thread
+                const int round = (int)(pending < sc.size() ? pending : sc.size());
                 int acc = 0;
                 uint32_t v = 0;
-                if (i < kMtN) {
-                    v = mt_temper(mt[i]) & mask;
+                if (sc.tid < round) {
+                    v = mt_temper(ring[(used + sc.tid) & (kRing - 1)]) & mask;
                     acc = (v <= (uint32_t)(n - 1));
                 }
-                int total;
-                int off = sc.scan_flags(acc, &total, scan);
-                int ord = have + off;
+                int off, total;
+#if defined(__CUDA_ARCH__)
+                if (sc.size() > 1) {
+                    unsigned ballot = __ballot_sync(0xffffffffu, acc);
+                    int lane = sc.tid & 31, warp = sc.tid >> 5;
+                    if (lane == 0) sh.counts[parity * 32 + warp] = __popc(ballot);
+                    sc.sync();
+                    off = __popc(ballot & ((1u << lane) - 1u));
+                    total = 0;
+                    for (int k = 0; k < nwarps; ++k) {
+                        int cnt = (int)sh.counts[parity * 32 + k];
+                        if (k < warp) off += cnt;
+                        total += cnt;
+                    }
+                    parity ^= 1;
+                } else
+#endif
+                {
+                    sc.sync();
+                    off = 0;
+                    total = acc;
+                }
+                if (sweep) gen += kSweep;
+                const int ord = have + off;
                 if (acc && ord < need) {
-                    int s = ord % kBootstrap;                       // row-major (pixel, sample) fill
-                    sc.add(&hist[(int)ranks[v] * 50 + (s >> 1)], 1u << (16 * (s & 1)));
+                    const int smp = ord % kBootstrap;                  // row-major (pixel, sample) fill
+                    const int rk = (int)sh.ranks[v];
+                    sc.add(&sh.hist[smp * rw + (rk >> 1)], 1u << (16 * (rk & 1)));
                 }
                 if (have + total >= need) {
-                    if (acc && ord == need - 1) ctl[0] = i + 1;      // first unconsumed output
+                    // the accept with ordinal need-1 is the column's last draw; later outputs of this
+                    // round belong to the next column and are tested again under its (mask, n)
+                    if (acc && ord == need - 1) sh.ctl[0] = sc.tid + 1;
                     sc.sync();
-                    pos = ctl[0];
+                    used += sh.ctl[0];
                     have = need;
                     sc.sync();
                 } else {
                     have += total;
-                    pos = (pos + sc.size() > kMtN) ? kMtN : pos + sc.size();
+                    used += round;
                 }
             }
             // median of every bootstrap sample from its rank histogram
+            sc.sync();
             const int k1 = (n - 1) / 2, k2 = n / 2;
-            for (int s = sc.tid; s < kBootstrap; s += sc.size()) {
+            for (int smp = sc.tid; smp < kBootstrap; smp += sc.size()) {
+                const uint32_t* row = sh.hist + smp * rw;
                 int cum = 0, r1 = -1, r2 = -1;
-                for (int r = 0; r < n; ++r) {
-                    cum += (int)((hist[r * 50 + (s >> 1)] >> (16 * (s & 1))) & 0xffffu);
-                    if (r1 < 0 && cum > k1) r1 = r;
-                    if (cum > k2) { r2 = r; break; }
+                for (int wd = 0; wd < rw && r2 < 0; ++wd) {
+                    uint32_t pair = row[wd];
+                    for (int half = 0; half < 2; ++half) {
+                        cum += (int)((pair >> (16 * half)) & 0xffffu);
+                        int r = 2 * wd + half;
+                        if (r1 < 0 && cum > k1) r1 = r;
+                        if (r2 < 0 && cum > k2) r2 = r;
+                    }
                 }
-                meds[s] = (k1 == k2) ? srt[r1] : (srt[r1] + srt[r2]) * 0.5;
+                sh.meds[smp] = (k1 == k2) ? srt[r1] : (srt[r1] + srt[r2]) * 0.5;
             }
         } else {
-            for (int s = sc.tid; s < kBootstrap; s += sc.size()) meds[s] = srt[0];
+            for (int smp = sc.tid; smp < kBootstrap; smp += sc.size()) sh.meds[smp] = srt[0];
         }
         sc.sync();
+        // np.nanmean / np.std of the 100 medians in numpy's summation order (sky.py:40-41)
+        double mean = numpy_sum100(sc, sh.meds) / (double)kBootstrap;
+        if (sc.tid == 0) sh.sq[0] = mean;
+        sc.sync();
+        mean = sh.sq[0];
+        sc.sync();
+        for (int smp = sc.tid; smp < kBootstrap; smp += sc.size()) { double d = sh.meds[smp] - mean; sh.sq[smp] = d * d; }
+        sc.sync();
+        double var = numpy_sum100(sc, sh.sq) / (double)kBootstrap;
         if (sc.tid == 0) {
-            // np.nanmean / np.std of the 100 medians in numpy's summation order
-            double mean = numpy_sum(meds, kBootstrap) / (double)kBootstrap;
-            double sq[kBootstrap];
-            for (int s = 0; s < kBootstrap; ++s) { double d = meds[s] - mean; sq[s] = d * d; }
-            double var = numpy_sum(sq, kBootstrap) / (double)kBootstrap;
             sky[c] = mean;
             sky_err[c] = sqrt(var) / kSqrt99;
         }
         sc.sync();
     }
-    if (sc.tid == 0) *pos_io = pos;
+
+    // back to numpy's layout: the 624-word block that holds the last consumed word
+    long long block = (used > 0) ? ((used - 1) / kMtN) * kMtN : 0;
+    if (used == origin_used && used == 0) block = 0;
+    while (gen < block + kMtN) {
+        for (int j = sc.tid; j < kSweep; j += sc.size()) {
+            long long w = gen + j;
+            ring[w & (kRing - 1)] = mt_mix(ring[(w - kMtN) & (kRing - 1)], ring[(w - kMtN + 1) & (kRing - 1)],
+                                           ring[(w - kSweep) & (kRing - 1)]);
+        }
+        gen += kSweep;
+        sc.sync();
+    }
+    sc.sync();
+    for (int i = sc.tid; i < kMtN; i += sc.size()) state[i] = ring[(block + i) & (kRing - 1)];
+    if (sc.tid == 0) state[kMtN] = (uint32_t)(used - block);
     sc.sync();
 }
 

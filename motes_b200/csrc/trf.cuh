@@ -37,16 +37,28 @@ struct FitResult {
 //   y    [m]     profile being fitted
 //   unit [m]     (1+u)^-beta at the current base point
 //   a    [7*m]   columns 0..5: Jacobian (then J_h, then destroyed by QR); column 6: residual
-//   w, v [36]    Jacobi SVD work (replicated reads, lane-0 writes)
+//   w, v [36]    Jacobi SVD work (serial variant); vout [36] right singular vectors, row-major
 struct FitScratch {
     double* y;
     double* unit;
     double* a;
     double* w;
     double* v;
+    double* vout;
 };
 
-MOTES_HD size_t fit_scratch_doubles(int m) { return (size_t)9 * m + 72; }
+MOTES_HD size_t fit_scratch_doubles(int m) { return (size_t)9 * m + 108; }
+
+MOTES_HD FitScratch carve_fit_scratch(double* slab, int m) {
+    FitScratch ws;
+    ws.y = slab;
+    ws.unit = ws.y + m;
+    ws.a = ws.unit + m;
+    ws.w = ws.a + 7 * (size_t)m;
+    ws.v = ws.w + 36;
+    ws.vout = ws.v + 36;
+    return ws;
+}
 
 namespace trf_detail {
 
@@ -377,6 +389,105 @@ MOTES_HD void jacobi_svd6(const Ctx& ctx, const double* R, const double* z, doub
     ctx.sync();
 }
 
+#if defined(__CUDACC__)
+// Warp variant of the same decomposition.  Lane L (mod 8) < 6 owns row L of W (= R V) and of V;
+// the 15 column pairs of a sweep are visited in 5 rounds of 3 disjoint pairs (round-robin
+// ordering), so a round costs one 9-value reduction over the rows and one rotation latency
+// instead of three.  Every lane computes the rotation parameters from the all-reduced sums, so
+// all lanes stay in lock step.  Results: s, suf replicated in registers; V written to vout
+// (shared memory, row-major, columns sorted by descending singular value).
+__device__ __forceinline__ double sum8(double v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    return v;
+}
+
+template <int P, int Q>
+__device__ __forceinline__ void jacobi_pair_sums(const double (&w)[kParams], double& a, double& b, double& c) {
+    a = sum8(w[P] * w[P]);
+    b = sum8(w[Q] * w[Q]);
+    c = sum8(w[P] * w[Q]);
+}
+
+template <int P, int Q>
+__device__ __forceinline__ int jacobi_pair_rotate(double (&w)[kParams], double (&v)[kParams], double a, double b, double c) {
+    if (c == 0.0 || !(fabs(c) > kEps * sqrt(a * b))) return 0;
+    double d = b - a;
+    double t = (2.0 * c) * (d >= 0.0 ? 1.0 : -1.0) / (fabs(d) + sqrt(d * d + 4.0 * (c * c)));
+    double cs = rsqrt(1.0 + t * t);
+    double sn = cs * t;
+    double wp = w[P], wq = w[Q], vp = v[P], vq = v[Q];
+    w[P] = cs * wp - sn * wq;
+    w[Q] = sn * wp + cs * wq;
+    v[P] = cs * vp - sn * vq;
+    v[Q] = sn * vp + cs * vq;
+    return 1;
+}
+
+template <int P0, int Q0, int P1, int Q1, int P2, int Q2>
+__device__ __forceinline__ int jacobi_round(double (&w)[kParams], double (&v)[kParams]) {
+    double a0, b0, c0, a1, b1, c1, a2, b2, c2;
+    jacobi_pair_sums<P0, Q0>(w, a0, b0, c0);
+    jacobi_pair_sums<P1, Q1>(w, a1, b1, c1);
+    jacobi_pair_sums<P2, Q2>(w, a2, b2, c2);
+    int r = jacobi_pair_rotate<P0, Q0>(w, v, a0, b0, c0);
+    r |= jacobi_pair_rotate<P1, Q1>(w, v, a1, b1, c1);
+    r |= jacobi_pair_rotate<P2, Q2>(w, v, a2, b2, c2);
+    return r;
+}
+
+__device__ __forceinline__ void jacobi_svd6_warp(int lane, const double* R, const double* z, double* s, double* suf,
+                                                 double* vout) {
+    constexpr int n = kParams;
+    // rows are replicated in the four 8-lane groups so that every lane sees the same sums
+    const int row = lane & 7;
+    double w[n], v[n];
+#pragma unroll
+    for (int j = 0; j < n; ++j) {
+        w[j] = (row < n) ? R[(row < n ? row : 0) * n + j] : 0.0;
+        v[j] = (row == j) ? 1.0 : 0.0;
+    }
+    const double zl = (row < n) ? z[row < n ? row : 0] : 0.0;
+    for (int sweep = 0; sweep < 40; ++sweep) {
+        int rot = 0;
+        rot |= jacobi_round<0, 5, 1, 4, 2, 3>(w, v);
+        rot |= jacobi_round<0, 4, 3, 5, 1, 2>(w, v);
+        rot |= jacobi_round<0, 3, 2, 4, 1, 5>(w, v);
+        rot |= jacobi_round<0, 2, 1, 3, 4, 5>(w, v);
+        rot |= jacobi_round<0, 1, 2, 5, 3, 4>(w, v);
+        if (!rot) break;
+    }
+    double sv[n], sz[n];
+#pragma unroll
+    for (int j = 0; j < n; ++j) {
+        sv[j] = sqrt(sum8(w[j] * w[j]));
+        sz[j] = sum8(w[j] * zl);
+    }
+    // descending order of the singular values (replicated, branch-free selection of registers)
+    int order[n];
+#pragma unroll
+    for (int j = 0; j < n; ++j) {
+        int rank = 0;
+#pragma unroll
+        for (int k = 0; k < n; ++k) rank += (sv[k] > sv[j]) || (sv[k] == sv[j] && k < j);
+        order[j] = rank;          // column j goes to position rank
+    }
+#pragma unroll
+    for (int j = 0; j < n; ++j) {
+#pragma unroll
+        for (int pos = 0; pos < n; ++pos) {
+            if (order[j] == pos) {
+                s[pos] = sv[j];
+                suf[pos] = sz[j];
+                if (lane < n) vout[lane * n + pos] = v[j];
+            }
+        }
+    }
+    __syncwarp();
+}
+#endif
+
 // Residual sweep at parameters xe: writes f into out[] (and pow values into unit_out when given),
 // returns 0.5 * f.f through *cost, and whether every residual is finite.
 template <class Ctx>
@@ -573,8 +684,16 @@ MOTES_HD void trf_fit_moffat(const Ctx& ctx, int m, const double* profile, doubl
             }
             ctx.sync();
         }
-        double s[n], suf[n], V[n * n];
-        jacobi_svd6(ctx, R, z, ws.w, ws.v, s, suf, V);
+        double s[n], suf[n];
+        const double* V = ws.vout;
+#if defined(__CUDACC__)
+        if constexpr (Ctx::kLanes == 32) {
+            jacobi_svd6_warp(ctx.lane, R, z, s, suf, ws.vout);
+        } else
+#endif
+        {
+            jacobi_svd6(ctx, R, z, ws.w, ws.v, s, suf, ws.vout);
+        }
 
         double theta = fmax(0.995, 1.0 - g_norm);
         double gain = -1.0;

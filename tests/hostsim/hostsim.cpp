@@ -8,12 +8,7 @@
 extern "C" int hostsim_fit_batch(const double* profiles, int nfit, int m, const double* alpha0,
                                  double* params, double* cost, int* nfev, int* njev, int* status) {
     std::vector<double> slab(motes::fit_scratch_doubles(m));
-    motes::FitScratch ws;
-    ws.y = slab.data();
-    ws.unit = ws.y + m;
-    ws.a = ws.unit + m;
-    ws.w = ws.a + 7 * (size_t)m;
-    ws.v = ws.w + 36;
+    motes::FitScratch ws = motes::carve_fit_scratch(slab.data(), m);
     motes::SeqCtx ctx;
     for (int f = 0; f < nfit; ++f) {
         motes::FitResult r;
@@ -88,13 +83,18 @@ extern "C" int hostsim_sky_median(double* data, double* errs, int nspat, int ndi
                                   rank_of.data() + (size_t)c * nspat, good_row.data(), keys.data(), hist, &cell, &icell);
         if (flag[c] == motes::kSkyNoPixels) return -4;
     }
-    std::vector<uint32_t> bhist(50 * (size_t)nspat);
+    std::vector<uint32_t> bhist((size_t)motes::kBootstrap * motes::boot_row_words(nspat)), ring(motes::kRing), counts(64);
     std::vector<uint16_t> ranks(nspat);
-    double meds[100];
-    uint32_t scan[33];
-    int ctl[2];
-    motes::sky_bootstrap_frame(sc, mt, pos, ndisp, n_good, flag, sorted.data(), rank_of.data(), (size_t)nspat, sky,
-                               sky_err, bhist.data(), ranks.data(), meds, scan, ctl);
+    double meds[100], sq[100];
+    int ctl[4];
+    std::vector<uint32_t> state(625);
+    for (int i = 0; i < 624; ++i) state[i] = mt[i];
+    state[624] = (uint32_t)*pos;
+    motes::BootShared sh{ring.data(), counts.data(), ctl, bhist.data(), ranks.data(), meds, sq};
+    motes::sky_bootstrap_frame(sc, state.data(), ndisp, n_good, flag, sorted.data(), rank_of.data(), (size_t)nspat, sky,
+                               sky_err, sh);
+    for (int i = 0; i < 624; ++i) mt[i] = state[i];
+    *pos = (int)state[624];
     for (int c = 0; c < ndisp; ++c) motes::sky_apply_column(data, errs, nspat, ndisp, c, flag[c], sky[c], sky_err[c]);
     return 0;
 }
