@@ -150,8 +150,8 @@ MOTES_HD void sky_prepare_column(const Scope& sc, const double* col, int st, int
 }
 
 // ---- 2. bootstrap over the columns of one frame ---------------------------------------------
-// The generator is kept as a ring of the last 1024 state words indexed by absolute stream
-// position n (slot n & 1023): word n = mix(word n-624, word n-623, word n-397+... i.e. n-227),
+// The generator is kept as a ring of the last 2048 state words indexed by absolute stream
+// position n (slot n & 2047): word n = mix(word n-624, word n-623, word n-397+... i.e. n-227),
 // so any 227 consecutive new words are independent of each other and are produced by one
 // parallel sweep.  A numpy RandomState (624 words + position) maps to words [0, 624) with
 // `used` = position, and back (the block of 624 that holds the last consumed word).
@@ -161,7 +161,7 @@ MOTES_HD void sky_prepare_column(const Scope& sc, const double* col, int st, int
 // counts give every accepted draw its ordinal k in the stream order, hence its bootstrap sample
 // k % 100 (np.random.choice fills its (n, 100) index array row-major), and the draw is counted
 // into that sample's rank histogram.
-constexpr int kRing = 1024;
+constexpr int kRing = 2048;          // > 624 (block) + 2*227 (look-ahead) + 256 (round), power of two
 constexpr int kSweep = kMtN - kMtM;      // 227
 
 struct BootShared {
@@ -208,12 +208,17 @@ MOTES_HD void sky_bootstrap_frame(const Scope& sc, uint32_t* state /* 625 words,
                                   const BootShared& sh) {
     uint32_t* ring = sh.ring;
     for (int i = sc.tid; i < kMtN; i += sc.size()) ring[i] = state[i];
-    long long gen = kMtN;                 // words generated so far (absolute)
-    long long used = (long long)state[kMtN];
-    const long long origin_used = used;
+    // stream positions modulo 2^32 (only differences and the low 10 bits are ever used)
+    uint32_t gen = kMtN;
+    uint32_t used = state[kMtN];
+    unsigned long long used_total = state[kMtN];     // absolute, advanced once per column
     sc.sync();
-    const int nwarps = (sc.size() + 31) / 32;
     int parity = 0;
+#if defined(__CUDA_ARCH__)
+    const int lane = sc.tid & 31, warp = sc.tid >> 5;
+    unsigned char* counts8 = reinterpret_cast<unsigned char*>(sh.counts);     // 2 x 8 bytes used
+    const unsigned long long below_mask = (warp >= 8) ? ~0ull : ((1ull << (8 * warp)) - 1ull);
+#endif
 
     for (int c = 0; c < ncol; ++c) {
         if (flag[c] != kSkyModelled) {
@@ -233,40 +238,40 @@ MOTES_HD void sky_bootstrap_frame(const Scope& sc, uint32_t* state /* 625 words,
             sc.sync();
             const int need = n * kBootstrap;
             const uint32_t mask = rejection_mask((uint32_t)n);
+            const uint32_t top = (uint32_t)(n - 1);
+            const uint32_t used_at_start = used;
             int have = 0;
             while (have < need) {
                 // (a) keep at least one round of outputs ahead
-                const long long pending = gen - used;
-                const bool sweep = pending <= kSweep;
+                const uint32_t pending = gen - used;
+                const bool sweep = pending <= (uint32_t)kSweep;
                 if (sweep) {
                     for (int j = sc.tid; j < kSweep; j += sc.size()) {
-                        long long w = gen + j;
+                        const uint32_t w = gen + (uint32_t)j;
                         ring[w & (kRing - 1)] = mt_mix(ring[(w - kMtN) & (kRing - 1)], ring[(w - kMtN + 1) & (kRing - 1)],
                                                        ring[(w - kSweep) & (kRing - 1)]);
                     }
                 }
                 // (b) test one pending output per thread
-                const int round = (int)(pending < sc.size() ? pending : sc.size());
+                const int round = (int)(pending < (uint32_t)sc.size() ? pending : (uint32_t)sc.size());
                 int acc = 0;
                 uint32_t v = 0;
                 if (sc.tid < round) {
-                    v = mt_temper(ring[(used + sc.tid) & (kRing - 1)]) & mask;
-                    acc = (v <= (uint32_t)(n - 1));
+                    v = mt_temper(ring[(used + (uint32_t)sc.tid) & (kRing - 1)]) & mask;
+                    acc = (v <= top);
                 }
                 int off, total;
 #if defined(__CUDA_ARCH__)
                 if (sc.size() > 1) {
-                    unsigned ballot = __ballot_sync(0xffffffffu, acc);
-                    int lane = sc.tid & 31, warp = sc.tid >> 5;
-                    if (lane == 0) sh.counts[parity * 32 + warp] = __popc(ballot);
+                    // per-warp accept counts as bytes: one 64-bit load gives every thread all of them
+                    const unsigned ballot = __ballot_sync(0xffffffffu, acc);
+                    if (lane == 0) counts8[parity * 8 + warp] = (unsigned char)__popc(ballot);
                     sc.sync();
-                    off = __popc(ballot & ((1u << lane) - 1u));
-                    total = 0;
-                    for (int k = 0; k < nwarps; ++k) {
-                        int cnt = (int)sh.counts[parity * 32 + k];
-                        if (k < warp) off += cnt;
-                        total += cnt;
-                    }
+                    const unsigned long long all = *reinterpret_cast<const unsigned long long*>(counts8 + parity * 8);
+                    const unsigned long long low = all & below_mask;
+                    total = (int)(__vsadu4((unsigned)all, 0u) + __vsadu4((unsigned)(all >> 32), 0u));
+                    off = (int)(__vsadu4((unsigned)low, 0u) + __vsadu4((unsigned)(low >> 32), 0u)) +
+                          __popc(ballot & ((1u << lane) - 1u));
                     parity ^= 1;
                 } else
 #endif
@@ -275,7 +280,7 @@ MOTES_HD void sky_bootstrap_frame(const Scope& sc, uint32_t* state /* 625 words,
                     off = 0;
                     total = acc;
                 }
-                if (sweep) gen += kSweep;
+                if (sweep) gen += (uint32_t)kSweep;
                 const int ord = have + off;
                 if (acc && ord < need) {
                     const int smp = ord % kBootstrap;                  // row-major (pixel, sample) fill
@@ -287,14 +292,15 @@ MOTES_HD void sky_bootstrap_frame(const Scope& sc, uint32_t* state /* 625 words,
                     // round belong to the next column and are tested again under its (mask, n)
                     if (acc && ord == need - 1) sh.ctl[0] = sc.tid + 1;
                     sc.sync();
-                    used += sh.ctl[0];
+                    used += (uint32_t)sh.ctl[0];
                     have = need;
                     sc.sync();
                 } else {
                     have += total;
-                    used += round;
+                    used += (uint32_t)round;
                 }
             }
+            used_total += (unsigned long long)(used - used_at_start);
             // median of every bootstrap sample from its rank histogram
             sc.sync();
             const int k1 = (n - 1) / 2, k2 = n / 2;
@@ -332,21 +338,23 @@ MOTES_HD void sky_bootstrap_frame(const Scope& sc, uint32_t* state /* 625 words,
         sc.sync();
     }
 
-    // back to numpy's layout: the 624-word block that holds the last consumed word
-    long long block = (used > 0) ? ((used - 1) / kMtN) * kMtN : 0;
-    if (used == origin_used && used == 0) block = 0;
-    while (gen < block + kMtN) {
+    // back to numpy's layout: the 624-word block that holds the last consumed word.  `block` is the
+    // absolute index of its first word; ring indices are recovered relative to `used`.
+    const unsigned long long block = (used_total > 0) ? ((used_total - 1) / kMtN) * kMtN : 0;
+    const uint32_t into_block = (uint32_t)(used_total - block);          // numpy's position, 1..624 (or 0)
+    const uint32_t block32 = used - into_block;                           // ring index of the block start
+    while ((uint32_t)(gen - block32) < (uint32_t)kMtN) {
         for (int j = sc.tid; j < kSweep; j += sc.size()) {
-            long long w = gen + j;
+            const uint32_t w = gen + (uint32_t)j;
             ring[w & (kRing - 1)] = mt_mix(ring[(w - kMtN) & (kRing - 1)], ring[(w - kMtN + 1) & (kRing - 1)],
                                            ring[(w - kSweep) & (kRing - 1)]);
         }
-        gen += kSweep;
+        gen += (uint32_t)kSweep;
         sc.sync();
     }
     sc.sync();
-    for (int i = sc.tid; i < kMtN; i += sc.size()) state[i] = ring[(block + i) & (kRing - 1)];
-    if (sc.tid == 0) state[kMtN] = (uint32_t)(used - block);
+    for (int i = sc.tid; i < kMtN; i += sc.size()) state[i] = ring[(block32 + (uint32_t)i) & (kRing - 1)];
+    if (sc.tid == 0) state[kMtN] = into_block;
     sc.sync();
 }
 

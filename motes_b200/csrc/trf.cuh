@@ -437,18 +437,34 @@ __device__ __forceinline__ int jacobi_round(double (&w)[kParams], double (&v)[kP
     return r;
 }
 
+// `warm`: vout holds the V of the previous outer iteration; the sweeps then start from W = R V_prev
+// (any orthogonal start converges to the same decomposition), which near convergence of the fit
+// is already almost orthogonal and needs one or two sweeps instead of five or six.
 __device__ __forceinline__ void jacobi_svd6_warp(int lane, const double* R, const double* z, double* s, double* suf,
-                                                 double* vout) {
+                                                 double* vout, bool warm) {
     constexpr int n = kParams;
     // rows are replicated in the four 8-lane groups so that every lane sees the same sums
     const int row = lane & 7;
+    const int rr = row < n ? row : 0;
     double w[n], v[n];
+    if (warm) {
 #pragma unroll
-    for (int j = 0; j < n; ++j) {
-        w[j] = (row < n) ? R[(row < n ? row : 0) * n + j] : 0.0;
-        v[j] = (row == j) ? 1.0 : 0.0;
+        for (int j = 0; j < n; ++j) {
+            double acc = 0.0;
+#pragma unroll
+            for (int k = 0; k < n; ++k) acc = fma(R[rr * n + k], vout[k * n + j], acc);
+            w[j] = (row < n) ? acc : 0.0;
+            v[j] = (row < n) ? vout[rr * n + j] : 0.0;
+        }
+        __syncwarp();
+    } else {
+#pragma unroll
+        for (int j = 0; j < n; ++j) {
+            w[j] = (row < n) ? R[rr * n + j] : 0.0;
+            v[j] = (row == j) ? 1.0 : 0.0;
+        }
     }
-    const double zl = (row < n) ? z[row < n ? row : 0] : 0.0;
+    const double zl = (row < n) ? z[rr] : 0.0;
     for (int sweep = 0; sweep < 40; ++sweep) {
         int rot = 0;
         rot |= jacobi_round<0, 5, 1, 4, 2, 3>(w, v);
@@ -688,7 +704,7 @@ MOTES_HD void trf_fit_moffat(const Ctx& ctx, int m, const double* profile, doubl
         const double* V = ws.vout;
 #if defined(__CUDACC__)
         if constexpr (Ctx::kLanes == 32) {
-            jacobi_svd6_warp(ctx.lane, R, z, s, suf, ws.vout);
+            jacobi_svd6_warp(ctx.lane, R, z, s, suf, ws.vout, njev > 1);
         } else
 #endif
         {
