@@ -437,9 +437,10 @@ __device__ __forceinline__ int jacobi_round(double (&w)[kParams], double (&v)[kP
     return r;
 }
 
-// `warm`: vout holds the V of the previous outer iteration; the sweeps then start from W = R V_prev
-// (any orthogonal start converges to the same decomposition), which near convergence of the fit
-// is already almost orthogonal and needs one or two sweeps instead of five or six.
+// `warm`: vout holds the V of the previous outer iteration and the sweeps start from W = R V_prev
+// (any orthogonal start converges to the same decomposition).  Measured on B200 (round 1): no gain
+// in fit time and one more stopping-point flip on the faint-source golden case, so the solver
+// calls it cold, like scipy's fresh SVD every iteration.
 __device__ __forceinline__ void jacobi_svd6_warp(int lane, const double* R, const double* z, double* s, double* suf,
                                                  double* vout, bool warm) {
     constexpr int n = kParams;
@@ -704,7 +705,7 @@ MOTES_HD void trf_fit_moffat(const Ctx& ctx, int m, const double* profile, doubl
         const double* V = ws.vout;
 #if defined(__CUDACC__)
         if constexpr (Ctx::kLanes == 32) {
-            jacobi_svd6_warp(ctx.lane, R, z, s, suf, ws.vout, njev > 1);
+            jacobi_svd6_warp(ctx.lane, R, z, s, suf, ws.vout, false);
         } else
 #endif
         {
