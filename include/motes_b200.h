@@ -69,7 +69,7 @@ typedef struct motes_params {
     double sky_snr_limit;          /* -ks  tracing.py:160 */
     double sky_fwhm_multiplier;    /* -kf  used for BOTH the sky and the extraction limits (core.py:208) */
     int32_t subtract_sky;          /* -k   */
-    int32_t sky_order;             /* -ko  0 = bootstrap median (sky.py:17-43) */
+    int32_t sky_order;             /* -ko  0 = bootstrap median (sky.py:17-43), 1..5 = bootstrap polynomial (sky.py:177-254) */
     int32_t spatial_floor;         /* axes_dict["data_spatial_floor"] */
     int32_t wavelength_start;      /* axes_dict["wavelength_start"] */
 } motes_params;
@@ -91,8 +91,8 @@ typedef struct motes_outputs {
     double* median_params;    /* [F][6]  fit of the full-frame median profile (tracing.py:403-456) */
     double* scale;            /* [F]  data_scaling_factor */
     double* seeing_px;        /* [F]  header_parameters["seeing"] after tracing.py:449 */
-    double* sky_model;        /* [F][ndisp] per-column sky level (order 0); 0 where not modelled */
-    double* sky_uncertainty;  /* [F][ndisp] */
+    double* sky_model;        /* sky_order 0: [F][ndisp] per-column sky level; sky_order > 0: [F][nspat][ndisp]; 0 where not modelled */
+    double* sky_uncertainty;  /* same shape as sky_model */
     int32_t* sky_flag;        /* [F][ndisp] 0 modelled, 1 skipped as constant (sky.py:338-339), 2 no sky pixels */
     int32_t* frame_status;    /* [F] 0, MOTES_E_NOSKY or MOTES_E_FIT: what the reference would have raised for that frame */
 } motes_outputs;
@@ -151,9 +151,11 @@ int motes_bin_profiles_host(motes_handle* h, const double* data, int nspat, int 
 int motes_interp_limits_host(motes_handle* h, const double* table, int nbins, int ndisp, double* lim_lo,
                              double* lim_hi);
 
-/* a9: sky.subtract_sky with sky_order 0 (sky.py:257-399).  data / errs / lim_lo / lim_hi are updated
- * in place as the reference does; rng_state[625] is numpy's legacy RandomState, advanced by exactly
- * the draws the reference consumes.  Returns MOTES_E_NOSKY where the reference raises RuntimeError. */
+/* a9: sky.subtract_sky (sky.py:257-399).  data / errs / lim_lo / lim_hi are updated in place as the
+ * reference does; rng_state[625] is numpy's legacy RandomState (no cached Gaussian), advanced by exactly
+ * the draws the reference consumes.  sky_order 0 = bootstrap median (sky.py:17-43): sky / sky_err hold
+ * ndisp values; sky_order 1..5 = bootstrap polynomial (sky.py:177-254): they hold (nspat, ndisp) frames.
+ * Returns MOTES_E_NOSKY where the reference raises RuntimeError. */
 int motes_sky_subtract_host(motes_handle* h, double* data, double* errs, int nspat, int ndisp, double* lim_lo,
                             double* lim_hi, int spatial_floor, int sky_order, uint32_t* rng_state,
                             double* sky, double* sky_err, int32_t* flag, int32_t* n_sky, int32_t* n_good);

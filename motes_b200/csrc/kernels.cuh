@@ -321,7 +321,7 @@ sky_prepare_kernel(const double* __restrict__ data, size_t frame_stride, int nsp
                    double* __restrict__ limits /* [F][2][ndisp], clamped in place */, int spatial_floor,
                    int32_t* __restrict__ n_sky, int32_t* __restrict__ n_good, int32_t* __restrict__ flag,
                    double* __restrict__ sorted /* [F][ndisp][nspat] */, uint16_t* __restrict__ rank_of,
-                   FrameState* __restrict__ st) {
+                   uint16_t* __restrict__ good_row /* optional, same shape as rank_of */, FrameState* __restrict__ st) {
     extern __shared__ __align__(16) unsigned char sp_smem[];
     double* tile = reinterpret_cast<double*>(sp_smem);
     unsigned long long* keys_all = reinterpret_cast<unsigned long long*>(tile + (size_t)nspat * kTileStride);
@@ -348,6 +348,8 @@ sky_prepare_kernel(const double* __restrict__ data, size_t frame_stride, int nsp
         sky_prepare_column(sc, tile + c, kTileStride, nspat, lo, hi, spatial_floor, &ns, &ng, &fl,
                            sorted + col * nspat, rank_of + col * nspat, rows_all + (size_t)warp * nspat,
                            keys_all + (size_t)warp * nspat, hist_all + warp * 256, cells + warp, &icell);
+        if (good_row && fl == kSkyModelled)
+            for (int g = sc.tid; g < ng; g += 32) good_row[col * nspat + g] = rows_all[(size_t)warp * nspat + g];
         if (sc.tid == 0) {
             n_sky[col] = ns;
             n_good[col] = ng;
@@ -381,6 +383,50 @@ sky_bootstrap_kernel(uint32_t* __restrict__ rng /* [F][625]: 624 state words + p
     const size_t base = (size_t)f * ndisp;
     sky_bootstrap_frame(sc, rng + (size_t)f * 625, ndisp, n_good + base, flag + base, sorted + base * nspat,
                         rank_of + base * nspat, (size_t)nspat, sky + base, sky_err + base, sh);
+}
+
+// Bootstrap polynomial sky (sky_order > 0): one CTA per frame, columns in order.
+__global__ void __launch_bounds__(kBootThreads)
+sky_bootstrap_poly_kernel(uint32_t* __restrict__ rng, int nspat, int ndisp, int order, int spatial_floor,
+                          const double* __restrict__ errs, size_t frame_stride, const int32_t* __restrict__ n_good,
+                          const int32_t* __restrict__ flag, const double* __restrict__ sorted,
+                          const uint16_t* __restrict__ rank_of, const uint16_t* __restrict__ good_row,
+                          double* __restrict__ yscratch /* [F][100*nspat] */, double* __restrict__ model,
+                          double* __restrict__ model_err /* [F][nspat][ndisp] */, const FrameState* __restrict__ st) {
+    extern __shared__ __align__(16) unsigned char sp2_smem[];
+    PolyShared sh;
+    sh.q = reinterpret_cast<double*>(sp2_smem);
+    sh.rmat = sh.q + (size_t)nspat * kMaxPoly;
+    sh.colscale = sh.rmat + kMaxPoly * kMaxPoly;
+    sh.coef = sh.colscale + kMaxPoly;
+    sh.loc = sh.coef + kBootstrap * kMaxPoly;
+    sh.scl = sh.loc + nspat;
+    sh.red = sh.scl + nspat;
+    sh.samples = sh.red + 40;
+    sh.ring = reinterpret_cast<uint32_t*>(sh.samples + (size_t)(kBootThreads / 32) * kBootstrap);
+    sh.counts = sh.ring + kRing;
+    sh.ctl = reinterpret_cast<int*>(sh.counts + 16);
+    sh.rows = reinterpret_cast<uint16_t*>(sh.ctl + 4);
+    BlockScope sc{(int)threadIdx.x};
+    const int f = blockIdx.x;
+    if (st[f].status != 0) return;
+    const size_t base = (size_t)f * ndisp;
+    sky_bootstrap_poly_frame(sc, rng + (size_t)f * 625, ndisp, nspat, ndisp, order, spatial_floor,
+                             errs + (size_t)f * frame_stride, n_good + base, flag + base, sorted + base * nspat,
+                             rank_of + base * nspat, good_row + base * nspat, (size_t)nspat,
+                             yscratch + (size_t)f * kBootstrap * nspat, model + (size_t)f * frame_stride,
+                             model_err + (size_t)f * frame_stride, sh);
+}
+
+__global__ void __launch_bounds__(128)
+sky_apply_poly_kernel(double* __restrict__ data, double* __restrict__ errs, size_t frame_stride, int nspat, int ndisp,
+                      const int32_t* __restrict__ flag, const double* __restrict__ model,
+                      const double* __restrict__ model_err, const FrameState* __restrict__ st) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x, f = blockIdx.y;
+    if (c >= ndisp || st[f].status != 0) return;
+    sky_apply_column_poly(data + (size_t)f * frame_stride, errs + (size_t)f * frame_stride, nspat, ndisp, c,
+                          flag[(size_t)f * ndisp + c], model + (size_t)f * frame_stride,
+                          model_err + (size_t)f * frame_stride);
 }
 
 __global__ void __launch_bounds__(128)

@@ -5,7 +5,7 @@
 namespace motes {
 
 // Work-area slots inside motes_handle::work
-enum WorkSlot { W_STATE = 0, W_F64, W_I32, W_U8, W_SORTED, W_RANKS, W_PROFILES, W_RNG, W_QUAL, W_HOSTOUT };
+enum WorkSlot { W_STATE = 0, W_F64, W_I32, W_U8, W_SORTED, W_RANKS, W_PROFILES, W_GOODROW, W_YSCRATCH, W_MODEL, W_MODELERR };
 
 // Device-side working set of one batch.  All pointers are carved out of handle scratch.
 struct Batch {
@@ -31,6 +31,9 @@ struct Batch {
     double *sorted, *sky, *sky_err;
     uint16_t* rank_of;
     double* spectra;
+    // sky_order > 0 only
+    uint16_t* good_row;
+    double *yscratch, *model, *model_err;
 };
 
 struct Carver {
@@ -83,7 +86,7 @@ static size_t carve_i32(Batch& b, void* base) {
     return c.off + 256;
 }
 
-static int make_batch(motes_handle* h, Batch& b, int F, int nspat, int ndisp, int cap, bool need_sky) {
+static int make_batch(motes_handle* h, Batch& b, int F, int nspat, int ndisp, int cap, bool need_sky, bool need_poly = false) {
     b = Batch();
     b.F = F; b.nspat = nspat; b.ndisp = ndisp; b.cap = cap;
     MOTES_TRY(h->work[W_STATE].ensure(sizeof(FrameState) * (size_t)F));
@@ -101,6 +104,16 @@ static int make_batch(motes_handle* h, Batch& b, int F, int nspat, int ndisp, in
         b.sorted = h->work[W_SORTED].as<double>();
         MOTES_TRY(h->work[W_RANKS].ensure((size_t)F * ndisp * nspat * sizeof(uint16_t)));
         b.rank_of = h->work[W_RANKS].as<uint16_t>();
+    }
+    if (need_sky && need_poly) {
+        MOTES_TRY(h->work[W_GOODROW].ensure((size_t)F * ndisp * nspat * sizeof(uint16_t)));
+        b.good_row = h->work[W_GOODROW].as<uint16_t>();
+        MOTES_TRY(h->work[W_YSCRATCH].ensure((size_t)F * kBootstrap * nspat * sizeof(double)));
+        b.yscratch = h->work[W_YSCRATCH].as<double>();
+        MOTES_TRY(h->work[W_MODEL].ensure((size_t)F * ndisp * nspat * sizeof(double)));
+        b.model = h->work[W_MODEL].as<double>();
+        MOTES_TRY(h->work[W_MODELERR].ensure((size_t)F * ndisp * nspat * sizeof(double)));
+        b.model_err = h->work[W_MODELERR].as<double>();
     }
     return MOTES_OK;
 }
@@ -230,32 +243,57 @@ static size_t sky_boot_smem(int nspat) {
            (size_t)nspat * 2 + 64;
 }
 
+static size_t sky_poly_smem(int nspat) {
+    return ((size_t)nspat * kMaxPoly + kMaxPoly * kMaxPoly + kMaxPoly + kBootstrap * kMaxPoly + 2 * (size_t)nspat + 40 +
+            (size_t)(kBootThreads / 32) * kBootstrap) * 8 + kRing * 4 + 16 * 4 + 4 * 4 + (size_t)nspat * 2 + 64;
+}
+
 static int stage_sky(motes_handle* h, Batch& b, double* data, double* errs, size_t frame_stride, double* limits,
                      const motes_params& p, uint32_t* rng) {
-    if (p.sky_order != 0) return fail_arg("sky_order > 0 (bootstrap polynomial sky) is not implemented on the device yet");
+    if (p.sky_order < 0 || p.sky_order >= kMaxPoly) return fail_arg("sky_order must be 0..5");
     if (b.nspat > 65535) return fail_arg("nspat too large");
+    const bool poly = p.sky_order > 0;
     size_t smem = sky_prepare_smem(b.nspat);
-    if (smem > h->smem_optin || sky_boot_smem(b.nspat) > h->smem_optin)
+    if (smem > h->smem_optin || sky_boot_smem(b.nspat) > h->smem_optin || sky_poly_smem(b.nspat) > h->smem_optin)
         return fail_arg("nspat too large for the shared-memory sky kernels");
     MOTES_CUDA(cudaFuncSetAttribute(sky_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     {
-    StageTimer timer(h, ST_SKY_PREPARE);
-    sky_prepare_kernel<<<dim3((b.ndisp + kTileCols - 1) / kTileCols, b.F), kTileThreads, smem, h->stream>>>(
-        data, frame_stride, b.nspat, b.ndisp, limits, p.spatial_floor, b.n_sky, b.n_good, b.sky_flag, b.sorted,
-        b.rank_of, b.st);
-    MOTES_LAUNCHED(h);
+        StageTimer timer(h, ST_SKY_PREPARE);
+        sky_prepare_kernel<<<dim3((b.ndisp + kTileCols - 1) / kTileCols, b.F), kTileThreads, smem, h->stream>>>(
+            data, frame_stride, b.nspat, b.ndisp, limits, p.spatial_floor, b.n_sky, b.n_good, b.sky_flag, b.sorted,
+            b.rank_of, poly ? b.good_row : nullptr, b.st);
+        MOTES_LAUNCHED(h);
     }
-    smem = sky_boot_smem(b.nspat);
-    MOTES_CUDA(cudaFuncSetAttribute(sky_bootstrap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (!poly) {
+        smem = sky_boot_smem(b.nspat);
+        MOTES_CUDA(cudaFuncSetAttribute(sky_bootstrap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        {
+            StageTimer timer(h, ST_SKY_BOOTSTRAP);
+            sky_bootstrap_kernel<<<b.F, kBootThreads, smem, h->stream>>>(rng, b.nspat, b.ndisp, b.n_good, b.sky_flag,
+                                                                         b.sorted, b.rank_of, b.sky, b.sky_err, b.st);
+            MOTES_LAUNCHED(h);
+        }
+        StageTimer timer(h, ST_SKY_APPLY);
+        sky_apply_kernel<<<dim3((b.ndisp + 127) / 128, b.F), 128, 0, h->stream>>>(data, errs, frame_stride, b.nspat,
+                                                                                 b.ndisp, b.sky_flag, b.sky, b.sky_err, b.st);
+        MOTES_LAUNCHED(h);
+        return MOTES_OK;
+    }
+    if (!b.good_row) return fail_arg("internal: polynomial sky scratch missing");
+    smem = sky_poly_smem(b.nspat);
+    MOTES_CUDA(cudaFuncSetAttribute(sky_bootstrap_poly_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MOTES_CUDA(cudaMemsetAsync(b.model, 0, sizeof(double) * (size_t)b.F * frame_stride, h->stream));
+    MOTES_CUDA(cudaMemsetAsync(b.model_err, 0, sizeof(double) * (size_t)b.F * frame_stride, h->stream));
     {
-    StageTimer timer(h, ST_SKY_BOOTSTRAP);
-    sky_bootstrap_kernel<<<b.F, kBootThreads, smem, h->stream>>>(rng, b.nspat, b.ndisp, b.n_good, b.sky_flag, b.sorted,
-                                                                 b.rank_of, b.sky, b.sky_err, b.st);
-    MOTES_LAUNCHED(h);
+        StageTimer timer(h, ST_SKY_BOOTSTRAP);
+        sky_bootstrap_poly_kernel<<<b.F, kBootThreads, smem, h->stream>>>(
+            rng, b.nspat, b.ndisp, p.sky_order, p.spatial_floor, errs, frame_stride, b.n_good, b.sky_flag, b.sorted,
+            b.rank_of, b.good_row, b.yscratch, b.model, b.model_err, b.st);
+        MOTES_LAUNCHED(h);
     }
     StageTimer timer(h, ST_SKY_APPLY);
-    sky_apply_kernel<<<dim3((b.ndisp + 127) / 128, b.F), 128, 0, h->stream>>>(data, errs, frame_stride, b.nspat, b.ndisp,
-                                                                             b.sky_flag, b.sky, b.sky_err, b.st);
+    sky_apply_poly_kernel<<<dim3((b.ndisp + 127) / 128, b.F), 128, 0, h->stream>>>(data, errs, frame_stride, b.nspat,
+                                                                                  b.ndisp, b.sky_flag, b.model, b.model_err, b.st);
     MOTES_LAUNCHED(h);
     return MOTES_OK;
 }
@@ -458,7 +496,7 @@ int motes_run_frames_dev(motes_handle* h, double* data, double* errs, const uint
     MOTES_TRY(check_run_args(h, data, errs, qual, nframes, nspat, ndisp, cap, params, seeing, pixres, rng_states, out));
     MOTES_CUDA(cudaSetDevice(h->device));
     Batch b;
-    MOTES_TRY(make_batch(h, b, nframes, nspat, ndisp, cap, params->subtract_sky != 0));
+    MOTES_TRY(make_batch(h, b, nframes, nspat, ndisp, cap, params->subtract_sky != 0, params->sky_order > 0));
     const motes_params p = *params;
     const motes_outputs o = *out;
     auto emit = [&]() -> int {
@@ -475,8 +513,13 @@ int motes_run_frames_dev(motes_handle* h, double* data, double* errs, const uint
             MOTES_TRY(copy_dd(h, o.sky_params, b.params8[0], F * cp * 8));
             MOTES_TRY(copy_dd(h, o.sky_bins, b.bins_i[0], F * cp * 2));
             MOTES_TRY(copy_dd(h, o.sky_bin_snr, b.bins_snr[0], F * cp));
-            MOTES_TRY(copy_dd(h, o.sky_model, b.sky, F * nd));
-            MOTES_TRY(copy_dd(h, o.sky_uncertainty, b.sky_err, F * nd));
+            if (p.sky_order > 0) {
+                MOTES_TRY(copy_dd(h, o.sky_model, b.model, F * nd * b.nspat));
+                MOTES_TRY(copy_dd(h, o.sky_uncertainty, b.model_err, F * nd * b.nspat));
+            } else {
+                MOTES_TRY(copy_dd(h, o.sky_model, b.sky, F * nd));
+                MOTES_TRY(copy_dd(h, o.sky_uncertainty, b.sky_err, F * nd));
+            }
             MOTES_TRY(copy_dd(h, o.sky_flag, b.sky_flag, F * nd));
         }
         if (o.median_params) MOTES_CUDA(cudaMemcpy2DAsync(o.median_params, 6 * sizeof(double), b.st->median_params, sizeof(FrameState), 6 * sizeof(double), F, cudaMemcpyDeviceToDevice, h->stream));
@@ -494,7 +537,7 @@ int motes_run_frames_host(motes_handle* h, double* data, double* errs, const uin
     MOTES_TRY(check_run_args(h, data, errs, qual, nframes, nspat, ndisp, cap, params, seeing, pixres, rng_states, out));
     MOTES_CUDA(cudaSetDevice(h->device));
     Batch b;
-    MOTES_TRY(make_batch(h, b, nframes, nspat, ndisp, cap, params->subtract_sky != 0));
+    MOTES_TRY(make_batch(h, b, nframes, nspat, ndisp, cap, params->subtract_sky != 0, params->sky_order > 0));
     const motes_params p = *params;
     const motes_outputs o = *out;
     const size_t npix = (size_t)nframes * nspat * ndisp;
@@ -521,8 +564,13 @@ int motes_run_frames_host(motes_handle* h, double* data, double* errs, const uin
             MOTES_TRY(download(h, o.sky_params, b.params8[0], F * cp * 8));
             MOTES_TRY(download(h, o.sky_bins, b.bins_i[0], F * cp * 2));
             MOTES_TRY(download(h, o.sky_bin_snr, b.bins_snr[0], F * cp));
-            MOTES_TRY(download(h, o.sky_model, b.sky, F * nd));
-            MOTES_TRY(download(h, o.sky_uncertainty, b.sky_err, F * nd));
+            if (p.sky_order > 0) {
+                MOTES_TRY(download(h, o.sky_model, b.model, F * nd * b.nspat));
+                MOTES_TRY(download(h, o.sky_uncertainty, b.model_err, F * nd * b.nspat));
+            } else {
+                MOTES_TRY(download(h, o.sky_model, b.sky, F * nd));
+                MOTES_TRY(download(h, o.sky_uncertainty, b.sky_err, F * nd));
+            }
             MOTES_TRY(download(h, o.sky_flag, b.sky_flag, F * nd));
             MOTES_TRY(download(h, rng_states, d_rng, F * 625));
         }
@@ -664,7 +712,7 @@ int motes_sky_subtract_host(motes_handle* h, double* data, double* errs, int nsp
     MOTES_CUDA(cudaSetDevice(h->device));
     const size_t npix = (size_t)nspat * ndisp;
     Batch b;
-    MOTES_TRY(make_batch(h, b, 1, nspat, ndisp, 1, true));
+    MOTES_TRY(make_batch(h, b, 1, nspat, ndisp, 1, true, sky_order > 0));
     double *d_data, *d_errs;
     uint32_t* d_rng;
     MOTES_TRY(upload(h, h->stage[0], data, npix, &d_data));
@@ -691,8 +739,13 @@ int motes_sky_subtract_host(motes_handle* h, double* data, double* errs, int nsp
     }
     MOTES_TRY(download(h, data, d_data, npix));
     MOTES_TRY(download(h, errs, d_errs, npix));
-    MOTES_TRY(download(h, sky, b.sky, (size_t)ndisp));
-    MOTES_TRY(download(h, sky_err, b.sky_err, (size_t)ndisp));
+    if (sky_order > 0) {
+        MOTES_TRY(download(h, sky, b.model, npix));
+        MOTES_TRY(download(h, sky_err, b.model_err, npix));
+    } else {
+        MOTES_TRY(download(h, sky, b.sky, (size_t)ndisp));
+        MOTES_TRY(download(h, sky_err, b.sky_err, (size_t)ndisp));
+    }
     MOTES_TRY(download(h, rng_state, d_rng, (size_t)625));
     MOTES_CUDA(cudaStreamSynchronize(h->stream));
     return MOTES_OK;

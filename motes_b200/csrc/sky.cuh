@@ -358,6 +358,312 @@ MOTES_HD void sky_bootstrap_frame(const Scope& sc, uint32_t* state /* 625 words,
     sc.sync();
 }
 
+// ---- 2b. bootstrap polynomial sky (sky.sky_polynomial, sky.py:177-254) ------------------------
+// Per column: every good sky pixel j is replaced 100 times by N(pixel_j, err_j) drawn with numpy's
+// legacy polar Gaussian (np.random.normal: two 53-bit uniforms per attempt, accept 0 < r2 < 1,
+// return f*x2 and cache f*x1), a polynomial of the requested order is fitted to each of the 100
+// perturbed sky vectors, and the model / uncertainty of every spatial pixel are the median / std
+// of the 100 polynomial values there.
+//
+// The generator words are consumed four at a time (one attempt); accepted attempts are numbered
+// in stream order: attempt k feeds pixel k / 50, samples 2 (k % 50) and 2 (k % 50) + 1.
+// The 100 least-squares fits share one design matrix: a QR (modified Gram-Schmidt) of the
+// column-normalised Vandermonde matrix is built once per column and every sample is a
+// projection + back-substitution.  np.polyfit solves the same scaled system with LAPACK gelsd;
+// the two agree to ~1e-13 in the fitted values, i.e. this mode is
+// tolerance-parity, not bit-parity (CUDA's log() also differs from libm's in the last ulp).
+constexpr int kMaxPoly = 6;              // order <= 5
+
+struct PolyShared {
+    uint32_t* ring;      // kRing
+    uint32_t* counts;    // 16 words
+    int* ctl;            // 4
+    double* q;           // max_good * kMaxPoly : Vandermonde -> Q
+    double* rmat;        // kMaxPoly * kMaxPoly
+    double* colscale;    // kMaxPoly
+    double* coef;        // 100 * kMaxPoly (ascending powers)
+    double* loc;         // max_good
+    double* scl;         // max_good
+    double* red;         // 40 doubles: block reduction scratch
+    double* samples;     // per warp 100 (device) / 100 (host)
+    uint16_t* rows;      // max_good
+};
+
+template <class Scope>
+MOTES_HD double scope_dsum(const Scope& sc, double v, double* red) {
+#if defined(__CUDA_ARCH__)
+    if (sc.size() > 1) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        const int lane = sc.tid & 31, warp = sc.tid >> 5, nw = (sc.size() + 31) >> 5;
+        if (lane == 0) red[warp] = v;
+        sc.sync();
+        double t = 0.0;
+        for (int k = 0; k < nw; ++k) t += red[k];       // fixed order: every thread gets the same bits
+        sc.sync();
+        return t;
+    }
+#endif
+    (void)red;
+    return v;
+}
+
+// y: global scratch of 100 * max_good doubles for this frame, pixel-major (y[j * 100 + s]).
+// model / model_err: (nspat, ndisp) frames receiving this column's result at [pixel * ndisp + c].
+template <class Scope>
+MOTES_HD void sky_bootstrap_poly_frame(const Scope& sc, uint32_t* state, int ncol, int nspat, int ndisp, int order,
+                                       int spatial_floor, const double* errs /* frame */, const int* n_good,
+                                       const int* flag, const double* sorted, const uint16_t* rank_of,
+                                       const uint16_t* good_row, size_t cs, double* y, double* model,
+                                       double* model_err, const PolyShared& sh) {
+    uint32_t* ring = sh.ring;
+    for (int i = sc.tid; i < kMtN; i += sc.size()) ring[i] = state[i];
+    uint32_t gen = kMtN;
+    uint32_t used = state[kMtN];
+    unsigned long long used_total = state[kMtN];
+    sc.sync();
+    const int p = order + 1;
+    int parity = 0;
+#if defined(__CUDA_ARCH__)
+    const int lane = sc.tid & 31, warp = sc.tid >> 5;
+    unsigned char* counts8 = reinterpret_cast<unsigned char*>(sh.counts);
+    const unsigned long long below_mask = (warp >= 8) ? ~0ull : ((1ull << (8 * warp)) - 1ull);
+#endif
+
+    for (int c = 0; c < ncol; ++c) {
+        if (flag[c] != kSkyModelled) continue;
+        const int n = n_good[c];
+        if (n < p) {          // np.polyfit would warn (rank deficient); the reference result is undefined here
+            for (int i = sc.tid; i < nspat; i += sc.size()) { model[(size_t)i * ndisp + c] = NAN; model_err[(size_t)i * ndisp + c] = NAN; }
+            continue;
+        }
+        // good pixels of this column in row order: value, error, axis
+        for (int g = sc.tid; g < n; g += sc.size()) {
+            const int row = (int)good_row[(size_t)c * cs + g];
+            sh.rows[g] = (uint16_t)row;
+            sh.loc[g] = sorted[(size_t)c * cs + rank_of[(size_t)c * cs + g]];
+            sh.scl[g] = errs[(size_t)row * ndisp + c];
+        }
+        sc.sync();
+
+        // ---- 100 Gaussian-perturbed copies of the sky vector (sky.py:218-225)
+        const int need = n * (kBootstrap / 2);          // accepted attempts (pairs of deviates)
+        const uint32_t used_at_start = used;
+        int have = 0;
+        while (have < need) {
+            const uint32_t pending = gen - used;
+            const bool sweep = pending <= (uint32_t)(kSweep + 3);
+            if (sweep) {
+                for (int j = sc.tid; j < kSweep; j += sc.size()) {
+                    const uint32_t w = gen + (uint32_t)j;
+                    ring[w & (kRing - 1)] = mt_mix(ring[(w - kMtN) & (kRing - 1)], ring[(w - kMtN + 1) & (kRing - 1)],
+                                                   ring[(w - kSweep) & (kRing - 1)]);
+                }
+            }
+            const int attempts = (int)(pending / 4u);
+            const int round = attempts < sc.size() ? attempts : sc.size();
+            int acc = 0;
+            double x1 = 0.0, x2 = 0.0, r2 = 0.0;
+            if (sc.tid < round) {
+                const uint32_t base = used + 4u * (uint32_t)sc.tid;
+                const uint32_t a0 = mt_temper(ring[base & (kRing - 1)]), b0 = mt_temper(ring[(base + 1) & (kRing - 1)]);
+                const uint32_t a1 = mt_temper(ring[(base + 2) & (kRing - 1)]), b1 = mt_temper(ring[(base + 3) & (kRing - 1)]);
+                const double u1 = ((double)(a0 >> 5) * 67108864.0 + (double)(b0 >> 6)) / 9007199254740992.0;
+                const double u2 = ((double)(a1 >> 5) * 67108864.0 + (double)(b1 >> 6)) / 9007199254740992.0;
+                x1 = 2.0 * u1 - 1.0;
+                x2 = 2.0 * u2 - 1.0;
+                r2 = x1 * x1 + x2 * x2;
+                acc = (r2 < 1.0 && r2 != 0.0);
+            }
+            int off, total;
+#if defined(__CUDA_ARCH__)
+            if (sc.size() > 1) {
+                const unsigned ballot = __ballot_sync(0xffffffffu, acc);
+                if (lane == 0) counts8[parity * 8 + warp] = (unsigned char)__popc(ballot);
+                sc.sync();
+                const unsigned long long all = *reinterpret_cast<const unsigned long long*>(counts8 + parity * 8);
+                const unsigned long long low = all & below_mask;
+                total = (int)(__vsadu4((unsigned)all, 0u) + __vsadu4((unsigned)(all >> 32), 0u));
+                off = (int)(__vsadu4((unsigned)low, 0u) + __vsadu4((unsigned)(low >> 32), 0u)) +
+                      __popc(ballot & ((1u << lane) - 1u));
+                parity ^= 1;
+            } else
+#endif
+            {
+                sc.sync();
+                off = 0;
+                total = acc;
+            }
+            if (sweep) gen += (uint32_t)kSweep;
+            const int ord = have + off;
+            if (acc && ord < need) {
+                const double f = sqrt(-2.0 * log(r2) / r2);
+                const int j = ord / (kBootstrap / 2), smp = 2 * (ord % (kBootstrap / 2));
+                y[(size_t)j * kBootstrap + smp] = sh.loc[j] + sh.scl[j] * (f * x2);         // returned first
+                y[(size_t)j * kBootstrap + smp + 1] = sh.loc[j] + sh.scl[j] * (f * x1);     // the cached deviate
+            }
+            if (have + total >= need) {
+                if (acc && ord == need - 1) sh.ctl[0] = sc.tid + 1;
+                sc.sync();
+                used += 4u * (uint32_t)sh.ctl[0];
+                have = need;
+                sc.sync();
+            } else {
+                have += total;
+                used += 4u * (uint32_t)round;
+            }
+        }
+        used_total += (unsigned long long)(used - used_at_start);
+        sc.sync();
+
+        // ---- QR of the column-normalised Vandermonde matrix (np.polyfit: lhs /= sqrt((lhs*lhs).sum(0)))
+        // column k of the design holds x^(order-k) as np.vander does
+        for (int g = sc.tid; g < n; g += sc.size()) {
+            const double x = (double)((int)sh.rows[g] + spatial_floor);
+            double pw = 1.0;
+            for (int k = p - 1; k >= 0; --k) { sh.q[(size_t)g * kMaxPoly + k] = pw; pw *= x; }
+        }
+        sc.sync();
+        for (int k = 0; k < p; ++k) {
+            double part = 0.0;
+            for (int g = sc.tid; g < n; g += sc.size()) { double t = sh.q[(size_t)g * kMaxPoly + k]; part += t * t; }
+            double nrm = sqrt(scope_dsum(sc, part, sh.red));
+            if (sc.tid == 0) sh.colscale[k] = nrm;
+            for (int g = sc.tid; g < n; g += sc.size()) sh.q[(size_t)g * kMaxPoly + k] /= nrm;
+            sc.sync();
+        }
+        for (int k = 0; k < p; ++k) {
+            double part = 0.0;
+            for (int g = sc.tid; g < n; g += sc.size()) { double t = sh.q[(size_t)g * kMaxPoly + k]; part += t * t; }
+            double rkk = sqrt(scope_dsum(sc, part, sh.red));
+            if (sc.tid == 0) sh.rmat[k * kMaxPoly + k] = rkk;
+            for (int g = sc.tid; g < n; g += sc.size()) sh.q[(size_t)g * kMaxPoly + k] /= rkk;
+            sc.sync();
+            for (int j2 = k + 1; j2 < p; ++j2) {
+                part = 0.0;
+                for (int g = sc.tid; g < n; g += sc.size()) part += sh.q[(size_t)g * kMaxPoly + k] * sh.q[(size_t)g * kMaxPoly + j2];
+                double rkj = scope_dsum(sc, part, sh.red);
+                if (sc.tid == 0) sh.rmat[k * kMaxPoly + j2] = rkj;
+                for (int g = sc.tid; g < n; g += sc.size()) sh.q[(size_t)g * kMaxPoly + j2] -= rkj * sh.q[(size_t)g * kMaxPoly + k];
+                sc.sync();
+            }
+        }
+        // ---- one projection + back-substitution per bootstrap sample
+        for (int smp = sc.tid; smp < kBootstrap; smp += sc.size()) {
+            double z[kMaxPoly], cf[kMaxPoly];
+            for (int k = 0; k < p; ++k) z[k] = 0.0;
+            for (int g = 0; g < n; ++g) {
+                const double yv = y[(size_t)g * kBootstrap + smp];
+                for (int k = 0; k < p; ++k) z[k] = fma(sh.q[(size_t)g * kMaxPoly + k], yv, z[k]);
+            }
+            for (int k = p - 1; k >= 0; --k) {
+                double acc2 = z[k];
+                for (int j2 = k + 1; j2 < p; ++j2) acc2 -= sh.rmat[k * kMaxPoly + j2] * cf[j2];
+                cf[k] = acc2 / sh.rmat[k * kMaxPoly + k];
+            }
+            // un-scale and flip to ascending powers (sky.py:230)
+            for (int k = 0; k < p; ++k) sh.coef[smp * kMaxPoly + (p - 1 - k)] = cf[k] / sh.colscale[k];
+        }
+        sc.sync();
+        // ---- per spatial pixel: median and std over the 100 polynomial values (sky.py:231-239)
+#if defined(__CUDA_ARCH__)
+        const int nwarp = (sc.size() + 31) >> 5;
+        const int wid = sc.size() > 1 ? warp : 0, ln = sc.size() > 1 ? lane : 0, lanes = sc.size() > 1 ? 32 : 1;
+#else
+        const int nwarp = 1, wid = 0, ln = 0, lanes = 1;
+#endif
+        double* vals = sh.samples + (size_t)wid * kBootstrap;
+        for (int px = wid; px < nspat; px += nwarp) {
+            const double x = (double)(px + spatial_floor);
+            for (int smp = ln; smp < kBootstrap; smp += lanes) {
+                double acc2 = 0.0, pw = 1.0;
+                for (int k = 0; k < p; ++k) { acc2 += pw * sh.coef[smp * kMaxPoly + k]; pw *= x; }
+                vals[smp] = acc2;
+            }
+#if defined(__CUDA_ARCH__)
+            __syncwarp();
+#endif
+            // np.median of 100: mean of the order statistics 49 and 50
+            double m1 = 0.0, m2 = 0.0, psum = 0.0;
+            for (int e = ln; e < kBootstrap; e += lanes) {
+                const double v = vals[e];
+                int rank = 0;
+                for (int j2 = 0; j2 < kBootstrap; ++j2) { const double o = vals[j2]; rank += (o < v) || (o == v && j2 < e); }
+                if (rank == 49) m1 = v;
+                if (rank == 50) m2 = v;
+                psum += v;
+            }
+            double mean;
+#if defined(__CUDA_ARCH__)
+            if (sc.size() > 1) {
+                for (int o = 16; o > 0; o >>= 1) {
+                    m1 += __shfl_xor_sync(0xffffffffu, m1, o);      // exactly one lane holds each (others 0)
+                    m2 += __shfl_xor_sync(0xffffffffu, m2, o);
+                    psum += __shfl_xor_sync(0xffffffffu, psum, o);
+                }
+            }
+#endif
+            mean = psum / (double)kBootstrap;
+            double sq = 0.0;
+            for (int e = ln; e < kBootstrap; e += lanes) { const double d = vals[e] - mean; sq += d * d; }
+#if defined(__CUDA_ARCH__)
+            if (sc.size() > 1)
+                for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+#endif
+            if (ln == 0) {
+                model[(size_t)px * ndisp + c] = (m1 + m2) * 0.5;
+                model_err[(size_t)px * ndisp + c] = sqrt(sq / (double)kBootstrap);
+            }
+#if defined(__CUDA_ARCH__)
+            __syncwarp();
+#endif
+        }
+        sc.sync();
+    }
+
+    const unsigned long long block = (used_total > 0) ? ((used_total - 1) / kMtN) * kMtN : 0;
+    const uint32_t into_block = (uint32_t)(used_total - block);
+    const uint32_t block32 = used - into_block;
+    while ((uint32_t)(gen - block32) < (uint32_t)kMtN) {
+        for (int j = sc.tid; j < kSweep; j += sc.size()) {
+            const uint32_t w = gen + (uint32_t)j;
+            ring[w & (kRing - 1)] = mt_mix(ring[(w - kMtN) & (kRing - 1)], ring[(w - kMtN + 1) & (kRing - 1)],
+                                           ring[(w - kSweep) & (kRing - 1)]);
+        }
+        gen += (uint32_t)kSweep;
+        sc.sync();
+    }
+    sc.sync();
+    for (int i = sc.tid; i < kMtN; i += sc.size()) state[i] = ring[(block32 + (uint32_t)i) & (kRing - 1)];
+    if (sc.tid == 0) state[kMtN] = into_block;
+    sc.sync();
+}
+
+// sky.py:375-378 for a column with a per-pixel model (order > 0), then the chip-gap re-marking
+MOTES_HD void sky_apply_column_poly(double* data, double* errs, int nspat, int ndisp, int c, int flag,
+                                    const double* model, const double* model_err) {
+    int lt = 0, eq = 0, n = 0;
+    double max_lt = -INFINITY, min_gt = INFINITY;
+    for (int r = 0; r < nspat; ++r) {
+        size_t g = (size_t)r * ndisp + c;
+        double d = data[g];
+        if (flag == kSkyModelled) {
+            d = d - model[g];
+            data[g] = d;
+            double e = errs[g], me = model_err[g];
+            errs[g] = sqrt((e * e) + (me * me));
+        }
+        if (d == d) {
+            ++n;
+            if (d < 0.0) { ++lt; if (d > max_lt) max_lt = d; }
+            else if (d == 0.0) ++eq;
+            else if (d < min_gt) min_gt = d;
+        }
+    }
+    if (median_equals(0.0, n, lt, eq, max_lt, min_gt))
+        for (int r = 0; r < nspat; ++r) data[(size_t)r * ndisp + c] += 1.0;
+}
+
 // ---- 3. subtraction, error propagation and chip-gap re-marking (one thread per column) ------
 // sky.py:375-378 and :396-397.
 MOTES_HD void sky_apply_column(double* data, double* errs, int nspat, int ndisp, int c, int flag, double sky,

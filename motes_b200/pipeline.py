@@ -105,6 +105,8 @@ def run_frames(data, errs, qual, args, seeing, pixel_resolution, seeds=None, rng
     result = {}
     for name in names:
         shape, dtype = OUTPUT_SHAPES[name](F, nspat, ndisp, cap)
+        if name in ("sky_model", "sky_uncertainty") and p.sky_order > 0:
+            shape = (F, nspat, ndisp)
         arr = np.zeros(shape, dtype=dtype)
         result[name] = arr
         setattr(out_struct, name, arr.ctypes.data)
@@ -155,7 +157,7 @@ def run_frame(frame_dict, axes_dict, header_parameters, args, seed=None):
         out.update({
             "sky_bins": np.column_stack([res["sky_bins"][0, :ns].astype(np.float64), res["sky_bin_snr"][0, :ns]]),
             "sky_params": res["sky_params"][0, :ns], "sky_limits": res["sky_limits"][0],
-            "sky_model": res["sky_model"][0][modelled], "sky_uncertainty": res["sky_uncertainty"][0][modelled],
+            "sky_model": res["sky_model"][0][..., modelled], "sky_uncertainty": res["sky_uncertainty"][0][..., modelled],
             "sky_flag": res["sky_flag"][0],
         })
     header_parameters["seeing"] = out["seeing_px"]

@@ -46,9 +46,13 @@ def subtract_sky(background_spatial_lo_limit, background_spatial_hi_limit, frame
     nspat, ndisp = data.shape
     lo = _lib.f64(background_spatial_lo_limit).copy()
     hi = _lib.f64(background_spatial_hi_limit).copy()
-    sky, sky_err = np.zeros(ndisp), np.zeros(ndisp)
+    sky_shape = (ndisp,) if order == 0 else (nspat, ndisp)
+    sky, sky_err = np.zeros(sky_shape), np.zeros(sky_shape)
     flag, n_sky, n_good = (np.zeros(ndisp, dtype=np.int32) for _ in range(3))
     state, rest = _take_global_rng()
+    if order > 0 and rest[1]:
+        raise ValueError("np.random holds a cached Gaussian deviate (has_gauss=1); call np.random.seed() or draw one "
+                         "np.random.normal() before a polynomial sky fit so the device can replay the stream")
     with h.lock:
         rc = _lib.lib.motes_sky_subtract_host(
             h.raw, _lib.ptr(data), _lib.ptr(errs), nspat, ndisp, _lib.ptr(lo), _lib.ptr(hi),
@@ -72,8 +76,12 @@ def subtract_sky(background_spatial_lo_limit, background_spatial_hi_limit, frame
         frame_dict["data"] = data
         frame_dict["errs"] = errs
     modelled = flag == 0
-    frame_dict["sky_model"] = np.tile(sky[modelled], (nspat, 1))          # sky.py:383-388
-    frame_dict["sky_uncertainty"] = np.tile(sky_err[modelled], (nspat, 1))
+    if order == 0:
+        frame_dict["sky_model"] = np.tile(sky[modelled], (nspat, 1))          # sky.py:383-388
+        frame_dict["sky_uncertainty"] = np.tile(sky_err[modelled], (nspat, 1))
+    else:
+        frame_dict["sky_model"] = np.ascontiguousarray(sky[:, modelled])      # sky.py:390-391
+        frame_dict["sky_uncertainty"] = np.ascontiguousarray(sky_err[:, modelled])
     if trace is not None:
         trace.update(n_sky=n_sky, n_good=n_good, flag=flag, sky=sky, sky_err=sky_err)
     return frame_dict

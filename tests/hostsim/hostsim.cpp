@@ -100,3 +100,41 @@ extern "C" int hostsim_sky_median(double* data, double* errs, int nspat, int ndi
 }
 
 extern "C" void hostsim_mt_seed(uint32_t* mt, uint32_t seed) { motes::mt_seed(mt, seed); }
+
+// Polynomial-order sky subtraction of one frame (sky.sky_polynomial) on the host simulation.
+extern "C" int hostsim_sky_poly(double* data, double* errs, int nspat, int ndisp, double* lim_lo, double* lim_hi,
+                                int spatial_floor, int order, uint32_t* mt, int* pos, double* model, double* model_err,
+                                int32_t* flag, int32_t* n_good) {
+    motes::SeqScope sc;
+    std::vector<double> sorted((size_t)ndisp * nspat), column(nspat);
+    std::vector<uint16_t> rank_of((size_t)ndisp * nspat), good_row((size_t)ndisp * nspat);
+    std::vector<unsigned long long> keys(nspat);
+    std::vector<int32_t> n_sky(ndisp);
+    uint32_t hist[256];
+    unsigned long long cell;
+    int icell;
+    for (int c = 0; c < ndisp; ++c) {
+        for (int r = 0; r < nspat; ++r) column[r] = data[(size_t)r * ndisp + c];
+        motes::sky_prepare_column(sc, column.data(), 1, nspat, lim_lo + c, lim_hi + c, spatial_floor, n_sky.data() + c,
+                                  n_good + c, flag + c, sorted.data() + (size_t)c * nspat,
+                                  rank_of.data() + (size_t)c * nspat, good_row.data() + (size_t)c * nspat, keys.data(),
+                                  hist, &cell, &icell);
+        if (flag[c] == motes::kSkyNoPixels) return -4;
+    }
+    std::vector<uint32_t> ring(motes::kRing), counts(16), state(625);
+    std::vector<double> q((size_t)nspat * motes::kMaxPoly), rmat(36), colscale(6), coef(600), loc(nspat), scl(nspat), red(40),
+        samples(100), y((size_t)100 * nspat);
+    std::vector<uint16_t> rows(nspat);
+    int ctl[4];
+    for (int i = 0; i < 624; ++i) state[i] = mt[i];
+    state[624] = (uint32_t)*pos;
+    motes::PolyShared sh{ring.data(), counts.data(), ctl, q.data(), rmat.data(), colscale.data(), coef.data(), loc.data(),
+                         scl.data(), red.data(), samples.data(), rows.data()};
+    motes::sky_bootstrap_poly_frame(sc, state.data(), ndisp, nspat, ndisp, order, spatial_floor, errs, n_good, flag,
+                                    sorted.data(), rank_of.data(), good_row.data(), (size_t)nspat, y.data(), model,
+                                    model_err, sh);
+    for (int i = 0; i < 624; ++i) mt[i] = state[i];
+    *pos = (int)state[624];
+    for (int c = 0; c < ndisp; ++c) motes::sky_apply_column_poly(data, errs, nspat, ndisp, c, flag[c], model, model_err);
+    return 0;
+}

@@ -89,3 +89,23 @@ def test_sky_without_sky_pixels_raises_runtime_error():
     n = axes["dispersion_axis_length"]
     with pytest.raises(RuntimeError):
         sky.subtract_sky(np.full(n, -5.0), np.full(n, 1e9), frame, axes, synth.default_args(), header, "x")
+
+
+def test_polynomial_sky_subtraction_matches_reference():
+    """sky_order = 2 (sky.sky_polynomial): same Gaussian draws from np.random's stream, QR polyfit."""
+    from motes_b200 import sky
+    from oracle import motes_oracle as mo
+    meta, g = load_golden("t1_sky2")
+    frame, axes, header, args = golden_inputs(meta)
+    ref = mo.run_frame(copy.deepcopy(frame), axes, dict(header), args, seed=meta["rng_seed"])
+    after = np.random.get_state()
+    lo, hi = (a.copy() for a in ref["sky_limits_unclamped"])
+    fd = {"data": frame["data"].copy(), "errs": frame["errs"].copy(), "qual": frame["qual"]}
+    np.random.seed(meta["rng_seed"])
+    fd = sky.subtract_sky(lo, hi, fd, axes, args, header, "synthetic")
+    assert fd["sky_model"].shape == g["sky_model"].shape
+    assert np.allclose(fd["sky_model"], g["sky_model"], rtol=1e-10, atol=0)
+    assert np.allclose(fd["sky_uncertainty"], g["sky_uncertainty"], rtol=1e-8, atol=0)
+    assert np.allclose(fd["data"], ref["data_after"], rtol=0, atol=1e-9 * np.abs(g["sky_model"]).max())
+    mine = np.random.get_state()
+    assert mine[2] == after[2] and np.array_equal(mine[1], after[1])

@@ -147,3 +147,37 @@ def test_mt_seed_matches_numpy(hostsim):
     hostsim.hostsim_mt_seed(mt.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)), ctypes.c_uint32(1234))
     np.random.seed(1234)
     assert np.array_equal(mt, np.random.get_state()[1])
+
+
+def test_polynomial_sky_matches_reference_within_tolerance(hostsim):
+    """sky_order = 2: same Gaussian draws (numpy legacy polar method on the MT19937 stream), QR polyfit
+    instead of LAPACK gelsd -> agreement far inside the flux tolerance, and the same RNG end state."""
+    import copy
+    meta, g = load_golden("t1_sky2")
+    frame, axes, header, args = golden_inputs(meta)
+    out = mo.run_frame(copy.deepcopy(frame), axes, dict(header), args, seed=meta["rng_seed"])
+    after = np.random.get_state()
+    lo, hi = (np.ascontiguousarray(a).copy() for a in out["sky_limits_unclamped"])
+    data, errs = np.ascontiguousarray(frame["data"]).copy(), np.ascontiguousarray(frame["errs"]).copy()
+    nspat, ndisp = data.shape
+    np.random.seed(meta["rng_seed"])
+    state = np.random.get_state()
+    u32p = ctypes.POINTER(ctypes.c_uint32)
+    mt = np.ascontiguousarray(state[1], dtype=np.uint32).copy()
+    pos = ctypes.c_int(int(state[2]))
+    model, model_err = np.zeros((nspat, ndisp)), np.zeros((nspat, ndisp))
+    flag, n_good = np.zeros(ndisp, dtype=np.int32), np.zeros(ndisp, dtype=np.int32)
+    rc = hostsim.hostsim_sky_poly(data.ctypes.data_as(dp), errs.ctypes.data_as(dp), nspat, ndisp, lo.ctypes.data_as(dp),
+                                  hi.ctypes.data_as(dp), int(axes["data_spatial_floor"]), int(args.sky_order),
+                                  mt.ctypes.data_as(u32p), ctypes.byref(pos), model.ctypes.data_as(dp),
+                                  model_err.ctypes.data_as(dp), flag.ctypes.data_as(ip), n_good.ctypes.data_as(ip))
+    assert rc == 0
+    modelled = flag == 0
+    assert np.array_equal(n_good, out["sky_n_good"])
+    ref_model, ref_err = g["sky_model"], g["sky_uncertainty"]          # (nspat, n_modelled)
+    assert ref_model.shape == (nspat, modelled.sum())
+    assert np.allclose(model[:, modelled], ref_model, rtol=1e-10, atol=0)
+    assert np.allclose(model_err[:, modelled], ref_err, rtol=1e-8, atol=0)
+    assert np.allclose(data, out["data_after"], rtol=0, atol=1e-9 * np.abs(ref_model).max())
+    assert np.allclose(errs, out["errs_after"], rtol=1e-10)
+    assert pos.value == after[2] and np.array_equal(mt, after[1])
