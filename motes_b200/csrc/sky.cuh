@@ -158,9 +158,12 @@ MOTES_HD void sky_prepare_column(const Scope& sc, const double* col, int st, int
 //
 // One loop iteration = one barrier: every thread (a) produces a word of the next sweep and
 // (b) tests one pending output of the current column; after the barrier the per-warp accept
-// counts give every accepted draw its ordinal k in the stream order, hence its bootstrap sample
-// k % 100 (np.random.choice fills its (n, 100) index array row-major), and the draw is counted
-// into that sample's rank histogram.
+// counts give every accepted draw its ordinal k in the stream order, hence its place in numpy's
+// row-major (n, 100) index array: pixel slot k / 100 of bootstrap sample k % 100.  Every slot is
+// written exactly once, with the RANK of the drawn pixel, by a plain 16-bit shared-memory store
+// (no atomics, nothing to clear between columns).  A sample's median is then the median of its n
+// ranks, found by a bitwise binary search with warp-wide counts, and looked up in the sorted
+// good-pixel values.
 constexpr int kRing = 2048;          // > 624 (block) + 2*227 (look-ahead) + 256 (round), power of two
 constexpr int kSweep = kMtN - kMtM;      // 227
 
@@ -168,7 +171,7 @@ struct BootShared {
     uint32_t* ring;      // kRing words
     uint32_t* counts;    // 2 x 32 per-warp accept counts (double buffered)
     int* ctl;            // 4 ints
-    uint32_t* hist;      // 100 rows x row_words: 16-bit counters, sample-major
+    uint32_t* hist;      // 100 rows x row_words words: per sample, the ranks of its n drawn pixels (uint16)
     uint16_t* ranks;     // max_good
     double* meds;        // 100
     double* sq;          // 100
@@ -233,7 +236,7 @@ MOTES_HD void sky_bootstrap_frame(const Scope& sc, uint32_t* state /* 625 words,
         }
         if (n > 1) {
             const int rw = boot_row_words(n);
-            for (int i = sc.tid; i < kBootstrap * rw; i += sc.size()) sh.hist[i] = 0;
+            uint16_t* slots = reinterpret_cast<uint16_t*>(sh.hist);
             for (int i = sc.tid; i < n; i += sc.size()) sh.ranks[i] = rank_of[(size_t)c * cs + i];
             sc.sync();
             const int need = n * kBootstrap;
@@ -283,9 +286,8 @@ MOTES_HD void sky_bootstrap_frame(const Scope& sc, uint32_t* state /* 625 words,
                 if (sweep) gen += (uint32_t)kSweep;
                 const int ord = have + off;
                 if (acc && ord < need) {
-                    const int smp = ord % kBootstrap;                  // row-major (pixel, sample) fill
-                    const int rk = (int)sh.ranks[v];
-                    sc.add(&sh.hist[smp * rw + (rk >> 1)], 1u << (16 * (rk & 1)));
+                    const int pix = ord / kBootstrap, smp = ord - pix * kBootstrap;     // row-major (pixel, sample) fill
+                    slots[smp * (2 * rw) + pix] = sh.ranks[v];
                 }
                 if (have + total >= need) {
                     // the accept with ordinal need-1 is the column's last draw; later outputs of this
@@ -301,22 +303,46 @@ MOTES_HD void sky_bootstrap_frame(const Scope& sc, uint32_t* state /* 625 words,
                 }
             }
             used_total += (unsigned long long)(used - used_at_start);
-            // median of every bootstrap sample from its rank histogram
+            // median of every bootstrap sample: bitwise binary search over its n ranks
             sc.sync();
-            const int k1 = (n - 1) / 2, k2 = n / 2;
-            for (int smp = sc.tid; smp < kBootstrap; smp += sc.size()) {
-                const uint32_t* row = sh.hist + smp * rw;
-                int cum = 0, r1 = -1, r2 = -1;
-                for (int wd = 0; wd < rw && r2 < 0; ++wd) {
-                    uint32_t pair = row[wd];
-                    for (int half = 0; half < 2; ++half) {
-                        cum += (int)((pair >> (16 * half)) & 0xffffu);
-                        int r = 2 * wd + half;
-                        if (r1 < 0 && cum > k1) r1 = r;
-                        if (r2 < 0 && cum > k2) r2 = r;
+            {
+                const int k1 = (n - 1) / 2, k2 = n / 2;
+                int nbits = 1;
+                while ((1 << nbits) < n) ++nbits;
+#if defined(__CUDA_ARCH__)
+                const bool wide = sc.size() >= 32;
+                const int g_id = wide ? warp : 0, g_n = wide ? (sc.size() >> 5) : 1;
+                const int l_id = wide ? lane : 0, l_n = wide ? 32 : 1;
+#else
+                const int g_id = 0, g_n = 1, l_id = 0, l_n = 1;
+#endif
+                for (int smp = g_id; smp < kBootstrap; smp += g_n) {
+                    const uint16_t* row = slots + smp * (2 * rw);
+                    int x1 = 0;
+                    for (int bit = nbits - 1; bit >= 0; --bit) {
+                        const int cand = x1 | (1 << bit);
+                        int cnt = 0;
+                        for (int j = l_id; j < n; j += l_n) cnt += ((int)row[j] < cand);
+#if defined(__CUDA_ARCH__)
+                        if (wide) cnt = __reduce_add_sync(0xffffffffu, cnt);
+#endif
+                        if (cnt <= k1) x1 = cand;
                     }
+                    int x2 = x1;
+                    if (k2 != k1) {
+                        int le = 0, nxt = 0x7fffffff;
+                        for (int j = l_id; j < n; j += l_n) {
+                            const int r = (int)row[j];
+                            le += (r <= x1);
+                            if (r > x1 && r < nxt) nxt = r;
+                        }
+#if defined(__CUDA_ARCH__)
+                        if (wide) { le = __reduce_add_sync(0xffffffffu, le); nxt = __reduce_min_sync(0xffffffffu, nxt); }
+#endif
+                        if (le <= k2) x2 = nxt;
+                    }
+                    if (l_id == 0) sh.meds[smp] = (k1 == k2) ? srt[x1] : (srt[x1] + srt[x2]) * 0.5;
                 }
-                sh.meds[smp] = (k1 == k2) ? srt[r1] : (srt[r1] + srt[r2]) * 0.5;
             }
         } else {
             for (int smp = sc.tid; smp < kBootstrap; smp += sc.size()) sh.meds[smp] = srt[0];
