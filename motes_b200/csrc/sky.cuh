@@ -150,8 +150,8 @@ MOTES_HD void sky_prepare_column(const Scope& sc, const double* col, int st, int
 }
 
 // ---- 2. bootstrap over the columns of one frame ---------------------------------------------
-// The generator is kept as a ring of the last 2048 state words indexed by absolute stream
-// position n (slot n & 2047): word n = mix(word n-624, word n-623, word n-397+... i.e. n-227),
+// The generator is kept as a ring of the last 4096 state words indexed by absolute stream
+// position n (slot n & 4095): word n = mix(word n-624, word n-623, word n-397+... i.e. n-227),
 // so any 227 consecutive new words are independent of each other and are produced by one
 // parallel sweep.  A numpy RandomState (624 words + position) maps to words [0, 624) with
 // `used` = position, and back (the block of 624 that holds the last consumed word).
@@ -164,12 +164,14 @@ MOTES_HD void sky_prepare_column(const Scope& sc, const double* col, int st, int
 // (no atomics, nothing to clear between columns).  A sample's median is then the median of its n
 // ranks, found by a bitwise binary search with warp-wide counts, and looked up in the sorted
 // good-pixel values.
-constexpr int kRing = 2048;          // > 624 (block) + 2*227 (look-ahead) + 256 (round), power of two
+constexpr int kRing = 4096;          // > 624 (block) + kSlabs*256 (round) + 2*227 (look-ahead), power of two
+constexpr int kSlabs = 4;            // outputs tested per thread and barrier
+constexpr int kPackWords = 8;        // packed median search: up to 64 * 8 = 512 ranks per sample
 constexpr int kSweep = kMtN - kMtM;      // 227
 
 struct BootShared {
     uint32_t* ring;      // kRing words
-    uint32_t* counts;    // 2 x 32 per-warp accept counts (double buffered)
+    uint32_t* counts;    // 2 x 32 bytes: per-(slab, warp) accept counts, double buffered (16-byte aligned)
     int* ctl;            // 4 ints
     uint32_t* hist;      // 100 rows x row_words words: per sample, the ranks of its n drawn pixels (uint16)
     uint16_t* ranks;     // max_good
@@ -245,61 +247,76 @@ MOTES_HD void sky_bootstrap_frame(const Scope& sc, uint32_t* state /* 625 words,
             const uint32_t used_at_start = used;
             int have = 0;
             while (have < need) {
-                // (a) keep at least one round of outputs ahead
-                const uint32_t pending = gen - used;
-                const bool sweep = pending <= (uint32_t)kSweep;
-                if (sweep) {
+                // (a) generation: kSlabs outputs per thread must be pending; one barrier per 227-word sweep
+                const uint32_t want = (uint32_t)(kSlabs * sc.size());
+                while ((uint32_t)(gen - used) < want) {
                     for (int j = sc.tid; j < kSweep; j += sc.size()) {
                         const uint32_t w = gen + (uint32_t)j;
                         ring[w & (kRing - 1)] = mt_mix(ring[(w - kMtN) & (kRing - 1)], ring[(w - kMtN + 1) & (kRing - 1)],
                                                        ring[(w - kSweep) & (kRing - 1)]);
                     }
+                    gen += (uint32_t)kSweep;
+                    sc.sync();
                 }
-                // (b) test one pending output per thread
-                const int round = (int)(pending < (uint32_t)sc.size() ? pending : (uint32_t)sc.size());
-                int acc = 0;
-                uint32_t v = 0;
-                if (sc.tid < round) {
-                    v = mt_temper(ring[(used + (uint32_t)sc.tid) & (kRing - 1)]) & mask;
-                    acc = (v <= top);
+                // (b) test kSlabs pending outputs per thread; stream order is slab-major, then thread
+                int acc[kSlabs], off[kSlabs];
+                uint32_t v[kSlabs];
+#pragma unroll
+                for (int k = 0; k < kSlabs; ++k) {
+                    v[k] = mt_temper(ring[(used + (uint32_t)(k * sc.size() + sc.tid)) & (kRing - 1)]) & mask;
+                    acc[k] = (v[k] <= top);
                 }
-                int off, total;
+                int total = 0;
 #if defined(__CUDA_ARCH__)
                 if (sc.size() > 1) {
-                    // per-warp accept counts as bytes: one 64-bit load gives every thread all of them
-                    const unsigned ballot = __ballot_sync(0xffffffffu, acc);
-                    if (lane == 0) counts8[parity * 8 + warp] = (unsigned char)__popc(ballot);
+                    // per-(slab, warp) accept counts as bytes: 32 bytes give every thread all of them
+                    unsigned ballot[kSlabs];
+#pragma unroll
+                    for (int k = 0; k < kSlabs; ++k) {
+                        ballot[k] = __ballot_sync(0xffffffffu, acc[k]);
+                        if (lane == 0) counts8[parity * 32 + k * 8 + warp] = (unsigned char)__popc(ballot[k]);
+                    }
                     sc.sync();
-                    const unsigned long long all = *reinterpret_cast<const unsigned long long*>(counts8 + parity * 8);
-                    const unsigned long long low = all & below_mask;
-                    total = (int)(__vsadu4((unsigned)all, 0u) + __vsadu4((unsigned)(all >> 32), 0u));
-                    off = (int)(__vsadu4((unsigned)low, 0u) + __vsadu4((unsigned)(low >> 32), 0u)) +
-                          __popc(ballot & ((1u << lane) - 1u));
+                    const uint4 c4 = *reinterpret_cast<const uint4*>(counts8 + parity * 32);      // slabs 0,1
+                    const uint4 c5 = *reinterpret_cast<const uint4*>(counts8 + parity * 32 + 16); // slabs 2,3
+                    const unsigned lo_w[kSlabs] = {c4.x, c4.z, c5.x, c5.z}, hi_w[kSlabs] = {c4.y, c4.w, c5.y, c5.w};
+                    const unsigned lanes_below = (1u << lane) - 1u;
+#pragma unroll
+                    for (int k = 0; k < kSlabs; ++k) {
+                        const unsigned long long all = ((unsigned long long)hi_w[k] << 32) | lo_w[k];
+                        const unsigned long long low = all & below_mask;
+                        off[k] = total + (int)(__vsadu4((unsigned)low, 0u) + __vsadu4((unsigned)(low >> 32), 0u)) +
+                                 __popc(ballot[k] & lanes_below);
+                        total += (int)(__vsadu4(lo_w[k], 0u) + __vsadu4(hi_w[k], 0u));
+                    }
                     parity ^= 1;
                 } else
 #endif
                 {
-                    sc.sync();
-                    off = 0;
-                    total = acc;
+                    for (int k = 0; k < kSlabs; ++k) { off[k] = total; total += acc[k]; }
                 }
-                if (sweep) gen += (uint32_t)kSweep;
-                const int ord = have + off;
-                if (acc && ord < need) {
-                    const int pix = ord / kBootstrap, smp = ord - pix * kBootstrap;     // row-major (pixel, sample) fill
-                    slots[smp * (2 * rw) + pix] = sh.ranks[v];
+                // (c) every accepted draw fills its slot of numpy's row-major (pixel, sample) array
+                int last_at = 0;
+#pragma unroll
+                for (int k = 0; k < kSlabs; ++k) {
+                    const int ord = have + off[k];
+                    if (acc[k] && ord < need) {
+                        const int pix = ord / kBootstrap, smp = ord - pix * kBootstrap;
+                        slots[smp * (2 * rw) + pix] = sh.ranks[v[k]];
+                        if (ord == need - 1) last_at = k * sc.size() + sc.tid + 1;
+                    }
                 }
                 if (have + total >= need) {
                     // the accept with ordinal need-1 is the column's last draw; later outputs of this
                     // round belong to the next column and are tested again under its (mask, n)
-                    if (acc && ord == need - 1) sh.ctl[0] = sc.tid + 1;
+                    if (last_at) sh.ctl[0] = last_at;
                     sc.sync();
                     used += (uint32_t)sh.ctl[0];
                     have = need;
                     sc.sync();
                 } else {
                     have += total;
-                    used += (uint32_t)round;
+                    used += want;
                 }
             }
             used_total += (unsigned long long)(used - used_at_start);
@@ -309,14 +326,63 @@ MOTES_HD void sky_bootstrap_frame(const Scope& sc, uint32_t* state /* 625 words,
                 const int k1 = (n - 1) / 2, k2 = n / 2;
                 int nbits = 1;
                 while ((1 << nbits) < n) ++nbits;
+                bool done = false;
 #if defined(__CUDA_ARCH__)
+                if (sc.size() >= 32 && n <= 64 * kPackWords) {
+                    // packed path: a warp owns a sample, each lane keeps up to kPackWords rank pairs in
+                    // registers; "rank >= cand" for both halves of a word is bit 15 of (half + 0x8000 - cand)
+                    done = true;
+                    const int nwords = (n + 1) >> 1;
+                    for (int smp = warp; smp < kBootstrap; smp += (sc.size() >> 5)) {
+                        const uint32_t* row = sh.hist + smp * rw;
+                        uint32_t reg[kPackWords];
+#pragma unroll
+                        for (int t = 0; t < kPackWords; ++t) {
+                            const int wd = lane + 32 * t;
+                            uint32_t wv = 0x7fff7fffu;                      // padding: larger than any rank
+                            if (wd < nwords) {
+                                wv = row[wd];
+                                if (2 * wd + 1 >= n) wv = (wv & 0xffffu) | 0x7fff0000u;
+                            }
+                            reg[t] = wv;
+                        }
+                        const int slots_total = 64 * kPackWords;
+                        int x1 = 0;
+                        for (int bit = nbits - 1; bit >= 0; --bit) {
+                            const int cand = x1 | (1 << bit);
+                            const uint32_t kk = (uint32_t)(0x8000 - cand) * 0x00010001u;
+                            uint32_t ge = 0;
+#pragma unroll
+                            for (int t = 0; t < kPackWords; ++t) ge += ((reg[t] + kk) >> 15) & 0x00010001u;
+                            const int ge_all = __reduce_add_sync(0xffffffffu, (int)((ge & 0xffffu) + (ge >> 16)));
+                            if (slots_total - ge_all <= k1) x1 = cand;
+                        }
+                        int x2 = x1;
+                        if (k2 != k1) {
+                            const uint32_t kk = (uint32_t)(0x8000 - (x1 + 1)) * 0x00010001u;
+                            uint32_t ge = 0;
+                            int nxt = 0x7fff;
+#pragma unroll
+                            for (int t = 0; t < kPackWords; ++t) {
+                                ge += ((reg[t] + kk) >> 15) & 0x00010001u;
+                                const int h0 = (int)(reg[t] & 0xffffu), h1 = (int)(reg[t] >> 16);
+                                if (h0 > x1 && h0 < nxt) nxt = h0;
+                                if (h1 > x1 && h1 < nxt) nxt = h1;
+                            }
+                            const int le = slots_total - __reduce_add_sync(0xffffffffu, (int)((ge & 0xffffu) + (ge >> 16)));
+                            nxt = __reduce_min_sync(0xffffffffu, nxt);
+                            if (le <= k2) x2 = nxt;
+                        }
+                        if (lane == 0) sh.meds[smp] = (k1 == k2) ? srt[x1] : (srt[x1] + srt[x2]) * 0.5;
+                    }
+                }
                 const bool wide = sc.size() >= 32;
                 const int g_id = wide ? warp : 0, g_n = wide ? (sc.size() >> 5) : 1;
                 const int l_id = wide ? lane : 0, l_n = wide ? 32 : 1;
 #else
                 const int g_id = 0, g_n = 1, l_id = 0, l_n = 1;
 #endif
-                for (int smp = g_id; smp < kBootstrap; smp += g_n) {
+                for (int smp = g_id; smp < kBootstrap && !done; smp += g_n) {
                     const uint16_t* row = slots + smp * (2 * rw);
                     int x1 = 0;
                     for (int bit = nbits - 1; bit >= 0; --bit) {
