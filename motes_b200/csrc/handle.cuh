@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -91,6 +92,7 @@ struct motes_handle {
     motes::Scratch work[12];
     motes::Scratch counters;    // small zero-initialised control block
     bool profiling = false;
+    bool boot_classic = false;   // MOTES_B200_BOOTSTRAP=classic selects the single-role bootstrap kernel
     std::vector<motes::StageSpan> spans;
     double stage_ms[motes::ST_COUNT] = {0};
     long long stage_launches[motes::ST_COUNT] = {0};

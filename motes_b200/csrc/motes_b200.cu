@@ -266,11 +266,17 @@ static int stage_sky(motes_handle* h, Batch& b, double* data, double* errs, size
     }
     if (!poly) {
         smem = sky_boot_smem(b.nspat);
-        MOTES_CUDA(cudaFuncSetAttribute(sky_bootstrap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         {
             StageTimer timer(h, ST_SKY_BOOTSTRAP);
-            sky_bootstrap_kernel<<<b.F, kBootThreads, smem, h->stream>>>(rng, b.nspat, b.ndisp, b.n_good, b.sky_flag,
-                                                                         b.sorted, b.rank_of, b.sky, b.sky_err, b.st);
+            if (h->boot_classic) {
+                MOTES_CUDA(cudaFuncSetAttribute(sky_bootstrap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                sky_bootstrap_kernel<<<b.F, kBootThreads, smem, h->stream>>>(rng, b.nspat, b.ndisp, b.n_good, b.sky_flag,
+                                                                             b.sorted, b.rank_of, b.sky, b.sky_err, b.st);
+            } else {
+                MOTES_CUDA(cudaFuncSetAttribute(sky_bootstrap_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                sky_bootstrap_ws_kernel<<<b.F, kWsThreads, smem, h->stream>>>(rng, b.nspat, b.ndisp, b.n_good, b.sky_flag,
+                                                                             b.sorted, b.rank_of, b.sky, b.sky_err, b.st);
+            }
             MOTES_LAUNCHED(h);
         }
         StageTimer timer(h, ST_SKY_APPLY);
@@ -382,6 +388,8 @@ int motes_create(int device, motes_handle** out) {
     if (e != cudaSuccess) { delete h; return fail_cuda(e, "cudaGetDeviceProperties", __FILE__, __LINE__); }
     h->sm_count = prop.multiProcessorCount;
     h->smem_optin = prop.sharedMemPerBlockOptin;
+    const char* boot = getenv("MOTES_B200_BOOTSTRAP");       // "classic": single-role kernel (A/B timing)
+    h->boot_classic = boot && strcmp(boot, "classic") == 0;
     e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete h; return fail_cuda(e, "cudaStreamCreate", __FILE__, __LINE__); }
     *out = h;
