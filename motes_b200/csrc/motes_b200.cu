@@ -388,8 +388,9 @@ int motes_create(int device, motes_handle** out) {
     if (e != cudaSuccess) { delete h; return fail_cuda(e, "cudaGetDeviceProperties", __FILE__, __LINE__); }
     h->sm_count = prop.multiProcessorCount;
     h->smem_optin = prop.sharedMemPerBlockOptin;
-    const char* boot = getenv("MOTES_B200_BOOTSTRAP");       // "classic": single-role kernel (A/B timing)
-    h->boot_classic = boot && strcmp(boot, "classic") == 0;
+    // "ws": warp-specialised variant (A/B timing; measured slower on B200: 571 vs 288 ms per 128 frames)
+    const char* boot = getenv("MOTES_B200_BOOTSTRAP");
+    h->boot_classic = !(boot && strcmp(boot, "ws") == 0);
     e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete h; return fail_cuda(e, "cudaStreamCreate", __FILE__, __LINE__); }
     *out = h;
