@@ -32,6 +32,7 @@ extern "C" {
 #define MOTES_E_NOMEM (-3)     /* device allocation failed */
 #define MOTES_E_NOSKY (-4)     /* a column has no sky pixel: reference raises RuntimeError (sky.py:323-335) */
 #define MOTES_E_FIT (-5)       /* a Moffat fit could not start: reference raises ValueError (scipy x0/bounds/residual checks) */
+#define MOTES_E_INTERNAL (-6)  /* a device-side invariant failed (e.g. the planned generator stream was too short) */
 
 /* per-fit status written by the fit kernels: scipy's termination codes 0..4, or */
 #define MOTES_FIT_X0_INFEASIBLE (-1)

@@ -17,7 +17,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmotes_b200.so")
 
-MOTES_OK, E_CUDA, E_ARG, E_NOMEM, E_NOSKY, E_FIT = 0, -1, -2, -3, -4, -5
+MOTES_OK, E_CUDA, E_ARG, E_NOMEM, E_NOSKY, E_FIT, E_INTERNAL = 0, -1, -2, -3, -4, -5, -6
 
 
 class MotesCudaError(RuntimeError):

@@ -76,7 +76,8 @@ struct Scratch {
 namespace motes {
 // Optional per-stage timing with CUDA events on the handle's stream (bench.py's roofline leg).
 enum Stage { ST_ROW_MEDIAN = 0, ST_MEDIAN_FIT, ST_COLUMN_STATS, ST_BINS, ST_BIN_PROFILES, ST_BIN_FITS, ST_LIMITS,
-             ST_SKY_PREPARE, ST_SKY_BOOTSTRAP, ST_SKY_APPLY, ST_EXTRACT, ST_COUNT };
+             ST_SKY_PREPARE, ST_SKY_BOOTSTRAP, ST_SKY_APPLY, ST_EXTRACT,
+             ST_BOOT_JUMP, ST_BOOT_STREAM, ST_BOOT_WALK, ST_BOOT_COLUMN, ST_COUNT };
 struct StageSpan { cudaEvent_t a, b; int stage; };
 }  // namespace motes
 
@@ -89,10 +90,13 @@ struct motes_handle {
     long long launches = 0;
     // scratch slots: host-API staging and per-stage work areas
     motes::Scratch stage[12];
-    motes::Scratch work[12];
+    motes::Scratch work[20];
     motes::Scratch counters;    // small zero-initialised control block
     bool profiling = false;
-    bool boot_classic = false;   // MOTES_B200_BOOTSTRAP=classic selects the single-role bootstrap kernel
+    int boot_mode = 0;           // MOTES_B200_BOOTSTRAP: 0 segmented (default), 1 classic (one CTA per frame), 2 warp-specialised
+    motes::Scratch jump_polys;   // device copy of the MT19937 jump polynomial table (mtjump.hpp)
+    bool jump_ready = false;
+    size_t stream_budget = 0;    // bytes the segmented bootstrap may use for generator streams (0 = auto)
     std::vector<motes::StageSpan> spans;
     double stage_ms[motes::ST_COUNT] = {0};
     long long stage_launches[motes::ST_COUNT] = {0};
@@ -112,8 +116,10 @@ struct StageTimer {
         idx = (int)h->spans.size() - 1;
         h->stage_launches[stage] += 1;
     }
-    ~StageTimer() {
+    void stop() {
         if (idx >= 0) cudaEventRecord(h->spans[idx].b, h->stream);
+        idx = -1;
     }
+    ~StageTimer() { stop(); }
 };
 }  // namespace motes

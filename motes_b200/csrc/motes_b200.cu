@@ -1,11 +1,14 @@
 // libmotes_b200.so: stage launchers and the C ABI declared in include/motes_b200.h.
 #include "handle.cuh"
 #include "kernels.cuh"
+#include "skyseg.cuh"
+#include "mtjump.hpp"
 
 namespace motes {
 
 // Work-area slots inside motes_handle::work
-enum WorkSlot { W_STATE = 0, W_F64, W_I32, W_U8, W_SORTED, W_RANKS, W_PROFILES, W_GOODROW, W_YSCRATCH, W_MODEL, W_MODELERR };
+enum WorkSlot { W_STATE = 0, W_F64, W_I32, W_U8, W_SORTED, W_RANKS, W_PROFILES, W_GOODROW, W_YSCRATCH, W_MODEL, W_MODELERR,
+                W_STREAM, W_WINDOWS, W_SNAPS, W_SEGI, W_SUBS };
 
 // Device-side working set of one batch.  All pointers are carved out of handle scratch.
 struct Batch {
@@ -248,6 +251,114 @@ static size_t sky_poly_smem(int nspat) {
             (size_t)(kBootThreads / 32) * kBootstrap) * 8 + kRing * 4 + 16 * 4 + 4 * 4 + (size_t)nspat * 2 + 64;
 }
 
+
+// Order-0 bootstrap with the frame's generator stream split across the GPU (skyseg.cuh).
+// *done = false when the layout does not fit (stream positions beyond 32 bits, no memory for even one
+// frame): the caller then falls back to the one-CTA-per-frame kernel, which has no such limits.
+static size_t sky_col_smem(int nspat) {
+    return (size_t)2 * kBootstrap * 8 + (size_t)kBootstrap * boot_row_words(nspat) * 4 + (size_t)nspat * 2 + 64;
+}
+
+static int stage_bootstrap_segmented(motes_handle* h, Batch& b, uint32_t* rng, bool* done) {
+    *done = false;
+    const JumpTable& table = jump_table();
+    if (!table.ok) return MOTES_OK;
+    unsigned long long p2 = 1;
+    while (p2 < (unsigned long long)b.nspat) p2 <<= 1;
+    const unsigned long long bound = 624ull + 100ull * (unsigned long long)b.ndisp * p2 + kSegSlack;
+    if (bound >= 0xff000000ull) return MOTES_OK;
+    const size_t col_smem = sky_col_smem(b.nspat);
+    if (col_smem > h->smem_optin) return MOTES_OK;
+    // per-frame footprint is dominated by the 16-bit stream: 2 bytes per generator word
+    size_t budget = h->stream_budget;
+    if (budget == 0) {
+        size_t free_b = 0, total_b = 0;
+        MOTES_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        free_b += h->work[W_STREAM].bytes + h->work[W_SNAPS].bytes + h->work[W_WINDOWS].bytes + h->work[W_SUBS].bytes;
+        budget = free_b / 2;
+    }
+    const size_t per_frame_est = (size_t)(bound * 2ull + bound / 26 + bound / 512 + (1u << 20));
+    int wave = (int)(budget / per_frame_est);
+    if (wave < 1) return MOTES_OK;
+    if (wave > b.F) wave = b.F;
+    const int waves = (b.F + wave - 1) / wave;
+    wave = (b.F + waves - 1) / waves;
+    // segment stride: enough CTAs to fill the machine, not more jumps than needed
+    SegLayout lay{};
+    const long long target = 8ll * h->sm_count;
+    int s = kSnapLog2;
+    while (s < 30 && (long long)wave * (long long)((bound + (1ull << s) - 1) >> s) > target) ++s;
+    lay.log2_stride = s;
+    lay.stride = 1u << s;
+    lay.segs = (int)((bound + lay.stride - 1) >> s);
+    const unsigned long long words = (unsigned long long)lay.segs << s;
+    lay.stream_len = words + 3ull * kWalkChunk;
+    lay.sub_len = (words >> kSubLog2) + 16;
+    lay.snaps = (int)(words >> kSnapLog2) + 1;
+    if (s + 10 > kJumpMaxLog2) return MOTES_OK;
+
+    if (!h->jump_ready) {
+        MOTES_TRY(h->jump_polys.ensure(table.words.size() * sizeof(uint32_t)));
+        MOTES_CUDA(cudaMemcpyAsync(h->jump_polys.ptr, table.words.data(), table.words.size() * sizeof(uint32_t),
+                                   cudaMemcpyHostToDevice, h->stream));
+        MOTES_CUDA(cudaStreamSynchronize(h->stream));
+        h->jump_ready = true;
+    }
+    MOTES_TRY(h->work[W_STREAM].ensure((size_t)wave * lay.stream_len * sizeof(uint16_t)));
+    MOTES_TRY(h->work[W_WINDOWS].ensure((size_t)wave * lay.segs * 624 * sizeof(uint32_t)));
+    MOTES_TRY(h->work[W_SNAPS].ensure((size_t)wave * lay.snaps * 624 * sizeof(uint32_t)));
+    MOTES_TRY(h->work[W_SUBS].ensure((size_t)wave * lay.sub_len * sizeof(uint32_t)));
+    MOTES_TRY(h->work[W_SEGI].ensure(((size_t)wave * 2 + (size_t)wave * b.ndisp * 2) * sizeof(uint32_t) + 256));
+    uint16_t* stream = h->work[W_STREAM].as<uint16_t>();
+    uint32_t* windows = h->work[W_WINDOWS].as<uint32_t>();
+    uint32_t* snaps = h->work[W_SNAPS].as<uint32_t>();
+    uint32_t* subs = h->work[W_SUBS].as<uint32_t>();
+    int32_t* seg_need = h->work[W_SEGI].as<int32_t>();
+    uint32_t* end_pos = reinterpret_cast<uint32_t*>(seg_need + wave);
+    uint32_t* col_start = end_pos + wave;
+    uint32_t* col_end = col_start + (size_t)wave * b.ndisp;
+    const uint32_t* polys = h->jump_polys.as<uint32_t>();
+    const size_t jump_smem = (size_t)(kJumpStreamWords + 624) * sizeof(uint32_t);
+    MOTES_CUDA(cudaFuncSetAttribute(mt_jump_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jump_smem));
+    MOTES_CUDA(cudaFuncSetAttribute(sky_column_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)col_smem));
+    const size_t walk_smem = (size_t)kWalkStages * kWalkChunkBytes;
+    MOTES_CUDA(cudaFuncSetAttribute(sky_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)walk_smem));
+
+    for (int f0 = 0; f0 < b.F; f0 += wave) {
+        const int nf = (b.F - f0 < wave) ? b.F - f0 : wave;
+        const size_t c0 = (size_t)f0 * b.ndisp;
+        uint32_t* rng_w = rng + (size_t)f0 * 625;
+        StageTimer t_jump(h, ST_BOOT_JUMP);
+        seg_plan_kernel<<<nf, 256, 0, h->stream>>>(rng_w, b.ndisp, b.n_good + c0, b.sky_flag + c0, lay, seg_need);
+        MOTES_LAUNCHED(h);
+        for (int r = 0; (1 << r) < lay.segs; ++r) {
+            const int count = ((1 << (r + 1)) <= lay.segs ? (1 << r) : lay.segs - (1 << r));
+            mt_jump_kernel<<<dim3(count, nf), kJumpThreads, jump_smem, h->stream>>>(
+                rng_w, windows, lay.segs, r, polys + (size_t)(s + r) * kJumpWords32, seg_need);
+            MOTES_LAUNCHED(h);
+        }
+        t_jump.stop();
+        StageTimer t_stream(h, ST_BOOT_STREAM);
+        mt_stream_kernel<<<dim3(lay.segs, nf), 256, 0, h->stream>>>(rng_w, windows, lay, seg_need, stream, snaps);
+        MOTES_LAUNCHED(h);
+        t_stream.stop();
+        StageTimer t_walk(h, ST_BOOT_WALK);
+        sky_walk_kernel<<<nf, kWalkThreads, walk_smem, h->stream>>>(stream, lay, rng_w, seg_need, b.ndisp, b.n_good + c0, b.sky_flag + c0,
+                                                   col_start, col_end, subs, end_pos, b.st + f0);
+        MOTES_LAUNCHED(h);
+        t_walk.stop();
+        StageTimer t_col(h, ST_BOOT_COLUMN);
+        sky_column_kernel<<<dim3(b.ndisp, nf), kColThreads, col_smem, h->stream>>>(
+            stream, lay, b.nspat, b.ndisp, b.n_good + c0, b.sky_flag + c0, b.sorted + c0 * b.nspat, b.rank_of + c0 * b.nspat,
+            col_start, col_end, subs, b.sky + c0, b.sky_err + c0, b.st + f0);
+        MOTES_LAUNCHED(h);
+        mt_export_kernel<<<nf, 256, 0, h->stream>>>(rng_w, snaps, lay, end_pos, b.st + f0);
+        MOTES_LAUNCHED(h);
+    }
+    *done = true;
+    return MOTES_OK;
+}
+
 static int stage_sky(motes_handle* h, Batch& b, double* data, double* errs, size_t frame_stride, double* limits,
                      const motes_params& p, uint32_t* rng) {
     if (p.sky_order < 0 || p.sky_order >= kMaxPoly) return fail_arg("sky_order must be 0..5");
@@ -265,19 +376,23 @@ static int stage_sky(motes_handle* h, Batch& b, double* data, double* errs, size
         MOTES_LAUNCHED(h);
     }
     if (!poly) {
-        smem = sky_boot_smem(b.nspat);
         {
-            StageTimer timer(h, ST_SKY_BOOTSTRAP);
-            if (h->boot_classic) {
-                MOTES_CUDA(cudaFuncSetAttribute(sky_bootstrap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                sky_bootstrap_kernel<<<b.F, kBootThreads, smem, h->stream>>>(rng, b.nspat, b.ndisp, b.n_good, b.sky_flag,
-                                                                             b.sorted, b.rank_of, b.sky, b.sky_err, b.st);
-            } else {
-                MOTES_CUDA(cudaFuncSetAttribute(sky_bootstrap_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                sky_bootstrap_ws_kernel<<<b.F, kWsThreads, smem, h->stream>>>(rng, b.nspat, b.ndisp, b.n_good, b.sky_flag,
-                                                                             b.sorted, b.rank_of, b.sky, b.sky_err, b.st);
+            bool done = false;
+            if (h->boot_mode == 0) MOTES_TRY(stage_bootstrap_segmented(h, b, rng, &done));
+            if (!done) {
+                StageTimer timer(h, ST_SKY_BOOTSTRAP);
+                smem = sky_boot_smem(b.nspat);
+                if (h->boot_mode != 2) {
+                    MOTES_CUDA(cudaFuncSetAttribute(sky_bootstrap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    sky_bootstrap_kernel<<<b.F, kBootThreads, smem, h->stream>>>(rng, b.nspat, b.ndisp, b.n_good, b.sky_flag,
+                                                                                 b.sorted, b.rank_of, b.sky, b.sky_err, b.st);
+                } else {
+                    MOTES_CUDA(cudaFuncSetAttribute(sky_bootstrap_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    sky_bootstrap_ws_kernel<<<b.F, kWsThreads, smem, h->stream>>>(rng, b.nspat, b.ndisp, b.n_good, b.sky_flag,
+                                                                                 b.sorted, b.rank_of, b.sky, b.sky_err, b.st);
+                }
+                MOTES_LAUNCHED(h);
             }
-            MOTES_LAUNCHED(h);
         }
         StageTimer timer(h, ST_SKY_APPLY);
         sky_apply_kernel<<<dim3((b.ndisp + 127) / 128, b.F), 128, 0, h->stream>>>(data, errs, frame_stride, b.nspat,
@@ -388,9 +503,11 @@ int motes_create(int device, motes_handle** out) {
     if (e != cudaSuccess) { delete h; return fail_cuda(e, "cudaGetDeviceProperties", __FILE__, __LINE__); }
     h->sm_count = prop.multiProcessorCount;
     h->smem_optin = prop.sharedMemPerBlockOptin;
-    // "ws": warp-specialised variant (A/B timing; measured slower on B200: 571 vs 288 ms per 128 frames)
+    // A/B switches: "classic" = one CTA walks a frame's whole stream, "ws" = its warp-specialised variant
     const char* boot = getenv("MOTES_B200_BOOTSTRAP");
-    h->boot_classic = !(boot && strcmp(boot, "ws") == 0);
+    h->boot_mode = (boot && strcmp(boot, "classic") == 0) ? 1 : (boot && strcmp(boot, "ws") == 0) ? 2 : 0;
+    const char* budget = getenv("MOTES_B200_STREAM_GB");
+    if (budget && atof(budget) > 0.0) h->stream_budget = (size_t)(atof(budget) * 1073741824.0);
     e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete h; return fail_cuda(e, "cudaStreamCreate", __FILE__, __LINE__); }
     *out = h;
@@ -404,6 +521,7 @@ int motes_destroy(motes_handle* h) {
     for (auto& s : h->stage) s.release();
     for (auto& s : h->work) s.release();
     h->counters.release();
+    h->jump_polys.release();
     if (h->owns_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return MOTES_OK;
@@ -441,7 +559,7 @@ int motes_profile_stage_count(void) { return ST_COUNT; }
 const char* motes_profile_stage_name(int stage) {
     static const char* names[ST_COUNT] = {"row_median", "median_fit", "column_stats", "snr_bins", "bin_profiles",
                                           "bin_fits", "limits", "sky_prepare", "sky_bootstrap", "sky_apply",
-                                          "extract"};
+                                          "extract", "boot_jump", "boot_stream", "boot_walk", "boot_column"};
     return (stage >= 0 && stage < ST_COUNT) ? names[stage] : "";
 }
 

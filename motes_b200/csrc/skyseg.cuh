@@ -1,0 +1,617 @@
+// Segmented replay of a frame's numpy MT19937 stream for the order-0 bootstrap sky
+// (sky.sky_median, /root/reference/src/motes/sky.py:17-43, called per column from
+// sky.subtract_sky :257-399).  Device only.
+//
+// The reference consumes ONE generator stream per frame, column after column, and the number of
+// words a column consumes depends on its own rejections - so a literal replay is a serial walk.
+// Here the walk is reduced to its irreducible part and everything else runs on the whole GPU:
+//
+//   plan     per frame: how much of the stream can be needed (sum over columns of 100 * (mask + 1)
+//            plus 2^20 words of slack, > 50 sigma of the rejection count);
+//   jump     generator windows at stream positions k * 2^s by polynomial jump-ahead (mtjump.hpp),
+//            doubling rounds: window(k) = g_{2^(s+r)}(T) window(k - 2^r);
+//   stream   one CTA per (frame, segment) runs the recurrence from its window and writes the low
+//            16 bits of every tempered output (all a masked-rejection draw of <= 65536 values
+//            looks at) to HBM, plus a raw 624-word snapshot every 2^16 words for the state export;
+//   walk     one CTA per frame scans the 16-bit stream once: for every column the position of its
+//            first draw and of its last accepted draw, and the accept count of the running column
+//            at every 2048-word boundary.  This is the only serial step (~2 bytes per word read);
+//   column   one CTA per (frame, column): every warp takes 2048-word pieces of the column's range,
+//            numbers the accepted draws with ballots (the piece's first ordinal comes from the walk),
+//            writes rank slots in numpy's row-major (pixel, sample) order into shared memory and
+//            reads the 100 sample medians off them; mean / std in numpy's summation order;
+//   export   numpy's RandomState after the frame: the 624-word block holding the last consumed
+//            word, regenerated from the nearest snapshot.
+#pragma once
+
+#include "sky.cuh"
+
+namespace motes {
+
+constexpr int kSnapLog2 = 16;                    // snapshot spacing (words)
+constexpr uint32_t kSnapStride = 1u << kSnapLog2;
+constexpr int kWalkChunk = 8192;                 // words per walk iteration (256 threads x 4 x 8)
+constexpr int kSubLog2 = 11;
+constexpr int kSubChunk = 1 << kSubLog2;         // granularity of the walk's running counts
+constexpr uint32_t kSegSlack = 1u << 20;
+constexpr int kJumpThreads = 640;
+constexpr int kJumpStreamWords = 19937 + 624 + 15;
+constexpr int kColThreads = 512;
+
+struct SegLayout {                 // per call, host-computed
+    int log2_stride;
+    uint32_t stride;               // words per segment
+    int segs;                      // segments allocated per frame (K)
+    unsigned long long stream_len; // 16-bit words per frame (padded for the walk's prefetch)
+    unsigned long long sub_len;    // running-count entries per frame
+    int snaps;                     // snapshots per frame
+};
+
+// ---- plan -------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+seg_plan_kernel(const uint32_t* __restrict__ rng, int ndisp, const int32_t* __restrict__ n_good,
+                const int32_t* __restrict__ flag, SegLayout lay, int32_t* __restrict__ seg_need) {
+    __shared__ unsigned long long part[8];
+    const int f = blockIdx.x;
+    unsigned long long acc = 0;
+    for (int c = threadIdx.x; c < ndisp; c += blockDim.x) {
+        const size_t col = (size_t)f * ndisp + c;
+        const int n = n_good[col];
+        if (flag[col] == kSkyModelled && n > 1) acc += 100ull * ((unsigned long long)rejection_mask((uint32_t)n) + 1ull);
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long total = rng[(size_t)f * 625 + 624];
+        for (int w = 0; w < 8; ++w) total += part[w];
+        total += kSegSlack;
+        unsigned long long need = (total + lay.stride - 1) >> lay.log2_stride;
+        if (need > (unsigned long long)lay.segs) need = lay.segs;
+        if (need < 1) need = 1;
+        seg_need[f] = (int32_t)need;
+    }
+}
+
+// ---- jump -------------------------------------------------------------------------------------
+// window(dst) = XOR over set coefficients c_i of the words [i, i + 624) of the stream that starts
+// at window(src).  Word 0 of a jumped window carries only its top bit (all the recurrence reads).
+__global__ void __launch_bounds__(kJumpThreads)
+mt_jump_kernel(const uint32_t* __restrict__ rng, uint32_t* __restrict__ windows, int segs, int round_log2,
+               const uint32_t* __restrict__ poly, const int32_t* __restrict__ seg_need) {
+    extern __shared__ __align__(16) uint32_t jump_smem[];
+    uint32_t* w = jump_smem;                          // kJumpStreamWords
+    uint32_t* coef = jump_smem + kJumpStreamWords;    // 624
+    const int f = blockIdx.y;
+    const int k = (1 << round_log2) + blockIdx.x;
+    if (k >= seg_need[f]) return;
+    const int src = k - (1 << round_log2);
+    const uint32_t* from = (src == 0) ? rng + (size_t)f * 625 : windows + ((size_t)f * segs + src) * 624;
+    for (int i = threadIdx.x; i < 624; i += blockDim.x) { w[i] = from[i]; coef[i] = poly[i]; }
+    __syncthreads();
+    for (int base = 624; base < 19937 + 624; base += kSweep) {
+        const int n = base + (int)threadIdx.x;
+        if ((int)threadIdx.x < kSweep && n < 19937 + 624) w[n] = mt_mix(w[n - 624], w[n - 623], w[n - kSweep]);
+        __syncthreads();
+    }
+    const int j = threadIdx.x;
+    if (j < 624) {
+        uint32_t acc = 0;
+        for (int iw = 0; iw < 624; ++iw) {
+            uint32_t cw = coef[iw];
+            const uint32_t* row = w + 32 * iw + j;
+            while (cw) {                               // uniform across the CTA
+                const int b = __ffs(cw) - 1;
+                cw &= cw - 1;
+                acc ^= row[b];
+            }
+        }
+        windows[((size_t)f * segs + k) * 624 + j] = acc;
+    }
+}
+
+// ---- stream -----------------------------------------------------------------------------------
+// Segment k of frame f: words (k L, (k+1) L] of the stream (segment 0 also the 624 state words),
+// tempered and truncated to 16 bits; raw snapshots of the generator window at multiples of 2^16.
+__global__ void __launch_bounds__(256)
+mt_stream_kernel(const uint32_t* __restrict__ rng, const uint32_t* __restrict__ windows, SegLayout lay,
+                 const int32_t* __restrict__ seg_need, uint16_t* __restrict__ stream, uint32_t* __restrict__ snaps) {
+    __shared__ uint32_t ring[kRing];
+    const int f = blockIdx.y, k = blockIdx.x;
+    if (k >= seg_need[f]) return;
+    const uint32_t base = (uint32_t)k << lay.log2_stride;
+    const uint32_t* from = (k == 0) ? rng + (size_t)f * 625 : windows + ((size_t)f * lay.segs + k) * 624;
+    uint16_t* out = stream + (size_t)f * lay.stream_len;
+    uint32_t* snap = snaps + (size_t)f * lay.snaps * 624;
+    for (int i = threadIdx.x; i < 624; i += blockDim.x) {
+        const uint32_t v = from[i];
+        ring[(base + i) & (kRing - 1)] = v;
+        if (k == 0 || i >= 1) out[base + i] = (uint16_t)mt_temper(v);     // word 0 of a jumped window is not a stream word
+        if (k == 0) snap[i] = v;
+    }
+    __syncthreads();
+    const uint32_t last_out = base + lay.stride;            // last stream position this segment writes
+    const uint32_t stop = last_out + 624;                   // words [base + 624, stop) are needed
+    uint32_t next_snap = ((base >> kSnapLog2) + 1) << kSnapLog2;
+    // Two words per thread and barrier: word n and word n + 227, whose "far" operand (n + 227 - 227)
+    // is the word just produced - it stays in a register, as does the far operand of the next round.
+    const uint32_t t = threadIdx.x;
+    uint32_t far = (t < (uint32_t)kSweep) ? ring[(base + 624 + t - kSweep) & (kRing - 1)] : 0u;
+    for (uint32_t gen = base + 624; gen < stop; gen += 2 * kSweep) {
+        if (t < (uint32_t)kSweep) {
+            const uint32_t n0 = gen + t, n1 = n0 + kSweep;
+            const uint32_t v0 = mt_mix(ring[(n0 - 624) & (kRing - 1)], ring[(n0 - 623) & (kRing - 1)], far);
+            const uint32_t v1 = mt_mix(ring[(n1 - 624) & (kRing - 1)], ring[(n1 - 623) & (kRing - 1)], v0);
+            ring[n0 & (kRing - 1)] = v0;
+            ring[n1 & (kRing - 1)] = v1;
+            if (n0 <= last_out) out[n0] = (uint16_t)mt_temper(v0);
+            if (n1 <= last_out) out[n1] = (uint16_t)mt_temper(v1);
+            far = v1;
+        }
+        __syncthreads();
+        const uint32_t have = gen + 2u * kSweep;                          // words below `have` exist
+        if (next_snap <= last_out && next_snap + 624 <= have) {
+            uint32_t* dst = snap + (size_t)(next_snap >> kSnapLog2) * 624;
+            for (int i = threadIdx.x; i < 624; i += blockDim.x) dst[i] = ring[(next_snap + i) & (kRing - 1)];
+            next_snap += kSnapStride;
+        }
+    }
+}
+
+// ---- walk -------------------------------------------------------------------------------------
+// Position bookkeeping of one frame.  The 16-bit stream is staged through a shared-memory ring by
+// TMA bulk copies (cp.async.bulk + mbarrier complete_tx): one CTA has to pull ~420 MB through one
+// SM, so ~200 KB are kept in flight to cover the HBM latency.  Thread t of sub-round q owns the 8
+// words at chunk + q * 2048 + 8 t .. + 7, so (q, t, element) order is stream order.
+constexpr int kWalkStages = 12;                                    // x 16 KB = 192 KB in flight
+constexpr int kWalkChunkBytes = kWalkChunk * 2;
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_addr(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_addr(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+
+// accepted draws among the 8 words of d (positions pos0 .. pos0 + 7) that lie in [from, limit)
+__device__ __forceinline__ int walk_count8(const uint4& d, uint32_t pos0, uint32_t from, uint32_t limit, uint32_t mask,
+                                           uint32_t top) {
+    const uint32_t w[4] = {d.x, d.y, d.z, d.w};
+    int cnt = 0;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const uint32_t v = ((w[e >> 1] >> ((e & 1) * 16)) & 0xffffu) & mask;
+        const uint32_t p = pos0 + (uint32_t)e;
+        cnt += (v <= top) && (p >= from) && (p < limit);
+    }
+    return cnt;
+}
+// the same without the position test, two words per operation: for v <= mask < 2 (top + 1) <= 0x10000 the
+// 16-bit sum v + 0x8000 - (top + 1) has bit 15 set exactly when v > top and never carries
+__device__ __forceinline__ int walk_count8_packed(const uint4& d, uint32_t mask2, uint32_t kk2) {
+    const uint32_t r0 = ((d.x & mask2) + kk2) & 0x80008000u, r1 = ((d.y & mask2) + kk2) & 0x80008000u;
+    const uint32_t r2 = ((d.z & mask2) + kk2) & 0x80008000u, r3 = ((d.w & mask2) + kk2) & 0x80008000u;
+    return 8 - __popc(r0 | (r1 >> 1) | (r2 >> 2) | (r3 >> 3));
+}
+
+constexpr int kWalkThreads = 1024;
+constexpr int kWalkWarps = kWalkThreads / 32;
+constexpr int kSubPerChunk = kWalkChunk / kSubChunk;       // 4
+
+// One CTA per frame.  Per column: every warp counts the accepted draws of one 2048-word piece of
+// the range the column is expected to span (100 (mask + 1) words, +1 piece: > 10 sigma), one
+// barrier, a prefix over the pieces gives the running counts and the piece in which the column's
+// last draw falls; that piece's warp pins the exact word.
+__global__ void __launch_bounds__(kWalkThreads, 1)
+sky_walk_kernel(const uint16_t* __restrict__ stream, SegLayout lay, const uint32_t* __restrict__ rng,
+                const int32_t* __restrict__ seg_need, int ndisp, const int32_t* __restrict__ n_good,
+                const int32_t* __restrict__ flag, uint32_t* __restrict__ col_start, uint32_t* __restrict__ col_end,
+                uint32_t* __restrict__ sub_have, uint32_t* __restrict__ end_pos, FrameState* __restrict__ st) {
+    extern __shared__ __align__(128) unsigned char walk_smem[];      // kWalkStages x 16 KB
+    __shared__ __align__(8) uint64_t full[kWalkStages];
+    __shared__ uint32_t piece_cnt[2][kWalkWarps];
+    __shared__ uint32_t cross;
+    const int f = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint16_t* s = stream + (size_t)f * lay.stream_len;
+    uint32_t* subs = sub_have + (size_t)f * lay.sub_len;
+    uint32_t* cs = col_start + (size_t)f * ndisp;
+    uint32_t* ce = col_end + (size_t)f * ndisp;
+    const uint32_t limit = ((uint32_t)seg_need[f] << lay.log2_stride) + 1u;     // positions [0, limit) exist
+    uint32_t P = rng[(size_t)f * 625 + 624];
+    if (st[f].status != 0) {
+        if (tid == 0) end_pos[f] = P;
+        return;
+    }
+    // chunk i of this walk = stream words [first + i * 8192, +8192); it lives in stage i % kWalkStages
+    const uint32_t first = P & ~(uint32_t)(kWalkChunk - 1);
+    if (tid == 0) {
+        for (int i = 0; i < kWalkStages; ++i) mbar_init(&full[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    uint32_t issued = 0;                       // thread 0: chunks handed to the copy engine so far
+    auto top_up = [&](uint32_t head_chunk) {   // thread 0 only; stages of chunks < head_chunk are free
+        while (issued < head_chunk + (uint32_t)kWalkStages) {
+            const uint32_t pos = first + issued * kWalkChunk;
+            if (pos >= limit) break;
+            const int stage = (int)(issued % kWalkStages);
+            mbar_expect_tx(&full[stage], kWalkChunkBytes);
+            tma_bulk_load(walk_smem + (size_t)stage * kWalkChunkBytes, s + pos, kWalkChunkBytes, &full[stage]);
+            ++issued;
+        }
+    };
+    if (tid == 0) top_up(0);
+    int parity = 0;
+    bool failed = false;
+    for (int c = 0; c < ndisp; ++c) {
+        const size_t col = (size_t)f * ndisp + c;
+        const int n = n_good[col];
+        if (failed || flag[col] != kSkyModelled || n <= 1) {
+            if (tid == 0) { cs[c] = P; ce[c] = P; }
+            continue;
+        }
+        const uint32_t need = (uint32_t)n * kBootstrap;
+        const uint32_t mask = rejection_mask((uint32_t)n), top = (uint32_t)(n - 1);
+        const bool packed_ok = top < 0x8000u;
+        const uint32_t mask2 = mask * 0x00010001u, kk2 = (0x8000u - (top + 1u)) * 0x00010001u;
+        if (tid == 0) cs[c] = P;
+        uint32_t have = 0;
+        uint32_t piece0 = P >> kSubLog2;            // first piece of the next span (absolute piece index)
+        while (true) {
+            if ((piece0 << kSubLog2) >= limit) { failed = true; break; }
+            // span: the pieces the rest of the column is expected to need, +1, at most one per warp and
+            // never more than the ring holds beyond the chunk the span starts in
+            const unsigned long long expect = ((unsigned long long)(need - have) * (mask + 1ull)) / (unsigned long long)n;
+            unsigned long long want = (expect >> kSubLog2) + 2ull;
+            const uint32_t room = (uint32_t)(kWalkStages - 1) * kSubPerChunk;
+            int span = (int)(want < (unsigned long long)kWalkWarps ? want : (unsigned long long)kWalkWarps);
+            if ((uint32_t)span > room) span = (int)room;
+            const uint32_t head_chunk = ((piece0 << kSubLog2) - first) / kWalkChunk;
+            if (tid == 0) top_up(head_chunk);
+            int cnt = 0;
+            const uint32_t sb = (piece0 + (uint32_t)warp) << kSubLog2;          // this warp's piece
+            if (warp < span && sb < limit) {
+                const uint32_t chunk = (sb - first) / kWalkChunk;
+                const int stage = (int)(chunk % kWalkStages);
+                mbar_wait(&full[stage], (chunk / kWalkStages) & 1u);
+                const uint4* src = reinterpret_cast<const uint4*>(walk_smem + (size_t)stage * kWalkChunkBytes +
+                                                                  (size_t)((sb - first) % kWalkChunk) * 2);
+                const bool interior = packed_ok && sb >= P && sb + kSubChunk <= limit;
+                if (interior) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) cnt += walk_count8_packed(src[k * 32 + lane], mask2, kk2);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        cnt += walk_count8(src[k * 32 + lane], sb + (uint32_t)(k * 256 + lane * 8), P, limit, mask, top);
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+            }
+            if (lane == 0) piece_cnt[parity][warp] = (uint32_t)cnt;
+            __syncthreads();
+            // inclusive prefix over the span's pieces, replicated in every warp
+            uint32_t incl = (lane < span) ? piece_cnt[parity][lane] : 0u;
+            const uint32_t own = incl;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            parity ^= 1;
+            const unsigned reach = __ballot_sync(0xffffffffu, lane < span && have + incl >= need);
+            const uint32_t span_total = __shfl_sync(0xffffffffu, incl, 31);
+            // running count of this column at the piece boundaries it covers
+            if (warp == 0 && lane < span) {
+                const uint32_t bpos = (piece0 + (uint32_t)lane) << kSubLog2;
+                if (bpos >= P && bpos < limit) subs[piece0 + (uint32_t)lane] = have + incl - own;
+            }
+            if (reach) {
+                const int j = __ffs(reach) - 1;
+                if (warp == j) {
+                    const uint32_t before = have + __shfl_sync(0xffffffffu, incl - own, j);
+                    uint32_t target = need - before;                    // 1-based ordinal inside this piece
+                    const uint32_t chunk = (sb - first) / kWalkChunk;
+                    const int stage = (int)(chunk % kWalkStages);
+                    const uint4* src = reinterpret_cast<const uint4*>(walk_smem + (size_t)stage * kWalkChunkBytes +
+                                                                      (size_t)((sb - first) % kWalkChunk) * 2);
+                    for (int k = 0; k < 8; ++k) {
+                        const uint4 d = src[k * 32 + lane];
+                        const uint32_t pos0 = sb + (uint32_t)(k * 256 + lane * 8);
+                        const uint32_t mine = (uint32_t)walk_count8(d, pos0, P, limit, mask, top);
+                        uint32_t li = mine;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const uint32_t t = __shfl_up_sync(0xffffffffu, li, o);
+                            if (lane >= o) li += t;
+                        }
+                        const uint32_t row_total = __shfl_sync(0xffffffffu, li, 31);
+                        if (target <= row_total) {
+                            if (li - mine < target && target <= li) {
+                                const uint32_t w4[4] = {d.x, d.y, d.z, d.w};
+                                uint32_t seen = li - mine;
+                                for (int e = 0; e < 8; ++e) {
+                                    const uint32_t v = ((w4[e >> 1] >> ((e & 1) * 16)) & 0xffffu) & mask;
+                                    const uint32_t p = pos0 + (uint32_t)e;
+                                    if ((v <= top) && (p >= P) && (p < limit)) {
+                                        if (++seen == target) { cross = p + 1; break; }
+                                    }
+                                }
+                            }
+                            break;
+                        }
+                        target -= row_total;
+                    }
+                } else {
+                    (void)__shfl_sync(0xffffffffu, incl - own, j);
+                }
+                __syncthreads();
+                P = cross;
+                if (tid == 0) ce[c] = P;
+                break;
+            }
+            have += span_total;
+            piece0 += (uint32_t)span;
+        }
+        if (failed) {
+            if (tid == 0) { ce[c] = P; atomicMin(&st[f].status, (int)MOTES_E_INTERNAL); }
+        }
+    }
+    if (tid == 0) end_pos[f] = P;
+}
+
+// ---- column -----------------------------------------------------------------------------------
+struct ColShared {
+    uint32_t* slots;     // 100 rows x row_words words (uint16 rank per drawn pixel)
+    uint16_t* ranks;     // nspat
+    double* meds;        // 100
+    double* sq;          // 100
+};
+
+// median of every bootstrap sample from its n rank slots: bitwise binary search, one warp per sample
+__device__ __forceinline__ void column_medians(const ColShared& sh, int n, int rw, const double* __restrict__ srt,
+                                               int lane, int warp, int nwarps) {
+    const int k1 = (n - 1) / 2, k2 = n / 2;
+    int nbits = 1;
+    while ((1 << nbits) < n) ++nbits;
+    const uint16_t* slots16 = reinterpret_cast<const uint16_t*>(sh.slots);
+    if (n <= 64 * kPackWords) {
+        const int nwords = (n + 1) >> 1;
+        for (int smp = warp; smp < kBootstrap; smp += nwarps) {
+            const uint32_t* row = sh.slots + smp * rw;
+            uint32_t reg[kPackWords];
+#pragma unroll
+            for (int t = 0; t < kPackWords; ++t) {
+                const int wd = lane + 32 * t;
+                uint32_t wv = 0x7fff7fffu;                      // padding: larger than any rank
+                if (wd < nwords) {
+                    wv = row[wd];
+                    if (2 * wd + 1 >= n) wv = (wv & 0xffffu) | 0x7fff0000u;
+                }
+                reg[t] = wv;
+            }
+            const int slots_total = 64 * kPackWords;
+            int x1 = 0;
+            for (int bit = nbits - 1; bit >= 0; --bit) {
+                const int cand = x1 | (1 << bit);
+                const uint32_t kk = (uint32_t)(0x8000 - cand) * 0x00010001u;
+                uint32_t ge = 0;
+#pragma unroll
+                for (int t = 0; t < kPackWords; ++t) ge += ((reg[t] + kk) >> 15) & 0x00010001u;
+                const int ge_all = __reduce_add_sync(0xffffffffu, (int)((ge & 0xffffu) + (ge >> 16)));
+                if (slots_total - ge_all <= k1) x1 = cand;
+            }
+            int x2 = x1;
+            if (k2 != k1) {
+                const uint32_t kk = (uint32_t)(0x8000 - (x1 + 1)) * 0x00010001u;
+                uint32_t ge = 0;
+                int nxt = 0x7fff;
+#pragma unroll
+                for (int t = 0; t < kPackWords; ++t) {
+                    ge += ((reg[t] + kk) >> 15) & 0x00010001u;
+                    const int h0 = (int)(reg[t] & 0xffffu), h1 = (int)(reg[t] >> 16);
+                    if (h0 > x1 && h0 < nxt) nxt = h0;
+                    if (h1 > x1 && h1 < nxt) nxt = h1;
+                }
+                const int le = slots_total - __reduce_add_sync(0xffffffffu, (int)((ge & 0xffffu) + (ge >> 16)));
+                nxt = __reduce_min_sync(0xffffffffu, nxt);
+                if (le <= k2) x2 = nxt;
+            }
+            if (lane == 0) sh.meds[smp] = (k1 == k2) ? srt[x1] : (srt[x1] + srt[x2]) * 0.5;
+        }
+        return;
+    }
+    for (int smp = warp; smp < kBootstrap; smp += nwarps) {
+        const uint16_t* row = slots16 + smp * (2 * rw);
+        int x1 = 0;
+        for (int bit = nbits - 1; bit >= 0; --bit) {
+            const int cand = x1 | (1 << bit);
+            int cnt = 0;
+            for (int j = lane; j < n; j += 32) cnt += ((int)row[j] < cand);
+            cnt = __reduce_add_sync(0xffffffffu, cnt);
+            if (cnt <= k1) x1 = cand;
+        }
+        int x2 = x1;
+        if (k2 != k1) {
+            int le = 0, nxt = 0x7fffffff;
+            for (int j = lane; j < n; j += 32) {
+                const int r = (int)row[j];
+                le += (r <= x1);
+                if (r > x1 && r < nxt) nxt = r;
+            }
+            le = __reduce_add_sync(0xffffffffu, le);
+            nxt = __reduce_min_sync(0xffffffffu, nxt);
+            if (le <= k2) x2 = nxt;
+        }
+        if (lane == 0) sh.meds[smp] = (k1 == k2) ? srt[x1] : (srt[x1] + srt[x2]) * 0.5;
+    }
+}
+
+// np.add.reduce over 100 doubles (pairwise_sum_DOUBLE: 8 accumulators, then the tail), by one warp
+__device__ __forceinline__ double warp_numpy_sum100(const double* a, int lane) {
+    double v = 0.0;
+    if (lane < 8) {
+        v = a[lane];
+        for (int i = 1; i < 12; ++i) v += a[8 * i + lane];
+    }
+    const double t = v + __shfl_down_sync(0xffffffffu, v, 1);
+    const double u = t + __shfl_down_sync(0xffffffffu, t, 2);
+    const double w = u + __shfl_down_sync(0xffffffffu, u, 4);
+    double res = ((w + a[96]) + a[97]) + a[98];
+    res = res + a[99];
+    return __shfl_sync(0xffffffffu, res, 0);
+}
+
+__global__ void __launch_bounds__(kColThreads, 2)
+sky_column_kernel(const uint16_t* __restrict__ stream, SegLayout lay, int nspat, int ndisp,
+                  const int32_t* __restrict__ n_good, const int32_t* __restrict__ flag,
+                  const double* __restrict__ sorted, const uint16_t* __restrict__ rank_of,
+                  const uint32_t* __restrict__ col_start, const uint32_t* __restrict__ col_end,
+                  const uint32_t* __restrict__ sub_have, double* __restrict__ sky, double* __restrict__ sky_err,
+                  const FrameState* __restrict__ st) {
+    extern __shared__ __align__(16) unsigned char col_smem[];
+    ColShared sh;
+    sh.meds = reinterpret_cast<double*>(col_smem);
+    sh.sq = sh.meds + kBootstrap;
+    sh.slots = reinterpret_cast<uint32_t*>(sh.sq + kBootstrap);
+    sh.ranks = reinterpret_cast<uint16_t*>(sh.slots + (size_t)kBootstrap * boot_row_words(nspat));
+    const int c = blockIdx.x, f = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int nwarps = kColThreads / 32;
+    if (st[f].status != 0) return;
+    const size_t col = (size_t)f * ndisp + c;
+    if (flag[col] != kSkyModelled) {
+        if (tid == 0) { sky[col] = 0.0; sky_err[col] = 0.0; }
+        return;
+    }
+    const int n = n_good[col];
+    if (n == 0) {
+        if (tid == 0) { sky[col] = NAN; sky_err[col] = NAN; }
+        return;
+    }
+    const double* srt = sorted + col * nspat;
+    if (n > 1) {
+        const int rw = boot_row_words(n);
+        uint16_t* slots16 = reinterpret_cast<uint16_t*>(sh.slots);
+        for (int i = tid; i < n; i += kColThreads) sh.ranks[i] = rank_of[col * nspat + i];
+        __syncthreads();
+        const uint16_t* s = stream + (size_t)f * lay.stream_len;
+        const uint32_t* subs = sub_have + (size_t)f * lay.sub_len;
+        const uint32_t P = col_start[col], Pend = col_end[col];
+        const int need = n * kBootstrap;
+        const uint32_t mask = rejection_mask((uint32_t)n), top = (uint32_t)(n - 1);
+        const unsigned lanes_below = (1u << lane) - 1u;
+        if (Pend > P) {
+            const uint32_t first = P >> kSubLog2, last = (Pend - 1) >> kSubLog2;
+            for (uint32_t sub = first + warp; sub <= last; sub += nwarps) {
+                const uint32_t sb = sub << kSubLog2;
+                const uint32_t start = max(P, sb), end = min(Pend, sb + (uint32_t)kSubChunk);
+                int ord0 = (sb > P) ? (int)subs[sub] : 0;
+                // four rows (512 words) of loads in flight per warp: the stream comes from HBM / L2
+                for (uint32_t row0 = start & ~127u; row0 < end; row0 += 512) {
+                    uint2 raw4[4];
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) raw4[r] = __ldg(reinterpret_cast<const uint2*>(s + row0 + 128u * r + 4u * lane));
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const uint32_t row = row0 + 128u * r;
+                        if (row >= end) break;
+                        const uint32_t pos = row + 4u * lane;
+                        const uint2 raw = raw4[r];
+                        const uint32_t v[4] = {raw.x & 0xffffu & mask, (raw.x >> 16) & mask, raw.y & 0xffffu & mask,
+                                               (raw.y >> 16) & mask};
+                        bool acc[4];
+                        unsigned bal[4];
+                        int before = 0, total = 0;
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const uint32_t p = pos + (uint32_t)e;
+                            acc[e] = (v[e] <= top) && (p >= start) && (p < end);
+                            bal[e] = __ballot_sync(0xffffffffu, acc[e]);
+                            before += __popc(bal[e] & lanes_below);
+                            total += __popc(bal[e]);
+                        }
+                        int ord = ord0 + before;
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            if (acc[e]) {
+                                if (ord < need) {
+                                    const int pix = ord / kBootstrap, smp = ord - pix * kBootstrap;
+                                    slots16[smp * (2 * rw) + pix] = sh.ranks[v[e]];
+                                }
+                                ++ord;
+                            }
+                        }
+                        ord0 += total;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        column_medians(sh, n, rw, srt, lane, warp, nwarps);
+    } else {
+        for (int smp = tid; smp < kBootstrap; smp += kColThreads) sh.meds[smp] = srt[0];
+    }
+    __syncthreads();
+    // np.nanmean / np.std of the 100 medians in numpy's summation order (sky.py:40-41)
+    if (warp == 0) {
+        const double mean = warp_numpy_sum100(sh.meds, lane) / (double)kBootstrap;
+        for (int smp = lane; smp < kBootstrap; smp += 32) { const double d = sh.meds[smp] - mean; sh.sq[smp] = d * d; }
+        __syncwarp();
+        const double var = warp_numpy_sum100(sh.sq, lane) / (double)kBootstrap;
+        if (lane == 0) {
+            sky[col] = mean;
+            sky_err[col] = sqrt(var) / kSqrt99;
+        }
+    }
+}
+
+// ---- export -----------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+mt_export_kernel(uint32_t* __restrict__ rng, const uint32_t* __restrict__ snaps, SegLayout lay,
+                 const uint32_t* __restrict__ end_pos, const FrameState* __restrict__ st) {
+    __shared__ uint32_t ring[kRing];
+    const int f = blockIdx.x;
+    uint32_t* state = rng + (size_t)f * 625;
+    const uint32_t E = end_pos[f];
+    if (st[f].status != 0 || E == state[624] || E == 0) return;
+    const uint32_t block = ((E - 1) / 624u) * 624u;
+    const uint32_t q = block >> kSnapLog2;
+    const uint32_t base = q << kSnapLog2;
+    const uint32_t* from = snaps + ((size_t)f * lay.snaps + q) * 624;
+    for (int i = threadIdx.x; i < 624; i += blockDim.x) ring[(base + i) & (kRing - 1)] = from[i];
+    __syncthreads();
+    const uint32_t stop = block + 624;
+    for (uint32_t gen = base + 624; gen < stop; gen += kSweep) {
+        const uint32_t n = gen + threadIdx.x;
+        if (threadIdx.x < kSweep && n < stop)
+            ring[n & (kRing - 1)] = mt_mix(ring[(n - 624) & (kRing - 1)], ring[(n - 623) & (kRing - 1)],
+                                           ring[(n - kSweep) & (kRing - 1)]);
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i < 624; i += blockDim.x) state[i] = ring[(block + i) & (kRing - 1)];
+    if (threadIdx.x == 0) state[624] = E - block;
+}
+
+}  // namespace motes
