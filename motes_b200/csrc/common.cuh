@@ -40,6 +40,10 @@ struct SeqCtx {
     static constexpr int kLanes = 1;
     int lane = 0;
     MOTES_HD double sum(double v) const { return v; }
+    template <int N>
+    MOTES_HD void sum_vec(const double (&in)[N], double (&out)[N]) const {
+        for (int j = 0; j < N; ++j) out[j] = in[j];
+    }
     MOTES_HD double max(double v) const { return v; }
     MOTES_HD int all(int p) const { return p; }
     MOTES_HD void sync() const {}
@@ -61,8 +65,73 @@ struct WarpCtx {
         for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
         return v;
     }
+    template <int N>
+    __device__ __forceinline__ void sum_vec(const double (&in)[N], double (&out)[N]) const {
+#pragma unroll
+        for (int j = 0; j < N; ++j) out[j] = sum(in[j]);
+    }
     __device__ __forceinline__ int all(int p) const { return __all_sync(0xffffffffu, p); }
     __device__ __forceinline__ void sync() const { __syncwarp(); }
+};
+
+// A whole CTA as one lane context: `lane` is the thread index, reductions combine the warps'
+// butterfly sums in warp order through a double-buffered shared scratch (one barrier per call).
+template <int THREADS>
+struct BlockCtx {
+    static constexpr int kLanes = THREADS;
+    static constexpr int kWarps = THREADS / 32;
+    static constexpr int kRedDoubles = 2 * kWarps * 8;
+    int lane;
+    double* red;            // kRedDoubles of shared memory
+    mutable int flip;
+    // N sums at once.  Instead of N full butterflies, the lanes first split the values between them
+    // (each halving stage exchanges half of what a lane still holds), so 8 values cost 9 shuffles
+    // instead of 40; the lane that ends up with value j is lane j << (5 - log2 P).
+    template <int H>
+    __device__ __forceinline__ static void halve(double* t, int l, int mask) {
+        const bool upper = (l & mask) != 0;
+#pragma unroll
+        for (int i = 0; i < H; ++i) {
+            const double send = upper ? t[i] : t[i + H];
+            const double keep = upper ? t[i + H] : t[i];
+            t[i] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
+        }
+    }
+    template <int N>
+    __device__ __forceinline__ void sum_vec(const double (&in)[N], double (&out)[N]) const {
+        static_assert(N <= 8, "at most 8 values per reduction");
+        constexpr int P = N <= 1 ? 1 : N <= 2 ? 2 : N <= 4 ? 4 : 8;
+        constexpr int LOG = P == 1 ? 0 : P == 2 ? 1 : P == 4 ? 2 : 3;
+        double t[P];
+#pragma unroll
+        for (int j = 0; j < P; ++j) t[j] = j < N ? in[j] : 0.0;
+        const int l = lane & 31;
+        if (P >= 8) halve<4>(t, l, 16);
+        if (P >= 4) halve<(P >= 8 ? 2 : 2)>(t, l, P >= 8 ? 8 : 16);
+        if (P >= 2) halve<1>(t, l, P >= 8 ? 4 : P >= 4 ? 8 : 16);
+#pragma unroll
+        for (int o = 16 >> LOG; o > 0; o >>= 1) t[0] += __shfl_xor_sync(0xffffffffu, t[0], o);
+        double* buf = red + flip * (kWarps * 8);
+        flip ^= 1;
+        const int j = l >> (5 - LOG);
+        if ((l & ((1 << (5 - LOG)) - 1)) == 0 && j < N) buf[(lane >> 5) * 8 + j] = t[0];
+        __syncthreads();
+#pragma unroll
+        for (int jj = 0; jj < N; ++jj) {
+            double acc = buf[jj];
+#pragma unroll
+            for (int w = 1; w < kWarps; ++w) acc += buf[w * 8 + jj];
+            out[jj] = acc;
+        }
+    }
+    __device__ __forceinline__ double sum(double v) const {
+        const double in[1] = {v};
+        double out[1];
+        sum_vec<1>(in, out);
+        return out[0];
+    }
+    __device__ __forceinline__ int all(int p) const { return __syncthreads_and(p); }
+    __device__ __forceinline__ void sync() const { __syncthreads(); }
 };
 #endif
 

@@ -90,9 +90,10 @@ struct motes_handle {
     long long launches = 0;
     // scratch slots: host-API staging and per-stage work areas
     motes::Scratch stage[12];
-    motes::Scratch work[20];
+    motes::Scratch work[24];
     motes::Scratch counters;    // small zero-initialised control block
     bool profiling = false;
+    int fit_mode = 0;            // MOTES_B200_FIT: 0 batched persistent grid (default), 1 one warp per fit
     int boot_mode = 0;           // MOTES_B200_BOOTSTRAP: 0 segmented (default), 1 classic (one CTA per frame), 2 warp-specialised
     motes::Scratch jump_polys;   // device copy of the MT19937 jump polynomial table (mtjump.hpp)
     bool jump_ready = false;

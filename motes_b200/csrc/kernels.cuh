@@ -5,7 +5,7 @@
 
 #include "common.cuh"
 #include "select.cuh"
-#include "trf.cuh"
+#include "trfb.cuh"
 #include "bins.cuh"
 #include "limits.cuh"
 #include "sky.cuh"
@@ -255,6 +255,94 @@ moffat_fit_kernel(FitBatch fb, unsigned int* work_counter) {
             if (fb.status) fb.status[idx] = r.status;
         }
         __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// a3, batched (trfb.cuh): a CTA takes a group of up to 32 fits from a queue and advances them in
+// lock step: sweep phase - the whole CTA works on one fit at a time (residual sweep at the trial
+// point, accept / reject / stop, re-linearisation); step phase - thread j chooses the next trial
+// step of fit j (SVD of the 6 x 6 triangle, trust-region step, step selection), so the
+// six-parameter logic runs once per fit instead of once per lane.  The states of the group live in
+// shared memory; nothing but the profiles is read from and the results written to HBM.
+// ---------------------------------------------------------------------------------------------
+constexpr int kFitThreads = 128;
+constexpr int kFitGroupMax = 32;
+constexpr int kStatusRetired = -200;          // finished (results written) or empty slot
+using FitBlockCtx = BlockCtx<kFitThreads>;
+
+__device__ __forceinline__ void fit_finalize(const FitBatch& fb, size_t idx, const FitState& st) {
+    for (int k = 0; k < kParams; ++k) fb.params[idx * kParams + k] = st.x[k];
+    if (fb.cost) fb.cost[idx] = st.cost;
+    if (fb.nfev) fb.nfev[idx] = st.nfev;
+    if (fb.njev) fb.njev[idx] = st.njev;
+    if (fb.status) fb.status[idx] = (st.status == kStatusRunning) ? (int)kFitMaxNfev : st.status;
+}
+
+__device__ __forceinline__ double fit_frame_scalar(const double* base, size_t stride, int f, size_t idx) {
+    return stride ? *reinterpret_cast<const double*>(reinterpret_cast<const char*>(base) + f * stride) : base[idx];
+}
+
+MOTES_HD size_t fit_group_smem(int m, int group) {
+    return (fit_sweep_doubles(m) + FitBlockCtx::kRedDoubles) * sizeof(double) + (size_t)group * sizeof(FitState);
+}
+
+__global__ void __launch_bounds__(kFitThreads, 4)
+moffat_fit_group_kernel(FitBatch fb, int group, unsigned int* __restrict__ queue) {
+    extern __shared__ __align__(16) double fitb_smem[];
+    __shared__ unsigned int s_item;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int m = fb.m;
+    double* slab = fitb_smem;
+    FitBlockCtx ctx{tid, fitb_smem + fit_sweep_doubles(m), 0};
+    FitState* states = reinterpret_cast<FitState*>(fitb_smem + fit_sweep_doubles(m) + FitBlockCtx::kRedDoubles);
+    const unsigned int total = (unsigned int)fb.nframes * (unsigned int)fb.bound;
+    while (true) {
+        if (tid == 0) s_item = atomicAdd(queue, 1u);
+        __syncthreads();
+        const unsigned int base = s_item * (unsigned int)group;
+        __syncthreads();
+        if (base >= total) break;
+        const int count = (int)min((unsigned int)group, total - base);
+        // ---- start points and bounds: one warp per fit
+        for (int j = warp; j < count; j += kFitThreads / 32) {
+            const unsigned int item = base + j;
+            const int f = item / fb.bound, slot = item % fb.bound;
+            if (fb.nbins && slot >= fb.nbins[f]) {
+                states[j].status = kStatusRetired;
+                continue;
+            }
+            const size_t idx = (size_t)f * fb.cap + slot;
+            const double alpha0 = fit_frame_scalar(fb.alpha0, fb.alpha0_frame_stride, f, idx);
+            const double scale = fb.scale ? fit_frame_scalar(fb.scale, fb.scale_frame_stride, f, 0) : 1.0;
+            fit_start(m, fb.profiles + idx * m, scale, alpha0, &states[j]);     // every lane writes the same values
+        }
+        __syncthreads();
+        while (true) {
+            // ---- sweep phase
+            for (int j = 0; j < count; ++j) {
+                if (states[j].status != kStatusRunning) continue;              // uniform
+                const unsigned int item = base + j;
+                const int f = item / fb.bound, slot = item % fb.bound;
+                const size_t idx = (size_t)f * fb.cap + slot;
+                const double scale = fb.scale ? fit_frame_scalar(fb.scale, fb.scale_frame_stride, f, 0) : 1.0;
+                fit_evaluate(ctx, m, fb.profiles + idx * m, scale, slab, &states[j]);
+            }
+            __syncthreads();
+            // ---- step phase
+            int running = 0;
+            if (tid < count && states[tid].status != kStatusRetired) {
+                if (fit_propose(m, states[tid])) {
+                    running = 1;
+                } else {
+                    const unsigned int item = base + tid;
+                    const int f = item / fb.bound, slot = item % fb.bound;
+                    fit_finalize(fb, (size_t)f * fb.cap + slot, states[tid]);
+                    states[tid].status = kStatusRetired;
+                }
+            }
+            if (!__syncthreads_or(running)) break;
+        }
     }
 }
 

@@ -139,8 +139,8 @@ static int stage_row_median(motes_handle* h, const double* data, size_t frame_st
     return MOTES_OK;
 }
 
-static int stage_fit(motes_handle* h, const FitBatch& fb) {
-    if (fb.nframes <= 0 || fb.bound <= 0) return MOTES_OK;
+// One warp per fit, whole iteration inside the warp (round-1 kernel; kept for A/B: MOTES_B200_FIT=warp).
+static int stage_fit_warp(motes_handle* h, const FitBatch& fb) {
     size_t per_warp = fit_scratch_doubles(fb.m) * sizeof(double);
     size_t budget = h->smem_optin > 2048 ? h->smem_optin - 1024 : h->smem_optin;
     int warps = (int)(budget / per_warp);
@@ -158,6 +158,31 @@ static int stage_fit(motes_handle* h, const FitBatch& fb) {
     MOTES_TRY(h->counters.ensure(256));
     MOTES_CUDA(cudaMemsetAsync(h->counters.ptr, 0, 256, h->stream));
     moffat_fit_kernel<<<(int)grid, warps * 32, smem, h->stream>>>(fb, h->counters.as<unsigned int>());
+    MOTES_LAUNCHED(h);
+    return MOTES_OK;
+}
+
+// Groups of fits advanced in lock step by one CTA each (kernels.cuh: moffat_fit_group_kernel).
+static int stage_fit(motes_handle* h, const FitBatch& fb) {
+    if (fb.nframes <= 0 || fb.bound <= 0) return MOTES_OK;
+    if (h->fit_mode == 1) return stage_fit_warp(h, fb);
+    const long long items = (long long)fb.nframes * fb.bound;
+    // enough groups to give every SM several CTAs; at most 32 fits (one per lane of the step phase) per group
+    long long group = items / (8ll * h->sm_count);
+    if (group < 1) group = 1;
+    if (group > kFitGroupMax) group = kFitGroupMax;
+    const size_t smem = fit_group_smem(fb.m, (int)group);
+    if (smem > h->smem_optin) return fail_arg("nspat too large for the shared-memory fit slab");
+    MOTES_CUDA(cudaFuncSetAttribute(moffat_fit_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    MOTES_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, moffat_fit_group_kernel, kFitThreads, smem));
+    if (per_sm < 1) per_sm = 1;
+    const long long groups = (items + group - 1) / group;
+    long long grid = (long long)h->sm_count * per_sm;
+    if (grid > groups) grid = groups;
+    MOTES_TRY(h->counters.ensure(256));
+    MOTES_CUDA(cudaMemsetAsync(h->counters.ptr, 0, 256, h->stream));
+    moffat_fit_group_kernel<<<(unsigned)grid, kFitThreads, smem, h->stream>>>(fb, (int)group, h->counters.as<unsigned int>());
     MOTES_LAUNCHED(h);
     return MOTES_OK;
 }
@@ -506,6 +531,8 @@ int motes_create(int device, motes_handle** out) {
     // A/B switches: "classic" = one CTA walks a frame's whole stream, "ws" = its warp-specialised variant
     const char* boot = getenv("MOTES_B200_BOOTSTRAP");
     h->boot_mode = (boot && strcmp(boot, "classic") == 0) ? 1 : (boot && strcmp(boot, "ws") == 0) ? 2 : 0;
+    const char* fitm = getenv("MOTES_B200_FIT");              // "warp": round-1 one-warp-per-fit kernel
+    h->fit_mode = (fitm && strcmp(fitm, "warp") == 0) ? 1 : 0;
     const char* budget = getenv("MOTES_B200_STREAM_GB");
     if (budget && atof(budget) > 0.0) h->stream_budget = (size_t)(atof(budget) * 1073741824.0);
     e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);

@@ -1,0 +1,349 @@
+// Batched form of the bounded TRF Moffat fit (same iteration as trf.cuh, i.e. scipy's trf_bounds
+// as called from /root/reference/src/motes/tracing.py:550-607), cut into phases so that a batch of
+// fits can be advanced in lock step by a persistent grid:
+//
+//   fit_start     start point and bounds from the profile (tracing.py:578-588)      one warp per fit
+//   fit_evaluate  residual sweep at the trial point, the accept / reject / stop logic of the inner
+//                 loop (trf.py:335-383), and for an accepted point the forward-difference Jacobian,
+//                 g = J^T f and the QR of [J_h ; sqrt(diag_h)] with f carried along   one CTA per fit
+//   fit_propose   Coleman-Li scaling, stop tests of the outer loop, SVD of the 6 x 6 triangle,
+//                 trust-region step and step selection (trf.py:280-333)              one THREAD per fit
+//
+// The six-parameter logic therefore runs once per fit instead of once per lane, and the
+// data-parallel sweeps run with a whole CTA per fit.  Everything between phases lives in FitState.
+#pragma once
+
+#include "trf.cuh"
+
+namespace motes {
+
+constexpr int kStatusRunning = -100;      // scipy's termination_status None
+
+struct FitState {
+    double x[kParams], lb[kParams], ub[kParams];
+    double g[kParams];
+    double R[kParams * kParams];          // upper triangle of the QR of the augmented scaled Jacobian
+    double z[kParams];                    // Q^T f
+    double x_new[kParams];
+    double cost, radius, alpha, predicted, step_h_norm, step_norm, x_norm;
+    int nfev, njev, status, first;
+};
+
+// Scratch of the sweep phases: unit [m] pow cache, a [7 m] Jacobian columns + residual column.
+MOTES_HD size_t fit_sweep_doubles(int m) { return (size_t)8 * m; }
+
+// ---- start point and bounds -------------------------------------------------------------------
+// Replicated serial scan of the profile (every lane of the calling scope computes the same values).
+MOTES_HD void fit_start(int m, const double* profile, double scale, double alpha0, FitState* st) {
+    using namespace trf_detail;
+    constexpr int n = kParams;
+    double top1 = -INFINITY, top2 = -INFINITY, top3 = -INFINITY;
+    int peak = 0, n_nan = 0;
+    bool peak_nan = false;
+    for (int i = 0; i < m; ++i) {
+        double val = profile[i] * scale;
+        if (val != val) {
+            if (!peak_nan) { peak_nan = true; peak = i; }       // np.argmax returns the first NaN
+            ++n_nan;
+            continue;
+        }
+        if (!peak_nan && val > top1) peak = i;
+        if (val > top1) { top3 = top2; top2 = top1; top1 = val; }
+        else if (val > top2) { top3 = top2; top2 = val; }
+        else if (val > top3) { top3 = val; }
+    }
+    double amp0;
+    if (m - n_nan >= 3 && n_nan == 0) amp0 = top2;
+    else if (n_nan == 1 && m >= 3) amp0 = (top2 + top1) * 0.5;
+    else if (n_nan == 2 && m >= 3) amp0 = top1;
+    else amp0 = (m >= 3) ? NAN : top1;
+    (void)top3;
+    // np.median(concatenate(col[:5], col[-5:]))
+    double ends[10];
+    int n_ends = 0;
+    for (int i = 0; i < 5 && i < m; ++i) ends[n_ends++] = profile[i] * scale;
+    for (int i = (m > 5 ? m - 5 : 0); i < m; ++i) ends[n_ends++] = profile[i] * scale;
+    bool ends_nan = false;
+    for (int i = 1; i < n_ends; ++i) {
+        double key = ends[i];
+        int j = i - 1;
+        while (j >= 0 && ends[j] > key) { ends[j + 1] = ends[j]; --j; }
+        ends[j + 1] = key;
+    }
+    for (int i = 0; i < n_ends; ++i) ends_nan = ends_nan || (ends[i] != ends[i]);
+    double level0 = (n_ends % 2) ? ends[n_ends / 2] : (ends[n_ends / 2 - 1] + ends[n_ends / 2]) * 0.5;
+    if (ends_nan) level0 = NAN;
+
+    const double x0[n] = {amp0, (double)peak, alpha0, kBetaStart, level0, 0.0};
+    const double lb[n] = {0.0, (double)peak - 1.0, 0.0, 0.0, -INFINITY, -INFINITY};
+    const double ub[n] = {INFINITY, (double)peak + 1.0, 5.0 * alpha0, 5.0, INFINITY, INFINITY};
+    for (int i = 0; i < n; ++i) { st->x[i] = x0[i]; st->lb[i] = lb[i]; st->ub[i] = ub[i]; st->x_new[i] = x0[i]; st->g[i] = 0.0; }
+    st->cost = NAN;
+    st->radius = 0.0;
+    st->alpha = 0.0;
+    st->predicted = 0.0;
+    st->step_h_norm = 0.0;
+    st->step_norm = 0.0;
+    st->x_norm = 0.0;
+    st->nfev = 0;
+    st->njev = 0;
+    st->first = 1;
+    st->status = kStatusRunning;
+    for (int i = 0; i < n; ++i)
+        if (!(lb[i] < ub[i])) { st->status = kFitBadBounds; return; }
+    if (!inside(st->x, lb, ub)) { st->status = kFitX0Infeasible; return; }
+    push_inside(st->x, lb, ub, 1e-10);
+}
+
+// ---- sweeps -----------------------------------------------------------------------------------
+template <class Ctx>
+MOTES_HD bool residual_sweep_b(const Ctx& ctx, int m, const double* profile, double scale, const double* xe,
+                               double* unit_out, double* out, double* cost) {
+    double acc = 0.0;
+    int finite = 1;
+    for (int i = ctx.lane; i < m; i += Ctx::kLanes) {
+        double r = (double)i;
+        double u = moffat_unit(r, xe[1], xe[2], xe[3]);
+        double f = moffat_value(u, r, xe[0], xe[4], xe[5]) - profile[i] * scale;
+        unit_out[i] = u;
+        out[i] = f;
+        acc += f * f;
+        finite &= (int)is_finite(f);
+    }
+    *cost = 0.5 * ctx.sum(acc);
+    return ctx.all(finite) != 0;
+}
+
+// Householder step K of the QR of [J_h | f] with the sparse pivot row sqrt(diag_h[K]) (see linearize).
+template <int K, class Ctx>
+MOTES_HD void qr_step(const Ctx& ctx, int m, double* a, double diag_hk, FitState* st) {
+    constexpr int n = kParams;
+    constexpr int W = n + 1 - K;              // columns K .. n (n = the residual column)
+    const bool leader = ctx.lane == 0;
+    const double* colk = a + (size_t)K * m;
+    double part[W], c[W];
+#pragma unroll
+    for (int j = 0; j < W; ++j) part[j] = 0.0;
+    for (int i = ctx.lane; i < m; i += Ctx::kLanes) {
+        double aki = colk[i];
+#pragma unroll
+        for (int j = 0; j < W; ++j) part[j] = fma(aki, a[(size_t)(K + j) * m + i], part[j]);
+    }
+    ctx.template sum_vec<W>(part, c);
+    double ek = sqrt(diag_hk);
+    double norm2 = c[0] + ek * ek;
+    if (norm2 > 0.0) {
+        double nrm = sqrt(norm2);
+        double v_piv = ek + nrm;
+        double tau = 1.0 / (norm2 + nrm * ek);
+        double wj[W];
+#pragma unroll
+        for (int j = 1; j < W; ++j) wj[j] = c[j] * tau;
+        if (leader) {
+            st->R[K * n + K] = -nrm;
+#pragma unroll
+            for (int j = 1; j < W; ++j) {
+                double rkj = -wj[j] * v_piv;
+                if (K + j < n) st->R[K * n + K + j] = rkj; else st->z[K] = rkj;
+            }
+        }
+        for (int i = ctx.lane; i < m; i += Ctx::kLanes) {
+            double aki = colk[i];
+#pragma unroll
+            for (int j = 1; j < W; ++j) a[(size_t)(K + j) * m + i] = fma(-wj[j], aki, a[(size_t)(K + j) * m + i]);
+        }
+    } else if (leader) {
+        st->z[K] = 0.0;
+    }
+    ctx.sync();
+}
+
+// Jacobian at x (residual in a[6m..7m), pow cache in unit), g = J^T f, then the QR of
+// [J diag(d) ; diag(sqrt(diag_h))] by Householder reflections pivoting on the sparse rows, with f
+// as a seventh column (trf.cuh explains the equivalence with scipy's SVD of the augmented matrix).
+// g, R, z go to *st, written by the scope's lane 0 only (st may be shared by the scope).
+template <class Ctx>
+MOTES_HD void linearize(const Ctx& ctx, int m, const double* profile, double scale, const double (&x)[kParams],
+                        const double (&lb)[kParams], const double (&ub)[kParams], const double* unit, double* a,
+                        FitState* st) {
+    using namespace trf_detail;
+    constexpr int n = kParams;
+    const bool leader = ctx.lane == 0;
+    double h[n];
+    fd_steps(x, lb, ub, h);
+    const double* f0 = a + 6 * (size_t)m;
+    double dx[n];
+#pragma unroll
+    for (int k = 0; k < n; ++k) dx[k] = (x[k] + h[k]) - x[k];
+    double gp[n] = {0, 0, 0, 0, 0, 0};
+    for (int i = ctx.lane; i < m; i += Ctx::kLanes) {
+        const double r = (double)i;
+        const double yi = profile[i] * scale, fi = f0[i], u0 = unit[i];
+        // A, B, m move the value but not the pow argument; c, alpha, beta need their own pow
+        const double uc = moffat_unit(r, x[1] + h[1], x[2], x[3]);
+        const double ua = moffat_unit(r, x[1], x[2] + h[2], x[3]);
+        const double ub_ = moffat_unit(r, x[1], x[2], x[3] + h[3]);
+        double col[n];
+        col[0] = ((moffat_value(u0, r, x[0] + h[0], x[4], x[5]) - yi) - fi) / dx[0];
+        col[1] = ((moffat_value(uc, r, x[0], x[4], x[5]) - yi) - fi) / dx[1];
+        col[2] = ((moffat_value(ua, r, x[0], x[4], x[5]) - yi) - fi) / dx[2];
+        col[3] = ((moffat_value(ub_, r, x[0], x[4], x[5]) - yi) - fi) / dx[3];
+        col[4] = ((moffat_value(u0, r, x[0], x[4] + h[4], x[5]) - yi) - fi) / dx[4];
+        col[5] = ((moffat_value(u0, r, x[0], x[4], x[5] + h[5]) - yi) - fi) / dx[5];
+#pragma unroll
+        for (int k = 0; k < n; ++k) { a[(size_t)k * m + i] = col[k]; gp[k] += col[k] * fi; }
+    }
+    double g[n];
+    ctx.template sum_vec<n>(gp, g);
+
+    double v[n], dv[n], d[n], diag_h[n];
+    coleman_li(x, g, lb, ub, v, dv);
+#pragma unroll
+    for (int i = 0; i < n; ++i) { d[i] = sqrt(v[i]); diag_h[i] = g[i] * dv[i]; }
+    if (leader) {
+#pragma unroll
+        for (int k = 0; k < n; ++k) st->g[k] = g[k];
+        for (int i = 0; i < n * n; ++i) st->R[i] = 0.0;
+    }
+    for (int i = ctx.lane; i < m; i += Ctx::kLanes) {
+#pragma unroll
+        for (int k = 0; k < n; ++k) a[(size_t)k * m + i] *= d[k];
+    }
+    ctx.sync();
+    qr_step<0>(ctx, m, a, diag_h[0], st);
+    qr_step<1>(ctx, m, a, diag_h[1], st);
+    qr_step<2>(ctx, m, a, diag_h[2], st);
+    qr_step<3>(ctx, m, a, diag_h[3], st);
+    qr_step<4>(ctx, m, a, diag_h[4], st);
+    qr_step<5>(ctx, m, a, diag_h[5], st);
+}
+
+// One trial: advances *st exactly as one pass of scipy's inner loop body after the step has been
+// chosen (or, for the first call, as the set-up in front of the outer loop).  *st may be shared by
+// the scope: every lane reads it, lane 0 writes it, with scope barriers around the writes.
+template <class Ctx>
+MOTES_HD void fit_evaluate(const Ctx& ctx, int m, const double* profile, double scale, double* slab, FitState* st) {
+    using namespace trf_detail;
+    constexpr int n = kParams;
+    const bool leader = ctx.lane == 0;
+    double* unit = slab;
+    double* a = slab + m;
+    double* fcol = a + 6 * (size_t)m;
+    double x[n], lb[n], ub[n];
+#pragma unroll
+    for (int i = 0; i < n; ++i) { lb[i] = st->lb[i]; ub[i] = st->ub[i]; }
+    if (st->first) {
+#pragma unroll
+        for (int i = 0; i < n; ++i) x[i] = st->x[i];
+        double cost;
+        bool finite = residual_sweep_b(ctx, m, profile, scale, x, unit, fcol, &cost);
+        ctx.sync();
+        if (!finite) {
+            if (leader) st->status = kFitNonFinite;
+            ctx.sync();
+            return;
+        }
+        if (leader) { st->cost = cost; st->nfev = 1; st->njev = 1; }
+        linearize(ctx, m, profile, scale, x, lb, ub, unit, a, st);
+        return;
+    }
+#pragma unroll
+    for (int i = 0; i < n; ++i) x[i] = st->x_new[i];
+    const double cost_old = st->cost, radius = st->radius, step_h_norm = st->step_h_norm, predicted = st->predicted;
+    const double step_norm = st->step_norm, x_norm = st->x_norm, alpha = st->alpha;
+    const int nfev = st->nfev, njev = st->njev;
+    double cost_new;
+    bool ok = residual_sweep_b(ctx, m, profile, scale, x, unit, fcol, &cost_new);
+    ctx.sync();                                   // every lane has read *st; lane 0 may write from here on
+    if (!ok) {
+        if (leader) { st->nfev = nfev + 1; st->radius = 0.25 * step_h_norm; }
+        ctx.sync();
+        return;
+    }
+    const double gain = cost_old - cost_new;
+    double ratio;
+    if (predicted > 0.0) ratio = gain / predicted;
+    else if (predicted == 0.0 && gain == 0.0) ratio = 1.0;
+    else ratio = 0.0;
+    double radius_new = radius;
+    if (ratio < 0.25) radius_new = 0.25 * step_h_norm;
+    else if (ratio > 0.75 && step_h_norm > 0.95 * radius) radius_new = radius * 2.0;
+    const bool f_ok = (gain < 1e-12 * cost_old) && (ratio > 0.25);
+    const bool x_ok = step_norm < 1e-8 * (1e-8 + x_norm);
+    int status = kStatusRunning;
+    if (f_ok && x_ok) status = kFitBoth;
+    else if (f_ok) status = kFitFtol;
+    else if (x_ok) status = kFitXtol;
+    if (leader) {
+        st->nfev = nfev + 1;
+        st->status = status;
+        if (status == kStatusRunning) {
+            st->alpha = alpha * (radius / radius_new);
+            st->radius = radius_new;
+        }
+        if (gain > 0.0) {
+#pragma unroll
+            for (int i = 0; i < n; ++i) st->x[i] = x[i];
+            st->cost = cost_new;
+            st->njev = njev + 1;      // scipy evaluates the Jacobian at the accepted point even when it then stops
+        }
+    }
+    if (gain > 0.0 && status == kStatusRunning) linearize(ctx, m, profile, scale, x, lb, ub, unit, a, st);
+    ctx.sync();
+}
+
+// Top of the outer loop up to the chosen step.  Returns false when the fit has ended (st.status final).
+MOTES_HD bool fit_propose(int m, FitState& st) {
+    using namespace trf_detail;
+    constexpr int n = kParams;
+    const int max_nfev = 100 * n;
+    if (st.status != kStatusRunning) return false;
+    double v[n], dv[n];
+    coleman_li(st.x, st.g, st.lb, st.ub, v, dv);
+    if (st.first) {
+        double t[n];
+        for (int i = 0; i < n; ++i) t[i] = st.x[i] / sqrt(v[i]);
+        st.radius = norm6(t);
+        if (st.radius == 0.0) st.radius = 1.0;
+        st.alpha = 0.0;
+        st.first = 0;
+    }
+    double g_norm = 0.0;
+    for (int i = 0; i < n; ++i) g_norm = fmax(g_norm, fabs(st.g[i] * v[i]));
+    if (g_norm < 1e-8) st.status = kFitGtol;
+    if (st.status != kStatusRunning) return false;
+    if (st.nfev >= max_nfev) { st.status = kFitMaxNfev; return false; }
+    double d[n], g_h[n];
+    for (int i = 0; i < n; ++i) { d[i] = sqrt(v[i]); g_h[i] = d[i] * st.g[i]; }
+    double s[n], suf[n], V[n * n], w[n * n], vv[n * n];
+    jacobi_svd6(SeqCtx{}, st.R, st.z, w, vv, s, suf, V);
+    const double theta = fmax(0.995, 1.0 - g_norm);
+    st.x_norm = norm6(st.x);
+    double p_h[n], step[n], step_h[n];
+    more_step(m, s, suf, V, st.radius, &st.alpha, p_h);
+    st.predicted = choose_step(st.x, st.R, g_h, p_h, d, st.radius, st.lb, st.ub, theta, step, step_h);
+    for (int i = 0; i < n; ++i) st.x_new[i] = st.x[i] + step[i];
+    push_inside(st.x_new, st.lb, st.ub, 0.0);
+    st.step_h_norm = norm6(step_h);
+    st.step_norm = norm6(step);
+    return true;
+}
+
+// The whole fit through the phases (host simulation and the reference for the persistent kernel).
+template <class Ctx>
+MOTES_HD void trf_fit_moffat_phased(const Ctx& ctx, int m, const double* profile, double scale, double alpha0,
+                                    double* slab, FitResult* res) {
+    FitState st;
+    fit_start(m, profile, scale, alpha0, &st);
+    while (st.status == kStatusRunning) {
+        fit_evaluate(ctx, m, profile, scale, slab, &st);
+        if (!fit_propose(m, st)) break;
+    }
+    for (int i = 0; i < kParams; ++i) res->x[i] = st.x[i];
+    res->cost = st.cost;
+    res->nfev = st.nfev;
+    res->njev = st.njev;
+    res->status = st.status;
+}
+
+}  // namespace motes

@@ -3,7 +3,7 @@
 // CUDA kernels (compiled here by g++) against scipy.  Never loaded by the motes_b200 package.
 #include <vector>
 #include <cstring>
-#include "../../motes_b200/csrc/trf.cuh"
+#include "../../motes_b200/csrc/trfb.cuh"
 
 extern "C" int hostsim_fit_batch(const double* profiles, int nfit, int m, const double* alpha0,
                                  double* params, double* cost, int* nfev, int* njev, int* status) {
@@ -18,6 +18,23 @@ extern "C" int hostsim_fit_batch(const double* profiles, int nfit, int m, const 
         nfev[f] = r.nfev;
         njev[f] = r.njev;
         status[f] = r.status;
+    }
+    return 0;
+}
+
+// The same fits through the phases the persistent GPU kernel runs (trfb.cuh): start -> evaluate -> propose.
+extern "C" int hostsim_fit_batch_phased(const double* profiles, int nfit, int m, const double* alpha0,
+                                        double* params, double* cost, int* nfev, int* njev, int* status) {
+    std::vector<double> slab(motes::fit_sweep_doubles(m));
+    motes::SeqCtx ctx;
+    for (int f = 0; f < nfit; ++f) {
+        motes::FitResult r;
+        motes::trf_fit_moffat_phased(ctx, m, profiles + (size_t)f * m, 1.0, alpha0[f], slab.data(), &r);
+        std::memcpy(params + 6 * (size_t)f, r.x, sizeof(r.x));
+        cost[f] = r.cost;
+        nfev[f] = r.nfev;
+        njev[f] = r.njev;
+        status[f] = r.status == motes::kStatusRunning ? 0 : r.status;
     }
     return 0;
 }

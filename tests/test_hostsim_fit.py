@@ -18,14 +18,14 @@ def hostsim():
     return ctypes.CDLL(os.path.join(HOSTSIM_DIR, "libmotes_hostsim.so"))
 
 
-def _fit(lib, profiles, alpha0):
+def _fit(lib, profiles, alpha0, entry="hostsim_fit_batch"):
     dp, ip = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int)
     profiles = np.ascontiguousarray(profiles, dtype=np.float64)
     nfit, m = profiles.shape
     a0 = np.full(nfit, alpha0)
     params, cost = np.zeros((nfit, 6)), np.zeros(nfit)
     nfev, njev, status = (np.zeros(nfit, dtype=np.int32) for _ in range(3))
-    lib.hostsim_fit_batch(profiles.ctypes.data_as(dp), nfit, m, a0.ctypes.data_as(dp), params.ctypes.data_as(dp),
+    getattr(lib, entry)(profiles.ctypes.data_as(dp), nfit, m, a0.ctypes.data_as(dp), params.ctypes.data_as(dp),
                           cost.ctypes.data_as(dp), nfev.ctypes.data_as(ip), njev.ctypes.data_as(ip),
                           status.ctypes.data_as(ip))
     return params, cost, nfev, njev, status
@@ -47,6 +47,18 @@ def test_solver_tracks_reference_fits(hostsim, name):
     assert np.allclose(cost, g["ext_fitinfo"][:, 3], rtol=1e-9)
     # iteration counts agree for most fits (they may differ by one at the ftol/xtol edge)
     assert np.mean(np.abs(nfev - g["ext_fitinfo"][:, 0]) <= 1) > 0.8
+
+
+@pytest.mark.parametrize("name", ["t1_sky0", "t1_faint", "c1_sky0"])
+def test_phased_solver_is_the_same_iteration(hostsim, name):
+    """The phase-split form the persistent GPU kernel runs takes the same decisions as the one-loop form."""
+    meta, g = load_golden(name)
+    profiles = g["ext_profiles"] * g["scale"]
+    alpha0 = g["seeing_px"] / meta["spec"]["pixel_resolution"]
+    a = _fit(hostsim, profiles, alpha0)
+    b = _fit(hostsim, profiles, alpha0, entry="hostsim_fit_batch_phased")
+    assert np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3]) and np.array_equal(a[4], b[4])
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
 
 
 def test_solver_error_codes(hostsim):
