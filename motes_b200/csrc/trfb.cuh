@@ -114,6 +114,41 @@ MOTES_HD bool residual_sweep_b(const Ctx& ctx, int m, const double* profile, dou
     return ctx.all(finite) != 0;
 }
 
+// ---- forward differences without a second pow --------------------------------------------------
+// scipy's 2-point Jacobian evaluates the model at x + h e_k with h ~ 1.5e-8 |x_k| (_numdiff.py).  For
+// the three parameters inside the pow that is pow(s', -beta') with s' = s (1 + delta), |delta| ~ 1e-6,
+// or beta' = beta + h.  Both are the base value u = pow(s, -beta) times exp(small):
+//     pow(s', -beta)     = u exp(-beta log1p(delta)),    delta = (q' - q) / s
+//     pow(s, -(beta+h))  = u exp(-h log(s))
+// evaluated with short series.  The result is within an ulp or two of the shifted pow - the same
+// accuracy the reference's libm / SVML pow has - at a fraction of its cost.  Steps that are not small
+// (a parameter sitting on a bound makes scipy take the whole feasible interval) use the real pow.
+MOTES_HD double expm1_small(double e) {          // |e| < 1e-2: truncation < 2e-17 relative
+    return e * (1.0 + e * (0.5 + e * (1.0 / 6.0 + e * (1.0 / 24.0 + e * (1.0 / 120.0 + e * (1.0 / 720.0))))));
+}
+MOTES_HD bool shifted_unit(double u, double q_shift, double q, double inv_s, double beta, double* out) {
+    const double delta = (q_shift - q) * inv_s;
+    if (!(fabs(delta) < 1e-3)) return false;
+    const double l = delta * (1.0 - delta * (0.5 - delta * (1.0 / 3.0 - delta * (0.25 - delta * 0.2))));   // log1p
+    const double e = -beta * l;
+    if (!(fabs(e) < 1e-2)) return false;
+    *out = fma(u, expm1_small(e), u);
+    return true;
+}
+MOTES_HD bool shifted_unit_beta(double u, double s, double dbeta, double* out) {
+    const double e = -dbeta * log(s);
+    if (!(fabs(e) < 1e-2)) return false;
+    *out = fma(u, expm1_small(e), u);
+    return true;
+}
+#if defined(__CUDACC__)
+__host__ __device__ __noinline__ inline double moffat_unit_call(double r, double c, double alpha, double beta) {
+    return moffat_unit(r, c, alpha, beta);
+}
+#else
+inline double moffat_unit_call(double r, double c, double alpha, double beta) { return moffat_unit(r, c, alpha, beta); }
+#endif
+
 // Householder step K of the QR of [J_h | f] with the sparse pivot row sqrt(diag_h[K]) (see linearize).
 template <int K, class Ctx>
 MOTES_HD void qr_step(const Ctx& ctx, int m, double* a, double diag_hk, FitState* st) {
@@ -175,21 +210,33 @@ MOTES_HD void linearize(const Ctx& ctx, int m, const double* profile, double sca
     double dx[n];
 #pragma unroll
     for (int k = 0; k < n; ++k) dx[k] = (x[k] + h[k]) - x[k];
+    double inv_dx[n];
+#pragma unroll
+    for (int k = 0; k < n; ++k) inv_dx[k] = 1.0 / dx[k];
+    const double c1 = x[1] + h[1], a1 = x[2] + h[2];
+    const double aa = x[2] * x[2], aa1 = a1 * a1;
     double gp[n] = {0, 0, 0, 0, 0, 0};
     for (int i = ctx.lane; i < m; i += Ctx::kLanes) {
         const double r = (double)i;
         const double yi = profile[i] * scale, fi = f0[i], u0 = unit[i];
-        // A, B, m move the value but not the pow argument; c, alpha, beta need their own pow
-        const double uc = moffat_unit(r, x[1] + h[1], x[2], x[3]);
-        const double ua = moffat_unit(r, x[1], x[2] + h[2], x[3]);
-        const double ub_ = moffat_unit(r, x[1], x[2], x[3] + h[3]);
+        // A, B, m move the value but not the pow argument.  c, alpha, beta move it by a part in ~1e8:
+        // the shifted pow is the base pow times (s'/s)^-beta resp. s^-h, evaluated from the small
+        // relative change of s = 1 + q (shifted_unit); a full pow only when the step is not small.
+        const double off = r - x[1], off1 = r - c1;
+        const double q = (off * off) / aa;
+        const double s = 1.0 + q;
+        const double inv_s = 1.0 / s;
+        double uc, ua, ub_;
+        if (!shifted_unit(u0, (off1 * off1) / aa, q, inv_s, x[3], &uc)) uc = moffat_unit_call(r, c1, x[2], x[3]);
+        if (!shifted_unit(u0, (off * off) / aa1, q, inv_s, x[3], &ua)) ua = moffat_unit_call(r, x[1], a1, x[3]);
+        if (!shifted_unit_beta(u0, s, dx[3], &ub_)) ub_ = moffat_unit_call(r, x[1], x[2], x[3] + h[3]);
         double col[n];
-        col[0] = ((moffat_value(u0, r, x[0] + h[0], x[4], x[5]) - yi) - fi) / dx[0];
-        col[1] = ((moffat_value(uc, r, x[0], x[4], x[5]) - yi) - fi) / dx[1];
-        col[2] = ((moffat_value(ua, r, x[0], x[4], x[5]) - yi) - fi) / dx[2];
-        col[3] = ((moffat_value(ub_, r, x[0], x[4], x[5]) - yi) - fi) / dx[3];
-        col[4] = ((moffat_value(u0, r, x[0], x[4] + h[4], x[5]) - yi) - fi) / dx[4];
-        col[5] = ((moffat_value(u0, r, x[0], x[4], x[5] + h[5]) - yi) - fi) / dx[5];
+        col[0] = ((moffat_value(u0, r, x[0] + h[0], x[4], x[5]) - yi) - fi) * inv_dx[0];
+        col[1] = ((moffat_value(uc, r, x[0], x[4], x[5]) - yi) - fi) * inv_dx[1];
+        col[2] = ((moffat_value(ua, r, x[0], x[4], x[5]) - yi) - fi) * inv_dx[2];
+        col[3] = ((moffat_value(ub_, r, x[0], x[4], x[5]) - yi) - fi) * inv_dx[3];
+        col[4] = ((moffat_value(u0, r, x[0], x[4] + h[4], x[5]) - yi) - fi) * inv_dx[4];
+        col[5] = ((moffat_value(u0, r, x[0], x[4], x[5] + h[5]) - yi) - fi) * inv_dx[5];
 #pragma unroll
         for (int k = 0; k < n; ++k) { a[(size_t)k * m + i] = col[k]; gp[k] += col[k] * fi; }
     }
@@ -230,65 +277,61 @@ MOTES_HD void fit_evaluate(const Ctx& ctx, int m, const double* profile, double 
     double* a = slab + m;
     double* fcol = a + 6 * (size_t)m;
     double x[n], lb[n], ub[n];
+    const bool first = st->first != 0;
 #pragma unroll
-    for (int i = 0; i < n; ++i) { lb[i] = st->lb[i]; ub[i] = st->ub[i]; }
-    if (st->first) {
-#pragma unroll
-        for (int i = 0; i < n; ++i) x[i] = st->x[i];
-        double cost;
-        bool finite = residual_sweep_b(ctx, m, profile, scale, x, unit, fcol, &cost);
-        ctx.sync();
-        if (!finite) {
-            if (leader) st->status = kFitNonFinite;
-            ctx.sync();
-            return;
-        }
-        if (leader) { st->cost = cost; st->nfev = 1; st->njev = 1; }
-        linearize(ctx, m, profile, scale, x, lb, ub, unit, a, st);
-        return;
-    }
-#pragma unroll
-    for (int i = 0; i < n; ++i) x[i] = st->x_new[i];
+    for (int i = 0; i < n; ++i) { lb[i] = st->lb[i]; ub[i] = st->ub[i]; x[i] = first ? st->x[i] : st->x_new[i]; }
     const double cost_old = st->cost, radius = st->radius, step_h_norm = st->step_h_norm, predicted = st->predicted;
     const double step_norm = st->step_norm, x_norm = st->x_norm, alpha = st->alpha;
     const int nfev = st->nfev, njev = st->njev;
     double cost_new;
-    bool ok = residual_sweep_b(ctx, m, profile, scale, x, unit, fcol, &cost_new);
+    const bool ok = residual_sweep_b(ctx, m, profile, scale, x, unit, fcol, &cost_new);
     ctx.sync();                                   // every lane has read *st; lane 0 may write from here on
-    if (!ok) {
-        if (leader) { st->nfev = nfev + 1; st->radius = 0.25 * step_h_norm; }
-        ctx.sync();
-        return;
-    }
-    const double gain = cost_old - cost_new;
-    double ratio;
-    if (predicted > 0.0) ratio = gain / predicted;
-    else if (predicted == 0.0 && gain == 0.0) ratio = 1.0;
-    else ratio = 0.0;
-    double radius_new = radius;
-    if (ratio < 0.25) radius_new = 0.25 * step_h_norm;
-    else if (ratio > 0.75 && step_h_norm > 0.95 * radius) radius_new = radius * 2.0;
-    const bool f_ok = (gain < 1e-12 * cost_old) && (ratio > 0.25);
-    const bool x_ok = step_norm < 1e-8 * (1e-8 + x_norm);
-    int status = kStatusRunning;
-    if (f_ok && x_ok) status = kFitBoth;
-    else if (f_ok) status = kFitFtol;
-    else if (x_ok) status = kFitXtol;
-    if (leader) {
-        st->nfev = nfev + 1;
-        st->status = status;
-        if (status == kStatusRunning) {
-            st->alpha = alpha * (radius / radius_new);
-            st->radius = radius_new;
+    bool relinearize;
+    if (first) {
+        if (!ok) {
+            if (leader) st->status = kFitNonFinite;
+            ctx.sync();
+            return;
         }
-        if (gain > 0.0) {
+        if (leader) { st->cost = cost_new; st->nfev = 1; st->njev = 1; }
+        relinearize = true;
+    } else {
+        if (!ok) {
+            if (leader) { st->nfev = nfev + 1; st->radius = 0.25 * step_h_norm; }
+            ctx.sync();
+            return;
+        }
+        const double gain = cost_old - cost_new;
+        double ratio;
+        if (predicted > 0.0) ratio = gain / predicted;
+        else if (predicted == 0.0 && gain == 0.0) ratio = 1.0;
+        else ratio = 0.0;
+        double radius_new = radius;
+        if (ratio < 0.25) radius_new = 0.25 * step_h_norm;
+        else if (ratio > 0.75 && step_h_norm > 0.95 * radius) radius_new = radius * 2.0;
+        const bool f_ok = (gain < 1e-12 * cost_old) && (ratio > 0.25);
+        const bool x_ok = step_norm < 1e-8 * (1e-8 + x_norm);
+        int status = kStatusRunning;
+        if (f_ok && x_ok) status = kFitBoth;
+        else if (f_ok) status = kFitFtol;
+        else if (x_ok) status = kFitXtol;
+        if (leader) {
+            st->nfev = nfev + 1;
+            st->status = status;
+            if (status == kStatusRunning) {
+                st->alpha = alpha * (radius / radius_new);
+                st->radius = radius_new;
+            }
+            if (gain > 0.0) {
 #pragma unroll
-            for (int i = 0; i < n; ++i) st->x[i] = x[i];
-            st->cost = cost_new;
-            st->njev = njev + 1;      // scipy evaluates the Jacobian at the accepted point even when it then stops
+                for (int i = 0; i < n; ++i) st->x[i] = x[i];
+                st->cost = cost_new;
+                st->njev = njev + 1;  // scipy evaluates the Jacobian at the accepted point even when it then stops
+            }
         }
+        relinearize = gain > 0.0 && status == kStatusRunning;
     }
-    if (gain > 0.0 && status == kStatusRunning) linearize(ctx, m, profile, scale, x, lb, ub, unit, a, st);
+    if (relinearize) linearize(ctx, m, profile, scale, x, lb, ub, unit, a, st);
     ctx.sync();
 }
 

@@ -50,15 +50,23 @@ def test_solver_tracks_reference_fits(hostsim, name):
 
 
 @pytest.mark.parametrize("name", ["t1_sky0", "t1_faint", "c1_sky0"])
-def test_phased_solver_is_the_same_iteration(hostsim, name):
-    """The phase-split form the persistent GPU kernel runs takes the same decisions as the one-loop form."""
+def test_phased_solver_tracks_reference_fits(hostsim, name):
+    """The phase-split form the GPU group kernel runs (forward differences from the base pow instead of
+    a second pow) against the reference's fits, and against the one-loop form."""
     meta, g = load_golden(name)
-    profiles = g["ext_profiles"] * g["scale"]
+    scale = g["scale"]
+    profiles = g["ext_profiles"] * scale
     alpha0 = g["seeing_px"] / meta["spec"]["pixel_resolution"]
     a = _fit(hostsim, profiles, alpha0)
     b = _fit(hostsim, profiles, alpha0, entry="hostsim_fit_batch_phased")
-    assert np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3]) and np.array_equal(a[4], b[4])
-    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    ref = g["ext_params"][:, :6].copy()
+    ref[:, [0, 4, 5]] *= scale
+    err = param_errors(b[0], ref, profiles.shape[1])
+    assert np.all(b[4] >= 1) and np.all(b[4] <= 4)
+    assert_within_reference_noise(err, g, ref, scale, profiles.shape[1])
+    assert np.allclose(b[1], g["ext_fitinfo"][:, 3], rtol=1e-9)
+    assert np.mean(np.abs(b[2] - g["ext_fitinfo"][:, 0]) <= 1) > 0.8
+    assert np.mean(np.abs(b[2] - a[2]) <= 1) > 0.8
 
 
 def test_solver_error_codes(hostsim):
