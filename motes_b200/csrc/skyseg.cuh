@@ -113,48 +113,147 @@ mt_jump_kernel(const uint32_t* __restrict__ rng, uint32_t* __restrict__ windows,
 // ---- stream -----------------------------------------------------------------------------------
 // Segment k of frame f: words (k L, (k+1) L] of the stream (segment 0 also the 624 state words),
 // tempered and truncated to 16 bits; raw snapshots of the generator window at multiples of 2^16.
+//
+// The recurrence w[n] = mix(w[n-624], w[n-623]) ^ w[n-227] is run 454 words per barrier: thread
+// t < 227 produces w[n0] (n0 = gen + t) and w[n0 + 227]; the far operand of the first is the
+// thread's own second word of the previous round and that of the second is the word just made, so
+// both stay in registers.  The ring is 18 rows of 454 words and the loop is unrolled 18 times, which
+// turns every shared-memory and global address into "per-thread base + compile-time offset".
+constexpr int kRowWords = 2 * kSweep;                  // 454
+constexpr int kRingRows = 18;
+constexpr int kRingWords = kRingRows * kRowWords;       // 8172
+
+// ring address of stream word p (gen0 = first generated word; round j fills row (j + 2) % 18)
+__device__ __forceinline__ int stream_ring_slot(uint32_t p, uint32_t gen0) {
+    const int rel = (int)(p - gen0) + 2 * kRowWords;            // >= 284 for every word of the window
+    const int row = rel / kRowWords, col = rel - row * kRowWords;
+    return (row % kRingRows) * kRowWords + col;
+}
+
+template <int U>
+__device__ __forceinline__ void stream_round(uint32_t& far, const uint32_t* pa0, const uint32_t* pa0w, const uint32_t* pa1,
+                                             const uint32_t* pa1w, const uint32_t* pb, const uint32_t* pbw, uint32_t* pw,
+                                             uint32_t* pww, uint16_t* out_t) {
+    // operands of word n0: rows U / U + 1 (per thread), of word n1: row U + 1; results: row U + 2
+    const uint32_t a0 = (U == kRingRows - 1) ? pa0w[U * kRowWords] : pa0[U * kRowWords];
+    const uint32_t a1 = (U == kRingRows - 1) ? pa1w[U * kRowWords] : pa1[U * kRowWords];
+    const uint32_t* b = (U == kRingRows - 1) ? pbw : pb;
+    const uint32_t b0 = b[U * kRowWords], b1 = b[U * kRowWords + 1];
+    const uint32_t v0 = mt_mix(a0, a1, far);
+    const uint32_t v1 = mt_mix(b0, b1, v0);
+    uint32_t* w = (U >= kRingRows - 2) ? pww : pw;
+    w[U * kRowWords] = v0;
+    w[U * kRowWords + kSweep] = v1;
+    out_t[U * kRowWords] = (uint16_t)mt_temper(v0);
+    out_t[U * kRowWords + kSweep] = (uint16_t)mt_temper(v1);
+    far = v1;
+}
+
 __global__ void __launch_bounds__(256)
 mt_stream_kernel(const uint32_t* __restrict__ rng, const uint32_t* __restrict__ windows, SegLayout lay,
                  const int32_t* __restrict__ seg_need, uint16_t* __restrict__ stream, uint32_t* __restrict__ snaps) {
-    __shared__ uint32_t ring[kRing];
+    __shared__ uint32_t ring[kRingWords];
     const int f = blockIdx.y, k = blockIdx.x;
     if (k >= seg_need[f]) return;
     const uint32_t base = (uint32_t)k << lay.log2_stride;
+    const uint32_t gen0 = base + 624;
     const uint32_t* from = (k == 0) ? rng + (size_t)f * 625 : windows + ((size_t)f * lay.segs + k) * 624;
     uint16_t* out = stream + (size_t)f * lay.stream_len;
     uint32_t* snap = snaps + (size_t)f * lay.snaps * 624;
     for (int i = threadIdx.x; i < 624; i += blockDim.x) {
         const uint32_t v = from[i];
-        ring[(base + i) & (kRing - 1)] = v;
+        ring[stream_ring_slot(base + i, gen0)] = v;
         if (k == 0 || i >= 1) out[base + i] = (uint16_t)mt_temper(v);     // word 0 of a jumped window is not a stream word
         if (k == 0) snap[i] = v;
     }
     __syncthreads();
     const uint32_t last_out = base + lay.stride;            // last stream position this segment writes
-    const uint32_t stop = last_out + 624;                   // words [base + 624, stop) are needed
+    const uint32_t stop = last_out + 624;                   // words [gen0, stop) are needed (the tail feeds the last snapshot)
     uint32_t next_snap = ((base >> kSnapLog2) + 1) << kSnapLog2;
-    // Two words per thread and barrier: word n and word n + 227, whose "far" operand (n + 227 - 227)
-    // is the word just produced - it stays in a register, as does the far operand of the next round.
-    const uint32_t t = threadIdx.x;
-    uint32_t far = (t < (uint32_t)kSweep) ? ring[(base + 624 + t - kSweep) & (kRing - 1)] : 0u;
-    for (uint32_t gen = base + 624; gen < stop; gen += 2 * kSweep) {
-        if (t < (uint32_t)kSweep) {
-            const uint32_t n0 = gen + t, n1 = n0 + kSweep;
-            const uint32_t v0 = mt_mix(ring[(n0 - 624) & (kRing - 1)], ring[(n0 - 623) & (kRing - 1)], far);
-            const uint32_t v1 = mt_mix(ring[(n1 - 624) & (kRing - 1)], ring[(n1 - 623) & (kRing - 1)], v0);
-            ring[n0 & (kRing - 1)] = v0;
-            ring[n1 & (kRing - 1)] = v1;
+    const int t = threadIdx.x;
+    const bool worker = t < kSweep;
+    auto take_snapshot = [&](uint32_t have) {               // after a barrier; words below `have` exist
+        if (next_snap <= last_out && next_snap + 624 <= have) {
+            uint32_t* dst = snap + (size_t)(next_snap >> kSnapLog2) * 624;
+            for (int i = threadIdx.x; i < 624; i += blockDim.x) dst[i] = ring[stream_ring_slot(next_snap + i, gen0)];
+            next_snap += kSnapStride;
+        }
+    };
+    // per-thread operand columns (see the header comment); "w" pointers serve the rounds that wrap
+    const int tt = worker ? t : 0;
+    const int oa0 = (tt < 170) ? tt + 284 : kRowWords + tt - 170;
+    const int oa1 = (tt < 169) ? tt + 285 : kRowWords + tt - 169;
+    const uint32_t* pa0 = ring + oa0;
+    const uint32_t* pa1 = ring + oa1;
+    const uint32_t* pa0w = ring + (oa0 + (kRingRows - 1) * kRowWords) % kRingWords - (kRingRows - 1) * kRowWords;
+    const uint32_t* pa1w = ring + (oa1 + (kRingRows - 1) * kRowWords) % kRingWords - (kRingRows - 1) * kRowWords;
+    const uint32_t* pb = ring + kRowWords + tt + 57;
+    const uint32_t* pbw = pb - kRingWords;
+    uint32_t* pw = ring + 2 * kRowWords + tt;
+    uint32_t* pww = pw - kRingWords;
+    uint32_t far = ring[kRowWords + kSweep + tt];            // word gen0 + t - 227
+    uint32_t gen = gen0;
+    uint16_t* out_t = out + gen0 + tt;
+    // ---- full blocks of 18 rounds, every output inside the segment
+    while (gen + (uint32_t)kRingWords <= last_out + 1u) {
+        if (worker) {
+            stream_round<0>(far, pa0, pa0w, pa1, pa1w, pb, pbw, pw, pww, out_t);
+        }
+        __syncthreads();
+        if (worker) stream_round<1>(far, pa0, pa0w, pa1, pa1w, pb, pbw, pw, pww, out_t);
+        __syncthreads();
+        if (worker) stream_round<2>(far, pa0, pa0w, pa1, pa1w, pb, pbw, pw, pww, out_t);
+        __syncthreads();
+        if (worker) stream_round<3>(far, pa0, pa0w, pa1, pa1w, pb, pbw, pw, pww, out_t);
+        __syncthreads();
+        if (worker) stream_round<4>(far, pa0, pa0w, pa1, pa1w, pb, pbw, pw, pww, out_t);
+        __syncthreads();
+        if (worker) stream_round<5>(far, pa0, pa0w, pa1, pa1w, pb, pbw, pw, pww, out_t);
+        __syncthreads();
+        if (worker) stream_round<6>(far, pa0, pa0w, pa1, pa1w, pb, pbw, pw, pww, out_t);
+        __syncthreads();
+        if (worker) stream_round<7>(far, pa0, pa0w, pa1, pa1w, pb, pbw, pw, pww, out_t);
+        __syncthreads();
+        if (worker) stream_round<8>(far, pa0, pa0w, pa1, pa1w, pb, pbw, pw, pww, out_t);
+        __syncthreads();
+        take_snapshot(gen + 9u * kRowWords);
+        if (worker) stream_round<9>(far, pa0, pa0w, pa1, pa1w, pb, pbw, pw, pww, out_t);
+        __syncthreads();
+        if (worker) stream_round<10>(far, pa0, pa0w, pa1, pa1w, pb, pbw, pw, pww, out_t);
+        __syncthreads();
+        if (worker) stream_round<11>(far, pa0, pa0w, pa1, pa1w, pb, pbw, pw, pww, out_t);
+        __syncthreads();
+        if (worker) stream_round<12>(far, pa0, pa0w, pa1, pa1w, pb, pbw, pw, pww, out_t);
+        __syncthreads();
+        if (worker) stream_round<13>(far, pa0, pa0w, pa1, pa1w, pb, pbw, pw, pww, out_t);
+        __syncthreads();
+        if (worker) stream_round<14>(far, pa0, pa0w, pa1, pa1w, pb, pbw, pw, pww, out_t);
+        __syncthreads();
+        if (worker) stream_round<15>(far, pa0, pa0w, pa1, pa1w, pb, pbw, pw, pww, out_t);
+        __syncthreads();
+        if (worker) stream_round<16>(far, pa0, pa0w, pa1, pa1w, pb, pbw, pw, pww, out_t);
+        __syncthreads();
+        if (worker) stream_round<17>(far, pa0, pa0w, pa1, pa1w, pb, pbw, pw, pww, out_t);
+        __syncthreads();
+        gen += (uint32_t)kRingWords;
+        out_t += kRingWords;
+        take_snapshot(gen);
+    }
+    // ---- tail: generic rounds (the rest of the segment and the 624 words behind it)
+    // gen - gen0 is a multiple of 8172 here, so round j of the tail again fills row (j + 2) % 18
+    for (int j = 0; gen < stop; ++j, gen += (uint32_t)kRowWords) {
+        if (worker) {
+            const uint32_t n0 = gen + (uint32_t)t, n1 = n0 + (uint32_t)kSweep;
+            const uint32_t v0 = mt_mix(ring[stream_ring_slot(n0 - 624, gen0)], ring[stream_ring_slot(n0 - 623, gen0)], far);
+            const uint32_t v1 = mt_mix(ring[stream_ring_slot(n1 - 624, gen0)], ring[stream_ring_slot(n1 - 623, gen0)], v0);
+            ring[stream_ring_slot(n0, gen0)] = v0;
+            ring[stream_ring_slot(n1, gen0)] = v1;
             if (n0 <= last_out) out[n0] = (uint16_t)mt_temper(v0);
             if (n1 <= last_out) out[n1] = (uint16_t)mt_temper(v1);
             far = v1;
         }
         __syncthreads();
-        const uint32_t have = gen + 2u * kSweep;                          // words below `have` exist
-        if (next_snap <= last_out && next_snap + 624 <= have) {
-            uint32_t* dst = snap + (size_t)(next_snap >> kSnapLog2) * 624;
-            for (int i = threadIdx.x; i < 624; i += blockDim.x) dst[i] = ring[(next_snap + i) & (kRing - 1)];
-            next_snap += kSnapStride;
-        }
+        if ((j % 9) == 8 || gen + (uint32_t)kRowWords >= stop) take_snapshot(gen + (uint32_t)kRowWords);
     }
 }
 
@@ -389,59 +488,77 @@ struct ColShared {
     double* sq;          // 100
 };
 
-// median of every bootstrap sample from its n rank slots: bitwise binary search, one warp per sample
+// median of every bootstrap sample from its n rank slots: bitwise binary search, one warp per sample.
+// Packed path (n <= 64 NW): each lane keeps NW words = 2 NW ranks in registers; "rank >= cand" for
+// both halves of a word is bit 15 of (half + 0x8000 - cand).
+template <int NW>
+__device__ __forceinline__ void column_medians_packed(const ColShared& sh, int n, int rw, const double* __restrict__ srt,
+                                                      int lane, int warp, int nwarps) {
+    const int k1 = (n - 1) / 2, k2 = n / 2;
+    int nbits = 1;
+    while ((1 << nbits) < n) ++nbits;
+    const int nwords = (n + 1) >> 1;
+    constexpr int slots_total = 64 * NW;
+    for (int smp = warp; smp < kBootstrap; smp += nwarps) {
+        const uint32_t* row = sh.slots + smp * rw;
+        uint32_t reg[NW];
+#pragma unroll
+        for (int t = 0; t < NW; ++t) {
+            const int wd = lane + 32 * t;
+            uint32_t wv = 0x7fff7fffu;                      // padding: larger than any rank
+            if (wd < nwords) {
+                wv = row[wd];
+                if (2 * wd + 1 >= n) wv = (wv & 0xffffu) | 0x7fff0000u;
+            }
+            reg[t] = wv;
+        }
+        int x1 = 0;
+        for (int bit = nbits - 1; bit >= 0; --bit) {
+            const int cand = x1 | (1 << bit);
+            const uint32_t kk = (uint32_t)(0x8000 - cand) * 0x00010001u;
+            uint32_t ge = 0;
+#pragma unroll
+            for (int t = 0; t < NW; ++t) ge += ((reg[t] + kk) >> 15) & 0x00010001u;
+            const int ge_all = __reduce_add_sync(0xffffffffu, (int)((ge & 0xffffu) + (ge >> 16)));
+            if (slots_total - ge_all <= k1) x1 = cand;
+        }
+        int x2 = x1;
+        if (k2 != k1) {
+            const uint32_t kk = (uint32_t)(0x8000 - (x1 + 1)) * 0x00010001u;
+            uint32_t ge = 0;
+            int nxt = 0x7fff;
+#pragma unroll
+            for (int t = 0; t < NW; ++t) {
+                ge += ((reg[t] + kk) >> 15) & 0x00010001u;
+                const int h0 = (int)(reg[t] & 0xffffu), h1 = (int)(reg[t] >> 16);
+                if (h0 > x1 && h0 < nxt) nxt = h0;
+                if (h1 > x1 && h1 < nxt) nxt = h1;
+            }
+            const int le = slots_total - __reduce_add_sync(0xffffffffu, (int)((ge & 0xffffu) + (ge >> 16)));
+            nxt = __reduce_min_sync(0xffffffffu, nxt);
+            if (le <= k2) x2 = nxt;
+        }
+        if (lane == 0) sh.meds[smp] = (k1 == k2) ? srt[x1] : (srt[x1] + srt[x2]) * 0.5;
+    }
+}
+
 __device__ __forceinline__ void column_medians(const ColShared& sh, int n, int rw, const double* __restrict__ srt,
                                                int lane, int warp, int nwarps) {
+    switch ((n + 63) >> 6) {
+        case 1: column_medians_packed<1>(sh, n, rw, srt, lane, warp, nwarps); return;
+        case 2: column_medians_packed<2>(sh, n, rw, srt, lane, warp, nwarps); return;
+        case 3: column_medians_packed<3>(sh, n, rw, srt, lane, warp, nwarps); return;
+        case 4: column_medians_packed<4>(sh, n, rw, srt, lane, warp, nwarps); return;
+        case 5: column_medians_packed<5>(sh, n, rw, srt, lane, warp, nwarps); return;
+        case 6: column_medians_packed<6>(sh, n, rw, srt, lane, warp, nwarps); return;
+        case 7: column_medians_packed<7>(sh, n, rw, srt, lane, warp, nwarps); return;
+        case 8: column_medians_packed<8>(sh, n, rw, srt, lane, warp, nwarps); return;
+        default: break;
+    }
     const int k1 = (n - 1) / 2, k2 = n / 2;
     int nbits = 1;
     while ((1 << nbits) < n) ++nbits;
     const uint16_t* slots16 = reinterpret_cast<const uint16_t*>(sh.slots);
-    if (n <= 64 * kPackWords) {
-        const int nwords = (n + 1) >> 1;
-        for (int smp = warp; smp < kBootstrap; smp += nwarps) {
-            const uint32_t* row = sh.slots + smp * rw;
-            uint32_t reg[kPackWords];
-#pragma unroll
-            for (int t = 0; t < kPackWords; ++t) {
-                const int wd = lane + 32 * t;
-                uint32_t wv = 0x7fff7fffu;                      // padding: larger than any rank
-                if (wd < nwords) {
-                    wv = row[wd];
-                    if (2 * wd + 1 >= n) wv = (wv & 0xffffu) | 0x7fff0000u;
-                }
-                reg[t] = wv;
-            }
-            const int slots_total = 64 * kPackWords;
-            int x1 = 0;
-            for (int bit = nbits - 1; bit >= 0; --bit) {
-                const int cand = x1 | (1 << bit);
-                const uint32_t kk = (uint32_t)(0x8000 - cand) * 0x00010001u;
-                uint32_t ge = 0;
-#pragma unroll
-                for (int t = 0; t < kPackWords; ++t) ge += ((reg[t] + kk) >> 15) & 0x00010001u;
-                const int ge_all = __reduce_add_sync(0xffffffffu, (int)((ge & 0xffffu) + (ge >> 16)));
-                if (slots_total - ge_all <= k1) x1 = cand;
-            }
-            int x2 = x1;
-            if (k2 != k1) {
-                const uint32_t kk = (uint32_t)(0x8000 - (x1 + 1)) * 0x00010001u;
-                uint32_t ge = 0;
-                int nxt = 0x7fff;
-#pragma unroll
-                for (int t = 0; t < kPackWords; ++t) {
-                    ge += ((reg[t] + kk) >> 15) & 0x00010001u;
-                    const int h0 = (int)(reg[t] & 0xffffu), h1 = (int)(reg[t] >> 16);
-                    if (h0 > x1 && h0 < nxt) nxt = h0;
-                    if (h1 > x1 && h1 < nxt) nxt = h1;
-                }
-                const int le = slots_total - __reduce_add_sync(0xffffffffu, (int)((ge & 0xffffu) + (ge >> 16)));
-                nxt = __reduce_min_sync(0xffffffffu, nxt);
-                if (le <= k2) x2 = nxt;
-            }
-            if (lane == 0) sh.meds[smp] = (k1 == k2) ? srt[x1] : (srt[x1] + srt[x2]) * 0.5;
-        }
-        return;
-    }
     for (int smp = warp; smp < kBootstrap; smp += nwarps) {
         const uint16_t* row = slots16 + smp * (2 * rw);
         int x1 = 0;
@@ -539,28 +656,34 @@ sky_column_kernel(const uint16_t* __restrict__ stream, SegLayout lay, int nspat,
                         if (row >= end) break;
                         const uint32_t pos = row + 4u * lane;
                         const uint2 raw = raw4[r];
-                        const uint32_t v[4] = {raw.x & 0xffffu & mask, (raw.x >> 16) & mask, raw.y & 0xffffu & mask,
-                                               (raw.y >> 16) & mask};
-                        bool acc[4];
-                        unsigned bal[4];
-                        int before = 0, total = 0;
+                        const uint32_t v[4] = {raw.x & mask, (raw.x >> 16) & mask, raw.y & mask, (raw.y >> 16) & mask};
+                        // this lane's four words, in stream order: bit e of m4 = word e is an accepted draw
+                        unsigned m4 = (unsigned)(v[0] <= top) | ((unsigned)(v[1] <= top) << 1) |
+                                      ((unsigned)(v[2] <= top) << 2) | ((unsigned)(v[3] <= top) << 3);
+                        if (row < start || row + 128u > end) {           // first / last row of the piece
+                            unsigned inside = 0;
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const uint32_t p = pos + (uint32_t)e;
-                            acc[e] = (v[e] <= top) && (p >= start) && (p < end);
-                            bal[e] = __ballot_sync(0xffffffffu, acc[e]);
-                            before += __popc(bal[e] & lanes_below);
-                            total += __popc(bal[e]);
+                            for (int e = 0; e < 4; ++e) inside |= (unsigned)(pos + e >= start && pos + e < end) << e;
+                            m4 &= inside;
                         }
-                        int ord = ord0 + before;
+                        const int cnt = __popc(m4);
+                        // ordinal of the lane's first accept: accepts of the lower lanes (count <= 4: three ballots)
+                        const unsigned c0 = __ballot_sync(0xffffffffu, cnt & 1), c1 = __ballot_sync(0xffffffffu, cnt & 2),
+                                       c2 = __ballot_sync(0xffffffffu, cnt & 4);
+                        const int before = __popc(c0 & lanes_below) + 2 * __popc(c1 & lanes_below) + 4 * __popc(c2 & lanes_below);
+                        const int total = __popc(c0) + 2 * __popc(c1) + 4 * __popc(c2);
+                        if (ord0 + total <= need) {                       // always, unless walk and column disagree
+                            const int ord = ord0 + before;
+                            const int pix = ord / kBootstrap;
+                            int smp = ord - pix * kBootstrap;
+                            int at = smp * (2 * rw) + pix;                // slot of ordinal ord; the next one is a row down
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            if (acc[e]) {
-                                if (ord < need) {
-                                    const int pix = ord / kBootstrap, smp = ord - pix * kBootstrap;
-                                    slots16[smp * (2 * rw) + pix] = sh.ranks[v[e]];
+                            for (int e = 0; e < 4; ++e) {
+                                if (m4 & (1u << e)) {
+                                    slots16[at] = sh.ranks[v[e]];
+                                    at += 2 * rw;
+                                    if (++smp == kBootstrap) { smp = 0; at -= kBootstrap * 2 * rw - 1; }
                                 }
-                                ++ord;
                             }
                         }
                         ord0 += total;
