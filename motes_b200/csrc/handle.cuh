@@ -92,6 +92,14 @@ struct motes_handle {
     motes::Scratch stage[12];
     motes::Scratch work[24];
     motes::Scratch counters;    // small zero-initialised control block
+    // second lane: sub-batches of one call alternate between two streams (each with its own work areas) so
+    // that the latency-bound stages of one overlap the throughput-bound stages of the other
+    cudaStream_t lane1_stream = nullptr;
+    motes::Scratch lane1_work[24];
+    motes::Scratch lane1_counters;
+    cudaStream_t copy_stream = nullptr;     // host-to-device uploads of the next sub-batch
+    std::vector<cudaEvent_t> events;
+    int chunks = 0;              // MOTES_B200_CHUNKS: sub-batches per call (0 = auto)
     bool profiling = false;
     int fit_mode = 0;            // MOTES_B200_FIT: 0 batched persistent grid (default), 1 one warp per fit
     int boot_mode = 0;           // MOTES_B200_BOOTSTRAP: 0 segmented (default), 1 classic (one CTA per frame), 2 warp-specialised

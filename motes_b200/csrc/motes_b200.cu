@@ -3,6 +3,7 @@
 #include "kernels.cuh"
 #include "skyseg.cuh"
 #include "mtjump.hpp"
+#include <utility>
 
 namespace motes {
 
@@ -502,6 +503,116 @@ static int run_frames_core(motes_handle* h, Batch& b, double* data, double* errs
     return emit();
 }
 
+// Copies one sub-batch's results into the caller's block at frame offset f0.
+template <cudaMemcpyKind KIND>
+static int emit_outputs(motes_handle* h, const Batch& b, const motes_params& p, const motes_outputs& o, int f0) {
+    const size_t F = b.F, nd = b.ndisp, cp = b.cap, ns = b.nspat, at = (size_t)f0;
+    cudaStream_t st = h->stream;
+#define MOTES_PUT(dst, src, per_frame)                                                                              \
+    do {                                                                                                            \
+        if ((dst) && (src))                                                                                         \
+            MOTES_CUDA(cudaMemcpyAsync((dst) + at * (per_frame), (src), F * (per_frame) * sizeof(*(dst)), KIND, st)); \
+    } while (0)
+    MOTES_PUT(o.spectra, b.spectra, 4 * nd);
+    MOTES_PUT(o.ext_limits, b.limits[1], 2 * nd);
+    MOTES_PUT(o.ext_params, b.params8[1], cp * 8);
+    MOTES_PUT(o.ext_bins, b.bins_i[1], cp * 2);
+    MOTES_PUT(o.ext_bin_snr, b.bins_snr[1], cp);
+    MOTES_PUT(o.n_ext_bins, b.nbins[1], (size_t)1);
+    MOTES_PUT(o.n_sky_bins, b.nbins[0], (size_t)1);
+    if (p.subtract_sky) {
+        MOTES_PUT(o.sky_limits, b.limits[0], 2 * nd);
+        MOTES_PUT(o.sky_params, b.params8[0], cp * 8);
+        MOTES_PUT(o.sky_bins, b.bins_i[0], cp * 2);
+        MOTES_PUT(o.sky_bin_snr, b.bins_snr[0], cp);
+        if (p.sky_order > 0) {
+            MOTES_PUT(o.sky_model, b.model, nd * ns);
+            MOTES_PUT(o.sky_uncertainty, b.model_err, nd * ns);
+        } else {
+            MOTES_PUT(o.sky_model, b.sky, nd);
+            MOTES_PUT(o.sky_uncertainty, b.sky_err, nd);
+        }
+        MOTES_PUT(o.sky_flag, b.sky_flag, nd);
+    }
+#undef MOTES_PUT
+    if (o.median_params) MOTES_CUDA(cudaMemcpy2DAsync(o.median_params + at * 6, 6 * sizeof(double), b.st->median_params, sizeof(FrameState), 6 * sizeof(double), F, KIND, st));
+    if (o.scale) MOTES_CUDA(cudaMemcpy2DAsync(o.scale + at, sizeof(double), &b.st->scale, sizeof(FrameState), sizeof(double), F, KIND, st));
+    if (o.seeing_px) MOTES_CUDA(cudaMemcpy2DAsync(o.seeing_px + at, sizeof(double), &b.st->seeing_px, sizeof(FrameState), sizeof(double), F, KIND, st));
+    if (o.frame_status) MOTES_CUDA(cudaMemcpy2DAsync(o.frame_status + at, sizeof(int32_t), &b.st->status, sizeof(FrameState), sizeof(int32_t), F, KIND, st));
+    return MOTES_OK;
+}
+
+static void swap_lanes(motes_handle* h) {
+    std::swap(h->stream, h->lane1_stream);
+    for (int i = 0; i < 24; ++i) std::swap(h->work[i], h->lane1_work[i]);
+    std::swap(h->counters, h->lane1_counters);
+}
+
+static int get_event(motes_handle* h, size_t i, cudaEvent_t* ev) {
+    while (h->events.size() <= i) {
+        cudaEvent_t e;
+        MOTES_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        h->events.push_back(e);
+    }
+    *ev = h->events[i];
+    return MOTES_OK;
+}
+
+// Sub-batches per call (MOTES_B200_CHUNKS, default 1).  Measured on B200 with 128 frames of 4096 x 400:
+// 1 -> 253 ms, 2 -> 253 ms, 4 -> 308 ms, 8 -> 395 ms per step, and the host entry point loses more than the
+// overlapped upload gains: the throughput-bound kernels fill every SM, so the other lane's latency-bound
+// kernels queue behind them instead of running beside them, while every per-frame serial stage is paid
+// once per sub-batch.  The mechanism stays for callers whose batches exceed device memory.
+static int chunk_frames(const motes_handle* h, int nframes) {
+    int chunks = h->chunks > 0 ? h->chunks : 1;
+    if (chunks > nframes) chunks = nframes;
+    return (nframes + chunks - 1) / chunks;
+}
+
+// The whole path over device-resident frames [0, F), in sub-batches on alternating lanes.  `upload`
+// (optional) brings a sub-batch's frames to the device on the copy stream first; `emit` returns its
+// results.  On return the work is queued: lane 0 (h->stream) waits for lane 1.
+template <class Upload, class Emit>
+static int run_frames_chunked(motes_handle* h, double* data, double* errs, const uint8_t* qual, int nframes, int nspat,
+                              int ndisp, int cap, const motes_params& p, const double* seeing_dev,
+                              const double* pixres_dev, uint32_t* rng, Upload upload, Emit emit) {
+    const int per = chunk_frames(h, nframes);
+    const size_t frame_px = (size_t)nspat * ndisp;
+    cudaEvent_t ev_start, ev_done;
+    MOTES_TRY(get_event(h, 0, &ev_start));
+    MOTES_TRY(get_event(h, 1, &ev_done));
+    MOTES_CUDA(cudaEventRecord(ev_start, h->stream));
+    MOTES_CUDA(cudaStreamWaitEvent(h->lane1_stream, ev_start, 0));
+    MOTES_CUDA(cudaStreamWaitEvent(h->copy_stream, ev_start, 0));
+    int rc = MOTES_OK;
+    bool used_lane1 = false;
+    for (int f0 = 0, k = 0; f0 < nframes && rc == MOTES_OK; f0 += per, ++k) {
+        const int nf = (nframes - f0 < per) ? nframes - f0 : per;
+        cudaEvent_t ev_up;
+        rc = get_event(h, 2 + (size_t)k, &ev_up);
+        if (rc != MOTES_OK) break;
+        rc = upload(f0, nf, ev_up);                       // on h->copy_stream; records ev_up (or does nothing)
+        if (rc != MOTES_OK) break;
+        const bool lane1 = (k & 1) != 0 && nframes > per;
+        if (lane1) { swap_lanes(h); used_lane1 = true; }
+        rc = [&]() -> int {
+            MOTES_CUDA(cudaStreamWaitEvent(h->stream, ev_up, 0));
+            Batch b;
+            MOTES_TRY(make_batch(h, b, nf, nspat, ndisp, cap, p.subtract_sky != 0, p.sky_order > 0));
+            MOTES_TRY(run_frames_core(h, b, data + f0 * frame_px, errs + f0 * frame_px, qual + f0 * frame_px, p,
+                                      seeing_dev + f0, pixres_dev + f0, rng ? rng + (size_t)f0 * 625 : nullptr,
+                                      [&]() -> int { return emit(b, f0, nf); }));
+            return MOTES_OK;
+        }();
+        if (lane1) swap_lanes(h);
+    }
+    if (used_lane1) {
+        MOTES_CUDA(cudaEventRecord(ev_done, h->lane1_stream));
+        MOTES_CUDA(cudaStreamWaitEvent(h->stream, ev_done, 0));
+    }
+    return rc;
+}
+
 }  // namespace motes
 
 using namespace motes;
@@ -535,7 +646,11 @@ int motes_create(int device, motes_handle** out) {
     h->fit_mode = (fitm && strcmp(fitm, "warp") == 0) ? 1 : 0;
     const char* budget = getenv("MOTES_B200_STREAM_GB");
     if (budget && atof(budget) > 0.0) h->stream_budget = (size_t)(atof(budget) * 1073741824.0);
+    const char* chunks = getenv("MOTES_B200_CHUNKS");
+    if (chunks && atoi(chunks) > 0) h->chunks = atoi(chunks);
     e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->lane1_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete h; return fail_cuda(e, "cudaStreamCreate", __FILE__, __LINE__); }
     *out = h;
     return MOTES_OK;
@@ -546,9 +661,16 @@ int motes_destroy(motes_handle* h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (auto& s : h->stage) s.release();
+    if (h->lane1_stream) cudaStreamSynchronize(h->lane1_stream);
+    if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
     for (auto& s : h->work) s.release();
+    for (auto& s : h->lane1_work) s.release();
     h->counters.release();
+    h->lane1_counters.release();
     h->jump_polys.release();
+    for (auto& ev : h->events) cudaEventDestroy(ev);
+    if (h->lane1_stream) cudaStreamDestroy(h->lane1_stream);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->owns_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return MOTES_OK;
@@ -649,40 +771,16 @@ int motes_run_frames_dev(motes_handle* h, double* data, double* errs, const uint
                          uint32_t* rng_states, const motes_outputs* out) {
     MOTES_TRY(check_run_args(h, data, errs, qual, nframes, nspat, ndisp, cap, params, seeing, pixres, rng_states, out));
     MOTES_CUDA(cudaSetDevice(h->device));
-    Batch b;
-    MOTES_TRY(make_batch(h, b, nframes, nspat, ndisp, cap, params->subtract_sky != 0, params->sky_order > 0));
     const motes_params p = *params;
     const motes_outputs o = *out;
-    auto emit = [&]() -> int {
-        const size_t F = b.F, nd = b.ndisp, cp = b.cap;
-        MOTES_TRY(copy_dd(h, o.spectra, b.spectra, F * 4 * nd));
-        MOTES_TRY(copy_dd(h, o.ext_limits, b.limits[1], F * 2 * nd));
-        MOTES_TRY(copy_dd(h, o.ext_params, b.params8[1], F * cp * 8));
-        MOTES_TRY(copy_dd(h, o.ext_bins, b.bins_i[1], F * cp * 2));
-        MOTES_TRY(copy_dd(h, o.ext_bin_snr, b.bins_snr[1], F * cp));
-        MOTES_TRY(copy_dd(h, o.n_ext_bins, b.nbins[1], F));
-        MOTES_TRY(copy_dd(h, o.n_sky_bins, b.nbins[0], F));
-        if (p.subtract_sky) {
-            MOTES_TRY(copy_dd(h, o.sky_limits, b.limits[0], F * 2 * nd));
-            MOTES_TRY(copy_dd(h, o.sky_params, b.params8[0], F * cp * 8));
-            MOTES_TRY(copy_dd(h, o.sky_bins, b.bins_i[0], F * cp * 2));
-            MOTES_TRY(copy_dd(h, o.sky_bin_snr, b.bins_snr[0], F * cp));
-            if (p.sky_order > 0) {
-                MOTES_TRY(copy_dd(h, o.sky_model, b.model, F * nd * b.nspat));
-                MOTES_TRY(copy_dd(h, o.sky_uncertainty, b.model_err, F * nd * b.nspat));
-            } else {
-                MOTES_TRY(copy_dd(h, o.sky_model, b.sky, F * nd));
-                MOTES_TRY(copy_dd(h, o.sky_uncertainty, b.sky_err, F * nd));
-            }
-            MOTES_TRY(copy_dd(h, o.sky_flag, b.sky_flag, F * nd));
-        }
-        if (o.median_params) MOTES_CUDA(cudaMemcpy2DAsync(o.median_params, 6 * sizeof(double), b.st->median_params, sizeof(FrameState), 6 * sizeof(double), F, cudaMemcpyDeviceToDevice, h->stream));
-        if (o.scale) MOTES_CUDA(cudaMemcpy2DAsync(o.scale, sizeof(double), &b.st->scale, sizeof(FrameState), sizeof(double), F, cudaMemcpyDeviceToDevice, h->stream));
-        if (o.seeing_px) MOTES_CUDA(cudaMemcpy2DAsync(o.seeing_px, sizeof(double), &b.st->seeing_px, sizeof(FrameState), sizeof(double), F, cudaMemcpyDeviceToDevice, h->stream));
-        if (o.frame_status) MOTES_CUDA(cudaMemcpy2DAsync(o.frame_status, sizeof(int32_t), &b.st->status, sizeof(FrameState), sizeof(int32_t), F, cudaMemcpyDeviceToDevice, h->stream));
+    cudaEvent_t ev_none;
+    MOTES_TRY(get_event(h, 0, &ev_none));
+    auto upload = [&](int, int, cudaEvent_t ev) -> int {
+        MOTES_CUDA(cudaEventRecord(ev, h->copy_stream));      // nothing to upload: the event is immediately reachable
         return MOTES_OK;
     };
-    return run_frames_core(h, b, data, errs, qual, p, seeing, pixres, rng_states, emit);
+    auto emit = [&](const Batch& b, int f0, int) -> int { return emit_outputs<cudaMemcpyDeviceToDevice>(h, b, p, o, f0); };
+    return run_frames_chunked(h, data, errs, qual, nframes, nspat, ndisp, cap, p, seeing, pixres, rng_states, upload, emit);
 }
 
 int motes_run_frames_host(motes_handle* h, double* data, double* errs, const uint8_t* qual, int nframes, int nspat,
@@ -690,57 +788,47 @@ int motes_run_frames_host(motes_handle* h, double* data, double* errs, const uin
                           uint32_t* rng_states, int copy_back, const motes_outputs* out) {
     MOTES_TRY(check_run_args(h, data, errs, qual, nframes, nspat, ndisp, cap, params, seeing, pixres, rng_states, out));
     MOTES_CUDA(cudaSetDevice(h->device));
-    Batch b;
-    MOTES_TRY(make_batch(h, b, nframes, nspat, ndisp, cap, params->subtract_sky != 0, params->sky_order > 0));
     const motes_params p = *params;
     const motes_outputs o = *out;
-    const size_t npix = (size_t)nframes * nspat * ndisp;
+    const size_t frame_px = (size_t)nspat * ndisp;
+    const size_t npix = (size_t)nframes * frame_px;
     double *d_data, *d_errs, *d_seeing, *d_pixres;
     uint8_t* d_qual;
     uint32_t* d_rng = nullptr;
-    MOTES_TRY(upload(h, h->stage[0], data, npix, &d_data));
-    MOTES_TRY(upload(h, h->stage[1], errs, npix, &d_errs));
-    MOTES_TRY(upload(h, h->stage[2], qual, npix, &d_qual));
+    // frames go up sub-batch by sub-batch on the copy stream (below); the small per-frame arrays go now
+    MOTES_TRY(upload<double>(h, h->stage[0], nullptr, npix, &d_data));
+    MOTES_TRY(upload<double>(h, h->stage[1], nullptr, npix, &d_errs));
+    MOTES_TRY(upload<uint8_t>(h, h->stage[2], nullptr, npix, &d_qual));
     MOTES_TRY(upload(h, h->stage[3], seeing, (size_t)nframes, &d_seeing));
     MOTES_TRY(upload(h, h->stage[4], pixres, (size_t)nframes, &d_pixres));
     if (rng_states) MOTES_TRY(upload(h, h->stage[5], rng_states, (size_t)nframes * 625, &d_rng));
-    auto emit = [&]() -> int {
-        const size_t F = b.F, nd = b.ndisp, cp = b.cap;
-        MOTES_TRY(download(h, o.spectra, b.spectra, F * 4 * nd));
-        MOTES_TRY(download(h, o.ext_limits, b.limits[1], F * 2 * nd));
-        MOTES_TRY(download(h, o.ext_params, b.params8[1], F * cp * 8));
-        MOTES_TRY(download(h, o.ext_bins, b.bins_i[1], F * cp * 2));
-        MOTES_TRY(download(h, o.ext_bin_snr, b.bins_snr[1], F * cp));
-        MOTES_TRY(download(h, o.n_ext_bins, b.nbins[1], F));
-        MOTES_TRY(download(h, o.n_sky_bins, b.nbins[0], F));
-        if (p.subtract_sky) {
-            MOTES_TRY(download(h, o.sky_limits, b.limits[0], F * 2 * nd));
-            MOTES_TRY(download(h, o.sky_params, b.params8[0], F * cp * 8));
-            MOTES_TRY(download(h, o.sky_bins, b.bins_i[0], F * cp * 2));
-            MOTES_TRY(download(h, o.sky_bin_snr, b.bins_snr[0], F * cp));
-            if (p.sky_order > 0) {
-                MOTES_TRY(download(h, o.sky_model, b.model, F * nd * b.nspat));
-                MOTES_TRY(download(h, o.sky_uncertainty, b.model_err, F * nd * b.nspat));
-            } else {
-                MOTES_TRY(download(h, o.sky_model, b.sky, F * nd));
-                MOTES_TRY(download(h, o.sky_uncertainty, b.sky_err, F * nd));
-            }
-            MOTES_TRY(download(h, o.sky_flag, b.sky_flag, F * nd));
-            MOTES_TRY(download(h, rng_states, d_rng, F * 625));
-        }
-        if (o.median_params) MOTES_CUDA(cudaMemcpy2DAsync(o.median_params, 6 * sizeof(double), b.st->median_params, sizeof(FrameState), 6 * sizeof(double), F, cudaMemcpyDeviceToHost, h->stream));
-        if (o.scale) MOTES_CUDA(cudaMemcpy2DAsync(o.scale, sizeof(double), &b.st->scale, sizeof(FrameState), sizeof(double), F, cudaMemcpyDeviceToHost, h->stream));
-        if (o.seeing_px) MOTES_CUDA(cudaMemcpy2DAsync(o.seeing_px, sizeof(double), &b.st->seeing_px, sizeof(FrameState), sizeof(double), F, cudaMemcpyDeviceToHost, h->stream));
-        if (o.frame_status) MOTES_CUDA(cudaMemcpy2DAsync(o.frame_status, sizeof(int32_t), &b.st->status, sizeof(FrameState), sizeof(int32_t), F, cudaMemcpyDeviceToHost, h->stream));
+    auto upload_chunk = [&](int f0, int nf, cudaEvent_t ev) -> int {
+        const size_t off = (size_t)f0 * frame_px, cnt = (size_t)nf * frame_px;
+        MOTES_CUDA(cudaMemcpyAsync(d_data + off, data + off, cnt * sizeof(double), cudaMemcpyHostToDevice, h->copy_stream));
+        MOTES_CUDA(cudaMemcpyAsync(d_errs + off, errs + off, cnt * sizeof(double), cudaMemcpyHostToDevice, h->copy_stream));
+        MOTES_CUDA(cudaMemcpyAsync(d_qual + off, qual + off, cnt, cudaMemcpyHostToDevice, h->copy_stream));
+        MOTES_CUDA(cudaEventRecord(ev, h->copy_stream));
+        return MOTES_OK;
+    };
+    auto emit = [&](const Batch& b, int f0, int nf) -> int {
+        MOTES_TRY(emit_outputs<cudaMemcpyDeviceToHost>(h, b, p, o, f0));
+        if (p.subtract_sky && rng_states)
+            MOTES_CUDA(cudaMemcpyAsync(rng_states + (size_t)f0 * 625, d_rng + (size_t)f0 * 625, (size_t)nf * 625 * sizeof(uint32_t),
+                                       cudaMemcpyDeviceToHost, h->stream));
         if (copy_back) {
-            MOTES_TRY(download(h, data, d_data, npix));
-            MOTES_TRY(download(h, errs, d_errs, npix));
+            const size_t off = (size_t)f0 * frame_px, cnt = (size_t)nf * frame_px;
+            MOTES_CUDA(cudaMemcpyAsync(data + off, d_data + off, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+            MOTES_CUDA(cudaMemcpyAsync(errs + off, d_errs + off, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         }
         return MOTES_OK;
     };
-    MOTES_TRY(run_frames_core(h, b, d_data, d_errs, d_qual, p, d_seeing, d_pixres, d_rng, emit));
+    int rc = run_frames_chunked(h, d_data, d_errs, d_qual, nframes, nspat, ndisp, cap, p, d_seeing, d_pixres, d_rng,
+                                upload_chunk, emit);
+    // the caller's buffers must not be touched after return, whatever happened
+    cudaStreamSynchronize(h->copy_stream);
+    cudaStreamSynchronize(h->lane1_stream);
     MOTES_CUDA(cudaStreamSynchronize(h->stream));
-    return MOTES_OK;
+    return rc;
 }
 
 // ------------------------------------------------------------------------------------------ stage entry points

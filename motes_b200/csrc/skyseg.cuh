@@ -313,6 +313,15 @@ __device__ __forceinline__ int walk_count8_packed(const uint4& d, uint32_t mask2
     return 8 - __popc(r0 | (r1 >> 1) | (r2 >> 2) | (r3 >> 3));
 }
 
+// the 8 words at pos0 .. pos0 + 7 of a piece that ends inside the stream: packed count, with the words in
+// front of the column start `from` left out (only the one group that straddles `from` takes the slow path)
+__device__ __forceinline__ int walk_count8_from(const uint4& d, uint32_t pos0, uint32_t from, uint32_t limit,
+                                                uint32_t mask, uint32_t top, uint32_t mask2, uint32_t kk2) {
+    if (pos0 >= from) return walk_count8_packed(d, mask2, kk2);
+    if (pos0 + 8u <= from) return 0;
+    return walk_count8(d, pos0, from, limit, mask, top);
+}
+
 constexpr int kWalkThreads = 1024;
 constexpr int kWalkWarps = kWalkThreads / 32;
 constexpr int kSubPerChunk = kWalkChunk / kSubChunk;       // 4
@@ -381,8 +390,8 @@ sky_walk_kernel(const uint16_t* __restrict__ stream, SegLayout lay, const uint32
             if ((piece0 << kSubLog2) >= limit) { failed = true; break; }
             // span: the pieces the rest of the column is expected to need, +1, at most one per warp and
             // never more than the ring holds beyond the chunk the span starts in
-            const unsigned long long expect = ((unsigned long long)(need - have) * (mask + 1ull)) / (unsigned long long)n;
-            unsigned long long want = (expect >> kSubLog2) + 2ull;
+            const float expect = (float)(need - have) * __fdividef((float)(mask + 1u), (float)n);     // words, a heuristic
+            unsigned long long want = (unsigned long long)(expect * (1.0f / (float)kSubChunk)) + 2ull;
             const uint32_t room = (uint32_t)(kWalkStages - 1) * kSubPerChunk;
             int span = (int)(want < (unsigned long long)kWalkWarps ? want : (unsigned long long)kWalkWarps);
             if ((uint32_t)span > room) span = (int)room;
@@ -396,10 +405,14 @@ sky_walk_kernel(const uint16_t* __restrict__ stream, SegLayout lay, const uint32
                 mbar_wait(&full[stage], (chunk / kWalkStages) & 1u);
                 const uint4* src = reinterpret_cast<const uint4*>(walk_smem + (size_t)stage * kWalkChunkBytes +
                                                                   (size_t)((sb - first) % kWalkChunk) * 2);
-                const bool interior = packed_ok && sb >= P && sb + kSubChunk <= limit;
-                if (interior) {
+                if (packed_ok && sb >= P && sb + kSubChunk <= limit) {
 #pragma unroll
                     for (int k = 0; k < 8; ++k) cnt += walk_count8_packed(src[k * 32 + lane], mask2, kk2);
+                } else if (packed_ok && sb + kSubChunk <= limit) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        cnt += walk_count8_from(src[k * 32 + lane], sb + (uint32_t)(k * 256 + lane * 8), P, limit, mask, top,
+                                                mask2, kk2);
                 } else {
 #pragma unroll
                     for (int k = 0; k < 8; ++k)
@@ -438,7 +451,9 @@ sky_walk_kernel(const uint16_t* __restrict__ stream, SegLayout lay, const uint32
                     for (int k = 0; k < 8; ++k) {
                         const uint4 d = src[k * 32 + lane];
                         const uint32_t pos0 = sb + (uint32_t)(k * 256 + lane * 8);
-                        const uint32_t mine = (uint32_t)walk_count8(d, pos0, P, limit, mask, top);
+                        const uint32_t mine = (packed_ok && sb + kSubChunk <= limit)
+                                                  ? (uint32_t)walk_count8_from(d, pos0, P, limit, mask, top, mask2, kk2)
+                                                  : (uint32_t)walk_count8(d, pos0, P, limit, mask, top);
                         uint32_t li = mine;
 #pragma unroll
                         for (int o = 1; o < 32; o <<= 1) {
