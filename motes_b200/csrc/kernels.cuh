@@ -283,10 +283,18 @@ __device__ __forceinline__ double fit_frame_scalar(const double* base, size_t st
     return stride ? *reinterpret_cast<const double*>(reinterpret_cast<const char*>(base) + f * stride) : base[idx];
 }
 
+constexpr int kFitTeams = kFitThreads / 8;        // 8-lane teams of the step phase
+constexpr int kFitStepScratch = kFitTeams * 36 + 48;   // V per team, an identity R and a zero z for idle teams
+
 MOTES_HD size_t fit_group_smem(int m, int group) {
-    return (fit_sweep_doubles(m) + FitBlockCtx::kRedDoubles) * sizeof(double) + (size_t)group * sizeof(FitState);
+    return (fit_sweep_doubles(m) + FitBlockCtx::kRedDoubles + kFitStepScratch) * sizeof(double) +
+           (size_t)group * sizeof(FitState);
 }
 
+// out of line: the step logic is long, runs once per round and must not bloat the sweep loop's registers
+__device__ __noinline__ bool fit_propose_call(int m, FitState* st) { return fit_propose(m, *st); }
+
+template <bool TEAM_STEP>
 __global__ void __launch_bounds__(kFitThreads, 4)
 moffat_fit_group_kernel(FitBatch fb, int group, unsigned int* __restrict__ queue) {
     extern __shared__ __align__(16) double fitb_smem[];
@@ -295,7 +303,11 @@ moffat_fit_group_kernel(FitBatch fb, int group, unsigned int* __restrict__ queue
     const int m = fb.m;
     double* slab = fitb_smem;
     FitBlockCtx ctx{tid, fitb_smem + fit_sweep_doubles(m), 0};
-    FitState* states = reinterpret_cast<FitState*>(fitb_smem + fit_sweep_doubles(m) + FitBlockCtx::kRedDoubles);
+    double* vscratch = fitb_smem + fit_sweep_doubles(m) + FitBlockCtx::kRedDoubles;
+    double* idle_R = vscratch + kFitTeams * 36;          // identity; idle_z = idle_R + 36 (zeros)
+    FitState* states = reinterpret_cast<FitState*>(vscratch + kFitStepScratch);
+    if (tid < 48) idle_R[tid] = (tid < 36 && tid % 7 == 0) ? 1.0 : 0.0;
+    const int lane = tid & 31, team = tid >> 3, sub = tid & 7;
     const unsigned int total = (unsigned int)fb.nframes * (unsigned int)fb.bound;
     while (true) {
         if (tid == 0) s_item = atomicAdd(queue, 1u);
@@ -329,10 +341,34 @@ moffat_fit_group_kernel(FitBatch fb, int group, unsigned int* __restrict__ queue
                 fit_evaluate(ctx, m, fb.profiles + idx * m, scale, slab, &states[j]);
             }
             __syncthreads();
-            // ---- step phase
+            // ---- step phase.  Small groups (latency matters): 8-lane teams, one fit each; the SVD of the 6 x 6
+            // triangle is spread over the team (jacobi_svd6_warp), the scalar logic around it is replicated in
+            // the team and stored by its lane 0.  Large groups (throughput matters): one thread per fit.
             int running = 0;
-            if (tid < count && states[tid].status != kStatusRetired) {
-                if (fit_propose(m, states[tid])) {
+            if constexpr (TEAM_STEP) {
+                for (int first_fit = 0; first_fit < count; first_fit += kFitTeams) {
+                    const int j = first_fit + team;
+                    const bool have = j < count && states[j].status != kStatusRetired;
+                    FitState* st = &states[have ? j : 0];
+                    ProposeVars pv;
+                    const bool go = have && propose_begin(st, pv, sub == 0, st);
+                    double sv[kParams], suf[kParams];
+                    double* V = vscratch + team * 36;
+                    jacobi_svd6_warp(lane, go ? st->R : idle_R, go ? st->z : idle_R + 36, sv, suf, V, false);
+                    if (go) {
+                        propose_finish(m, st, pv, sv, suf, V, sub == 0, st);
+                        running = 1;
+                    } else if (have && sub == 0) {
+                        const unsigned int item = base + j;
+                        const int f = item / fb.bound, slot = item % fb.bound;
+                        fit_finalize(fb, (size_t)f * fb.cap + slot, *st);
+                        st->status = kStatusRetired;
+                    }
+                    __syncwarp();
+                }
+            } else if (tid < count && states[tid].status != kStatusRetired) {
+                (void)lane; (void)team; (void)sub;
+                if (fit_propose_call(m, &states[tid])) {
                     running = 1;
                 } else {
                     const unsigned int item = base + tid;

@@ -473,7 +473,7 @@ __device__ __forceinline__ void jacobi_svd6_warp(int lane, const double* R, cons
         rot |= jacobi_round<0, 3, 2, 4, 1, 5>(w, v);
         rot |= jacobi_round<0, 2, 1, 3, 4, 5>(w, v);
         rot |= jacobi_round<0, 1, 2, 5, 3, 4>(w, v);
-        if (!rot) break;
+        if (!__any_sync(0xffffffffu, rot)) break;      // the four 8-lane groups may hold different matrices
     }
     double sv[n], sz[n];
 #pragma unroll
@@ -497,7 +497,7 @@ __device__ __forceinline__ void jacobi_svd6_warp(int lane, const double* R, cons
             if (order[j] == pos) {
                 s[pos] = sv[j];
                 suf[pos] = sz[j];
-                if (lane < n) vout[lane * n + pos] = v[j];
+                if (row < n) vout[row * n + pos] = v[j];
             }
         }
     }

@@ -335,40 +335,87 @@ MOTES_HD void fit_evaluate(const Ctx& ctx, int m, const double* profile, double 
     ctx.sync();
 }
 
-// Top of the outer loop up to the chosen step.  Returns false when the fit has ended (st.status final).
-MOTES_HD bool fit_propose(int m, FitState& st) {
+// Top of the outer loop up to the chosen step, in two halves around the SVD of the 6 x 6 triangle so that
+// the SVD can be done by one thread (jacobi_svd6) or by an 8-lane team (jacobi_svd6_warp).  Both halves work
+// on register copies; `write` says whether this thread stores the results into *st.
+struct ProposeVars {
+    double x[kParams], lb[kParams], ub[kParams], g[kParams], d[kParams], g_h[kParams];
+    double radius, alpha, theta;
+    int status;
+};
+
+// Returns false when the fit has ended (st->status final).
+MOTES_HD bool propose_begin(const FitState* st, ProposeVars& pv, bool write, FitState* out) {
     using namespace trf_detail;
     constexpr int n = kParams;
     const int max_nfev = 100 * n;
-    if (st.status != kStatusRunning) return false;
+    pv.status = st->status;
+    if (pv.status != kStatusRunning) return false;
+#pragma unroll
+    for (int i = 0; i < n; ++i) { pv.x[i] = st->x[i]; pv.lb[i] = st->lb[i]; pv.ub[i] = st->ub[i]; pv.g[i] = st->g[i]; }
+    pv.radius = st->radius;
+    pv.alpha = st->alpha;
+    const int first = st->first, nfev = st->nfev;
     double v[n], dv[n];
-    coleman_li(st.x, st.g, st.lb, st.ub, v, dv);
-    if (st.first) {
+    coleman_li(pv.x, pv.g, pv.lb, pv.ub, v, dv);
+    if (first) {
         double t[n];
-        for (int i = 0; i < n; ++i) t[i] = st.x[i] / sqrt(v[i]);
-        st.radius = norm6(t);
-        if (st.radius == 0.0) st.radius = 1.0;
-        st.alpha = 0.0;
-        st.first = 0;
+#pragma unroll
+        for (int i = 0; i < n; ++i) t[i] = pv.x[i] / sqrt(v[i]);
+        pv.radius = norm6(t);
+        if (pv.radius == 0.0) pv.radius = 1.0;
+        pv.alpha = 0.0;
     }
     double g_norm = 0.0;
-    for (int i = 0; i < n; ++i) g_norm = fmax(g_norm, fabs(st.g[i] * v[i]));
-    if (g_norm < 1e-8) st.status = kFitGtol;
-    if (st.status != kStatusRunning) return false;
-    if (st.nfev >= max_nfev) { st.status = kFitMaxNfev; return false; }
-    double d[n], g_h[n];
-    for (int i = 0; i < n; ++i) { d[i] = sqrt(v[i]); g_h[i] = d[i] * st.g[i]; }
+#pragma unroll
+    for (int i = 0; i < n; ++i) g_norm = fmax(g_norm, fabs(pv.g[i] * v[i]));
+    if (g_norm < 1e-8) pv.status = kFitGtol;
+    else if (nfev >= max_nfev) pv.status = kFitMaxNfev;
+    if (pv.status != kStatusRunning) {
+        if (write) out->status = pv.status;
+        return false;
+    }
+#pragma unroll
+    for (int i = 0; i < n; ++i) { pv.d[i] = sqrt(v[i]); pv.g_h[i] = pv.d[i] * pv.g[i]; }
+    pv.theta = fmax(0.995, 1.0 - g_norm);
+    return true;
+}
+
+// s (descending), suf = s * (U^T z), V (row-major, right singular vectors in columns) from the SVD of st->R.
+MOTES_HD void propose_finish(int m, const FitState* st, ProposeVars& pv, const double* s, const double* suf,
+                             const double* V, bool write, FitState* out) {
+    using namespace trf_detail;
+    constexpr int n = kParams;
+    double R[n * n];
+#pragma unroll
+    for (int i = 0; i < n * n; ++i) R[i] = st->R[i];
+    double p_h[n], step[n], step_h[n], x_new[n];
+    more_step(m, s, suf, V, pv.radius, &pv.alpha, p_h);
+    const double predicted = choose_step(pv.x, R, pv.g_h, p_h, pv.d, pv.radius, pv.lb, pv.ub, pv.theta, step, step_h);
+#pragma unroll
+    for (int i = 0; i < n; ++i) x_new[i] = pv.x[i] + step[i];
+    push_inside(x_new, pv.lb, pv.ub, 0.0);
+    if (write) {
+#pragma unroll
+        for (int i = 0; i < n; ++i) out->x_new[i] = x_new[i];
+        out->predicted = predicted;
+        out->step_h_norm = norm6(step_h);
+        out->step_norm = norm6(step);
+        out->x_norm = norm6(pv.x);
+        out->radius = pv.radius;
+        out->alpha = pv.alpha;
+        out->first = 0;
+    }
+}
+
+// One thread per fit (host simulation; also the reference for the team version in kernels.cuh).
+MOTES_HD bool fit_propose(int m, FitState& st) {
+    constexpr int n = kParams;
+    ProposeVars pv;
+    if (!propose_begin(&st, pv, true, &st)) return false;
     double s[n], suf[n], V[n * n], w[n * n], vv[n * n];
     jacobi_svd6(SeqCtx{}, st.R, st.z, w, vv, s, suf, V);
-    const double theta = fmax(0.995, 1.0 - g_norm);
-    st.x_norm = norm6(st.x);
-    double p_h[n], step[n], step_h[n];
-    more_step(m, s, suf, V, st.radius, &st.alpha, p_h);
-    st.predicted = choose_step(st.x, st.R, g_h, p_h, d, st.radius, st.lb, st.ub, theta, step, step_h);
-    for (int i = 0; i < n; ++i) st.x_new[i] = st.x[i] + step[i];
-    push_inside(st.x_new, st.lb, st.ub, 0.0);
-    st.step_h_norm = norm6(step_h);
-    st.step_norm = norm6(step);
+    propose_finish(m, &st, pv, s, suf, V, true, &st);
     return true;
 }
 
