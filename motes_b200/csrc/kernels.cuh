@@ -440,6 +440,171 @@ constexpr int kTileStride = kTileCols + 1;
 constexpr int kTileThreads = 256;
 constexpr int kTileWarps = kTileThreads / 32;
 
+// Warp-level bitonic sort of EPL * 32 (key, row) pairs held in registers (position = lane * EPL + k),
+// ascending by key, ties by row - the order np.sort gives the sky pixels and the order in which the
+// rank-by-counting of sky_prepare_column breaks ties.
+template <int EPL>
+__device__ __forceinline__ void sort_pairs_warp(unsigned long long (&key)[EPL], uint32_t (&row)[EPL], int lane) {
+    constexpr int N = EPL * 32;
+#pragma unroll
+    for (int size = 2; size <= N; size <<= 1) {
+#pragma unroll
+        for (int d = size >> 1; d > 0; d >>= 1) {
+            if (d < EPL) {
+#pragma unroll
+                for (int k = 0; k < EPL; ++k) {
+                    if ((k & d) == 0) {
+                        const int k2 = k | d;
+                        const bool up = (size < EPL) ? ((k & size) == 0) : ((lane & (size / EPL)) == 0);
+                        const bool gt = (key[k] > key[k2]) || (key[k] == key[k2] && row[k] > row[k2]);
+                        if (gt == up) {
+                            const unsigned long long tk = key[k]; key[k] = key[k2]; key[k2] = tk;
+                            const uint32_t tr = row[k]; row[k] = row[k2]; row[k2] = tr;
+                        }
+                    }
+                }
+            } else {
+                const int dl = d / EPL;
+                const bool up = (lane & (size / EPL)) == 0 || size == N;
+                const bool keep_min = (((lane & dl) == 0) == up);
+#pragma unroll
+                for (int k = 0; k < EPL; ++k) {
+                    const unsigned long long ok = __shfl_xor_sync(0xffffffffu, key[k], dl);
+                    const uint32_t orow = __shfl_xor_sync(0xffffffffu, row[k], dl);
+                    const bool gt = (key[k] > ok) || (key[k] == ok && row[k] > orow);
+                    if (gt == keep_min) { key[k] = ok; row[k] = orow; }
+                }
+            }
+        }
+    }
+}
+
+// sky_prepare_column for nspat <= 32 EPL, one warp per column, by sorting instead of rank counting.
+// skeys: nspat 64-bit words, rank_by_row: nspat 16-bit words (both shared, per warp).
+template <int EPL>
+__device__ __forceinline__ void sky_prepare_column_sorted(int lane, const double* col, int st, int nspat, double* lim_lo,
+                                                          double* lim_hi, int spatial_floor, int* n_sky_out,
+                                                          int* n_good_out, int* flag_out, double* __restrict__ sorted,
+                                                          uint16_t* __restrict__ rank_of, uint16_t* __restrict__ good_row,
+                                                          unsigned long long* skeys, uint16_t* rank_by_row) {
+    double lo = *lim_lo, hi = *lim_hi;
+    const double top = (double)(nspat - 1) + (double)spatial_floor;
+    if (lo < 0.0) lo = 0.0;
+    if (hi > top) hi = top;
+    __syncwarp();
+    if (lane == 0) { *lim_lo = lo; *lim_hi = hi; }
+    const double edge_lo = lo + (double)spatial_floor, edge_hi = hi + (double)spatial_floor;
+    unsigned long long key[EPL];
+    uint32_t row[EPL];
+    int my_sky = 0, my_nan = 0;
+    unsigned long long my_min = ~0ull, my_max = 0ull;
+#pragma unroll
+    for (int k = 0; k < EPL; ++k) {
+        const int i = 32 * k + lane;
+        key[k] = kKeyExcluded;
+        row[k] = (uint32_t)i;
+        if (i < nspat) {
+            rank_by_row[i] = 0xffffu;
+            const double axis = (double)(i + spatial_floor);
+            if (axis < edge_lo || axis > edge_hi) {
+                const double v = col[(size_t)i * st];
+                ++my_sky;
+                if (v != v) ++my_nan;
+                else {
+                    key[k] = key_of(v);
+                    my_min = key[k] < my_min ? key[k] : my_min;
+                    my_max = key[k] > my_max ? key[k] : my_max;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        my_sky += __shfl_xor_sync(0xffffffffu, my_sky, o);
+        my_nan += __shfl_xor_sync(0xffffffffu, my_nan, o);
+        const unsigned long long tmin = __shfl_xor_sync(0xffffffffu, my_min, o), tmax = __shfl_xor_sync(0xffffffffu, my_max, o);
+        my_min = tmin < my_min ? tmin : my_min;
+        my_max = tmax > my_max ? tmax : my_max;
+    }
+    const int n_sky = my_sky, n_valid = my_sky - my_nan;
+    *n_sky_out = n_sky;
+    *n_good_out = 0;
+    if (n_sky == 0) { *flag_out = kSkyNoPixels; return; }
+    // len(set(sky_pixels)) == 1 (sky.py:338): one pixel, or all pixels the same number (NaNs never collapse)
+    if (n_sky == 1 || (my_nan == 0 && value_of(my_min) == value_of(my_max))) { *flag_out = kSkySkipped; return; }
+    *flag_out = kSkyModelled;
+
+    sort_pairs_warp<EPL>(key, row, lane);
+    // np.nanmedian / np.nanstd of the valid sky pixels
+#pragma unroll
+    for (int k = 0; k < EPL; ++k) {
+        const int p = lane * EPL + k;
+        if (p < n_valid) skeys[p] = key[k];
+    }
+    __syncwarp();
+    double med = NAN;
+    if (n_valid > 0) {
+        const double a = value_of(skeys[(n_valid - 1) / 2]), b = value_of(skeys[n_valid / 2]);
+        med = ((n_valid & 1) ? a : (a + b) * 0.5);
+    }
+    double part = 0.0;
+#pragma unroll
+    for (int k = 0; k < EPL; ++k) part += (lane * EPL + k < n_valid) ? value_of(key[k]) : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    const double mean = part / (double)n_valid;
+    part = 0.0;
+#pragma unroll
+    for (int k = 0; k < EPL; ++k) {
+        const double dd = value_of(key[k]) - mean;
+        part += (lane * EPL + k < n_valid) ? dd * dd : 0.0;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    const double sigma = sqrt(part / (double)n_valid);
+    const double cut_lo = med - (10.0 * sigma), cut_hi = med + (10.0 * sigma);
+    // single-pass 10-sigma clip (sky.py:342-345): the survivors are a contiguous run [first, last) of the sorted values
+    int below = 0, under = 0;
+#pragma unroll
+    for (int k = 0; k < EPL; ++k) {
+        const bool valid = lane * EPL + k < n_valid;
+        const double v = value_of(key[k]);
+        below += valid && !(v > cut_lo);
+        under += valid && (v < cut_hi);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        below += __shfl_xor_sync(0xffffffffu, below, o);
+        under += __shfl_xor_sync(0xffffffffu, under, o);
+    }
+    const int first = below, last = under > below ? under : below;
+    const int n_good = last - first;
+    *n_good_out = n_good;
+#pragma unroll
+    for (int k = 0; k < EPL; ++k) {
+        const int p = lane * EPL + k;
+        if (p >= first && p < last) {
+            sorted[p - first] = value_of(key[k]);
+            rank_by_row[row[k]] = (uint16_t)(p - first);
+        }
+    }
+    __syncwarp();
+    // good pixels in row order -> their ranks (and rows)
+    int base = 0;
+    for (int start = 0; start < nspat; start += 32) {
+        const int i = start + lane;
+        const uint16_t r = (i < nspat) ? rank_by_row[i] : (uint16_t)0xffffu;
+        const unsigned bal = __ballot_sync(0xffffffffu, r != 0xffffu);
+        if (r != 0xffffu) {
+            const int g = base + __popc(bal & ((1u << lane) - 1u));
+            rank_of[g] = r;
+            if (good_row) good_row[g] = (uint16_t)i;
+        }
+        base += __popc(bal);
+    }
+    __syncwarp();
+}
+
 __global__ void __launch_bounds__(kTileThreads)
 sky_prepare_kernel(const double* __restrict__ data, size_t frame_stride, int nspat, int ndisp,
                    double* __restrict__ limits /* [F][2][ndisp], clamped in place */, int spatial_floor,
@@ -469,11 +634,26 @@ sky_prepare_kernel(const double* __restrict__ data, size_t frame_stride, int nsp
         double* hi = lo + ndisp;
         int ns, ng, fl;
         int icell;
-        sky_prepare_column(sc, tile + c, kTileStride, nspat, lo, hi, spatial_floor, &ns, &ng, &fl,
-                           sorted + col * nspat, rank_of + col * nspat, rows_all + (size_t)warp * nspat,
-                           keys_all + (size_t)warp * nspat, hist_all + warp * 256, cells + warp, &icell);
-        if (good_row && fl == kSkyModelled)
-            for (int g = sc.tid; g < ng; g += 32) good_row[col * nspat + g] = rows_all[(size_t)warp * nspat + g];
+        uint16_t* grow = (good_row != nullptr) ? good_row + col * nspat : nullptr;
+        if (nspat <= 128) {
+            sky_prepare_column_sorted<4>(sc.tid, tile + c, kTileStride, nspat, lo, hi, spatial_floor, &ns, &ng, &fl,
+                                         sorted + col * nspat, rank_of + col * nspat, grow, keys_all + (size_t)warp * nspat,
+                                         rows_all + (size_t)warp * nspat);
+        } else if (nspat <= 256) {
+            sky_prepare_column_sorted<8>(sc.tid, tile + c, kTileStride, nspat, lo, hi, spatial_floor, &ns, &ng, &fl,
+                                         sorted + col * nspat, rank_of + col * nspat, grow, keys_all + (size_t)warp * nspat,
+                                         rows_all + (size_t)warp * nspat);
+        } else if (nspat <= 512) {
+            sky_prepare_column_sorted<16>(sc.tid, tile + c, kTileStride, nspat, lo, hi, spatial_floor, &ns, &ng, &fl,
+                                          sorted + col * nspat, rank_of + col * nspat, grow, keys_all + (size_t)warp * nspat,
+                                          rows_all + (size_t)warp * nspat);
+        } else {
+            sky_prepare_column(sc, tile + c, kTileStride, nspat, lo, hi, spatial_floor, &ns, &ng, &fl,
+                               sorted + col * nspat, rank_of + col * nspat, rows_all + (size_t)warp * nspat,
+                               keys_all + (size_t)warp * nspat, hist_all + warp * 256, cells + warp, &icell);
+            if (good_row && fl == kSkyModelled)
+                for (int g = sc.tid; g < ng; g += 32) good_row[col * nspat + g] = rows_all[(size_t)warp * nspat + g];
+        }
         if (sc.tid == 0) {
             n_sky[col] = ns;
             n_good[col] = ng;
