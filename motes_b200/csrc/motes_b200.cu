@@ -288,6 +288,9 @@ static size_t sky_poly_smem(int nspat) {
 static size_t sky_col_smem(int nspat) {
     return (size_t)2 * kBootstrap * 8 + (size_t)kBootstrap * boot_row_words(nspat) * 4 + (size_t)nspat * 2 + 64;
 }
+static size_t sky_colh_smem(int nspat) {
+    return (size_t)2 * kBootstrap * 8 + (size_t)(kBootstrap * kHistStride) * 4 + (size_t)nspat * 2 + 64;
+}
 
 static int stage_bootstrap_segmented(motes_handle* h, Batch& b, uint32_t* rng, bool* done) {
     *done = false;
@@ -338,7 +341,7 @@ static int stage_bootstrap_segmented(motes_handle* h, Batch& b, uint32_t* rng, b
     MOTES_TRY(h->work[W_WINDOWS].ensure((size_t)wave * lay.segs * 624 * sizeof(uint32_t)));
     MOTES_TRY(h->work[W_SNAPS].ensure((size_t)wave * lay.snaps * 624 * sizeof(uint32_t)));
     MOTES_TRY(h->work[W_SUBS].ensure((size_t)wave * lay.sub_len * sizeof(uint32_t)));
-    MOTES_TRY(h->work[W_SEGI].ensure(((size_t)wave * 2 + (size_t)wave * b.ndisp * 2) * sizeof(uint32_t) + 256));
+    MOTES_TRY(h->work[W_SEGI].ensure(((size_t)wave * 2 + (size_t)wave * b.ndisp * 3 + 64) * sizeof(uint32_t) + 256));
     uint16_t* stream = h->work[W_STREAM].as<uint16_t>();
     uint32_t* windows = h->work[W_WINDOWS].as<uint32_t>();
     uint32_t* snaps = h->work[W_SNAPS].as<uint32_t>();
@@ -347,6 +350,11 @@ static int stage_bootstrap_segmented(motes_handle* h, Batch& b, uint32_t* rng, b
     uint32_t* end_pos = reinterpret_cast<uint32_t*>(seg_need + wave);
     uint32_t* col_start = end_pos + wave;
     uint32_t* col_end = col_start + (size_t)wave * b.ndisp;
+    uint32_t* retry_list = col_end + (size_t)wave * b.ndisp;          // columns the histogram kernel hands to the exact one
+    uint32_t* retry_count = retry_list + (size_t)wave * b.ndisp;
+    static const int col_mode = getenv("MOTES_B200_COLUMN") ? atoi(getenv("MOTES_B200_COLUMN")) : 256;   // 0: exact kernel only; else window
+    const size_t colh_smem = sky_colh_smem(b.nspat);
+    MOTES_CUDA(cudaFuncSetAttribute(sky_column_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)colh_smem));
     const uint32_t* polys = h->jump_polys.as<uint32_t>();
     const size_t jump_smem = (size_t)(kJumpStreamWords + 624) * sizeof(uint32_t);
     MOTES_CUDA(cudaFuncSetAttribute(mt_jump_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jump_smem));
@@ -378,10 +386,24 @@ static int stage_bootstrap_segmented(motes_handle* h, Batch& b, uint32_t* rng, b
         MOTES_LAUNCHED(h);
         t_walk.stop();
         StageTimer t_col(h, ST_BOOT_COLUMN);
-        sky_column_kernel<<<dim3(b.ndisp, nf), kColThreads, col_smem, h->stream>>>(
-            stream, lay, b.nspat, b.ndisp, b.n_good + c0, b.sky_flag + c0, b.sorted + c0 * b.nspat, b.rank_of + c0 * b.nspat,
-            col_start, col_end, subs, b.sky + c0, b.sky_err + c0, b.st + f0);
-        MOTES_LAUNCHED(h);
+        if (col_mode > 0) {
+            const int window = col_mode > 4 * kHistWords ? 4 * kHistWords : col_mode;
+            MOTES_CUDA(cudaMemsetAsync(retry_count, 0, sizeof(uint32_t), h->stream));
+            sky_column_hist_kernel<<<dim3(b.ndisp, nf), kColThreads, colh_smem, h->stream>>>(
+                stream, lay, b.nspat, b.ndisp, window, b.n_good + c0, b.sky_flag + c0, b.sorted + c0 * b.nspat,
+                b.rank_of + c0 * b.nspat, col_start, col_end, subs, b.sky + c0, b.sky_err + c0, b.st + f0, 0u, retry_list,
+                retry_count);
+            MOTES_LAUNCHED(h);
+            sky_column_kernel<<<dim3(2 * h->sm_count, 1), kColThreads, col_smem, h->stream>>>(
+                stream, lay, b.nspat, b.ndisp, b.n_good + c0, b.sky_flag + c0, b.sorted + c0 * b.nspat, b.rank_of + c0 * b.nspat,
+                col_start, col_end, subs, b.sky + c0, b.sky_err + c0, b.st + f0, retry_list, retry_count);
+            MOTES_LAUNCHED(h);
+        } else {
+            sky_column_kernel<<<dim3(b.ndisp, nf), kColThreads, col_smem, h->stream>>>(
+                stream, lay, b.nspat, b.ndisp, b.n_good + c0, b.sky_flag + c0, b.sorted + c0 * b.nspat, b.rank_of + c0 * b.nspat,
+                col_start, col_end, subs, b.sky + c0, b.sky_err + c0, b.st + f0, nullptr, nullptr);
+            MOTES_LAUNCHED(h);
+        }
         mt_export_kernel<<<nf, 256, 0, h->stream>>>(rng_w, snaps, lay, end_pos, b.st + f0);
         MOTES_LAUNCHED(h);
     }

@@ -615,19 +615,157 @@ __device__ __forceinline__ double warp_numpy_sum100(const double* a, int lane) {
     return __shfl_sync(0xffffffffu, res, 0);
 }
 
+// The accepted draws of one column, piece by piece: every warp takes 2048-word pieces of [P, Pend); the
+// ordinal of a piece's first accept comes from the walk.  sink(ord, m4, v) receives, per lane and row of
+// 128 words, the ordinal of the lane's first accept, the 4-bit accept mask of its four words (stream order)
+// and the four masked words.
+template <class Sink>
+__device__ __forceinline__ void column_draws(const uint16_t* __restrict__ s, const uint32_t* __restrict__ subs, uint32_t P,
+                                             uint32_t Pend, int n, int lane, int warp, int nwarps, Sink sink) {
+    if (Pend <= P) return;
+    const int need = n * kBootstrap;
+    const uint32_t mask = rejection_mask((uint32_t)n), top = (uint32_t)(n - 1);
+    const unsigned lanes_below = (1u << lane) - 1u;
+    const uint32_t first = P >> kSubLog2, last = (Pend - 1) >> kSubLog2;
+    for (uint32_t sub = first + warp; sub <= last; sub += nwarps) {
+        const uint32_t sb = sub << kSubLog2;
+        const uint32_t start = max(P, sb), end = min(Pend, sb + (uint32_t)kSubChunk);
+        int ord0 = (sb > P) ? (int)subs[sub] : 0;
+        // four rows (512 words) of loads in flight per warp: the stream comes from HBM / L2
+        for (uint32_t row0 = start & ~127u; row0 < end; row0 += 512) {
+            uint2 raw4[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) raw4[r] = __ldg(reinterpret_cast<const uint2*>(s + row0 + 128u * r + 4u * lane));
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const uint32_t row = row0 + 128u * r;
+                if (row >= end) break;
+                const uint32_t pos = row + 4u * lane;
+                const uint2 raw = raw4[r];
+                const uint32_t v[4] = {raw.x & mask, (raw.x >> 16) & mask, raw.y & mask, (raw.y >> 16) & mask};
+                unsigned m4 = (unsigned)(v[0] <= top) | ((unsigned)(v[1] <= top) << 1) | ((unsigned)(v[2] <= top) << 2) |
+                              ((unsigned)(v[3] <= top) << 3);
+                if (row < start || row + 128u > end) {           // first / last row of the piece
+                    unsigned inside = 0;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) inside |= (unsigned)(pos + e >= start && pos + e < end) << e;
+                    m4 &= inside;
+                }
+                const int cnt = __popc(m4);
+                // ordinal of the lane's first accept: accepts of the lower lanes (count <= 4: three ballots)
+                const unsigned c0 = __ballot_sync(0xffffffffu, cnt & 1), c1 = __ballot_sync(0xffffffffu, cnt & 2),
+                               c2 = __ballot_sync(0xffffffffu, cnt & 4);
+                const int before = __popc(c0 & lanes_below) + 2 * __popc(c1 & lanes_below) + 4 * __popc(c2 & lanes_below);
+                const int total = __popc(c0) + 2 * __popc(c1) + 4 * __popc(c2);
+                if (ord0 + total <= need) sink(ord0 + before, m4, v);      // always, unless walk and column disagree
+                ord0 += total;
+            }
+        }
+    }
+}
+
+// np.nanmean / np.std of the 100 medians in numpy's summation order (sky.py:40-41); warp 0 of the CTA
+__device__ __forceinline__ void column_mean_std(const double* meds, double* sq, int lane, double* sky, double* sky_err) {
+    const double mean = warp_numpy_sum100(meds, lane) / (double)kBootstrap;
+    for (int smp = lane; smp < kBootstrap; smp += 32) { const double d = meds[smp] - mean; sq[smp] = d * d; }
+    __syncwarp();
+    const double var = warp_numpy_sum100(sq, lane) / (double)kBootstrap;
+    if (lane == 0) {
+        *sky = mean;
+        *sky_err = sqrt(var) / kSqrt99;
+    }
+}
+
+// Exact for any n: every draw's rank is stored in numpy's (pixel, sample) slot, medians by bitwise search.
+// With `list` the CTAs walk a list of columns (the ones the histogram kernel below could not settle).
 __global__ void __launch_bounds__(kColThreads, 2)
 sky_column_kernel(const uint16_t* __restrict__ stream, SegLayout lay, int nspat, int ndisp,
                   const int32_t* __restrict__ n_good, const int32_t* __restrict__ flag,
                   const double* __restrict__ sorted, const uint16_t* __restrict__ rank_of,
                   const uint32_t* __restrict__ col_start, const uint32_t* __restrict__ col_end,
                   const uint32_t* __restrict__ sub_have, double* __restrict__ sky, double* __restrict__ sky_err,
-                  const FrameState* __restrict__ st) {
+                  const FrameState* __restrict__ st, const uint32_t* __restrict__ list,
+                  const uint32_t* __restrict__ list_count) {
     extern __shared__ __align__(16) unsigned char col_smem[];
     ColShared sh;
     sh.meds = reinterpret_cast<double*>(col_smem);
     sh.sq = sh.meds + kBootstrap;
     sh.slots = reinterpret_cast<uint32_t*>(sh.sq + kBootstrap);
     sh.ranks = reinterpret_cast<uint16_t*>(sh.slots + (size_t)kBootstrap * boot_row_words(nspat));
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int nwarps = kColThreads / 32;
+    const uint32_t items = list ? *list_count : 1u;
+    for (uint32_t item = list ? blockIdx.x : 0u; item < items; item += gridDim.x) {
+        const int c = list ? (int)(list[item] % (uint32_t)ndisp) : (int)blockIdx.x;
+        const int f = list ? (int)(list[item] / (uint32_t)ndisp) : (int)blockIdx.y;
+        if (st[f].status != 0) continue;
+        const size_t col = (size_t)f * ndisp + c;
+        if (flag[col] != kSkyModelled) {
+            if (tid == 0) { sky[col] = 0.0; sky_err[col] = 0.0; }
+            continue;
+        }
+        const int n = n_good[col];
+        if (n == 0) {
+            if (tid == 0) { sky[col] = NAN; sky_err[col] = NAN; }
+            continue;
+        }
+        const double* srt = sorted + col * nspat;
+        __syncthreads();                 // list mode: the previous column's medians have been consumed
+        if (n > 1) {
+            const int rw = boot_row_words(n);
+            uint16_t* slots16 = reinterpret_cast<uint16_t*>(sh.slots);
+            for (int i = tid; i < n; i += kColThreads) sh.ranks[i] = rank_of[col * nspat + i];
+            __syncthreads();
+            const uint16_t* ranks = sh.ranks;
+            column_draws(stream + (size_t)f * lay.stream_len, sub_have + (size_t)f * lay.sub_len, col_start[col], col_end[col],
+                         n, lane, warp, nwarps, [&](int ord, unsigned m4, const uint32_t (&v)[4]) {
+                             const int pix = ord / kBootstrap;
+                             int smp = ord - pix * kBootstrap;
+                             int at = smp * (2 * rw) + pix;          // slot of ordinal ord; the next one is a row down
+#pragma unroll
+                             for (int e = 0; e < 4; ++e) {
+                                 if (m4 & (1u << e)) {
+                                     slots16[at] = ranks[v[e]];
+                                     at += 2 * rw;
+                                     if (++smp == kBootstrap) { smp = 0; at -= kBootstrap * 2 * rw - 1; }
+                                 }
+                             }
+                         });
+            __syncthreads();
+            column_medians(sh, n, rw, srt, lane, warp, nwarps);
+        } else {
+            for (int smp = tid; smp < kBootstrap; smp += kColThreads) sh.meds[smp] = srt[0];
+        }
+        __syncthreads();
+        if (warp == 0) column_mean_std(sh.meds, sh.sq, lane, sky + col, sky_err + col);
+    }
+}
+
+// The same result from counts instead of slots: the median rank of a bootstrap sample of n ranks sits
+// within a few sqrt(n) / 2 of n / 2, so each sample only keeps an 8-bit histogram of the ranks inside a
+// window around n / 2 plus the number of draws below and above it; its median is read off a prefix sum.
+// A sample whose median falls outside the window (or a count that does not add up to n: a histogram byte
+// overflowed) sends the column to the exact kernel above through `list`.
+constexpr int kHistWords = 64;                      // 256 one-byte bins per sample
+constexpr int kHistStride = kHistWords + 3;         // + draws below / above the window, + 1 word of bank skew
+
+__global__ void __launch_bounds__(kColThreads, 3)
+sky_column_hist_kernel(const uint16_t* __restrict__ stream, SegLayout lay, int nspat, int ndisp, int window,
+                       const int32_t* __restrict__ n_good, const int32_t* __restrict__ flag,
+                       const double* __restrict__ sorted, const uint16_t* __restrict__ rank_of,
+                       const uint32_t* __restrict__ col_start, const uint32_t* __restrict__ col_end,
+                       const uint32_t* __restrict__ sub_have, double* __restrict__ sky, double* __restrict__ sky_err,
+                       const FrameState* __restrict__ st, uint32_t frame0, uint32_t* __restrict__ list,
+                       uint32_t* __restrict__ list_count) {
+    extern __shared__ __align__(16) unsigned char colh_smem[];
+    double* meds = reinterpret_cast<double*>(colh_smem);
+    double* sq = meds + kBootstrap;
+    // per sample: 64 words of 8-bit bins, then the counts of draws below and above the window
+    uint32_t* hist = reinterpret_cast<uint32_t*>(sq + kBootstrap);                 // 100 x kHistStride
+    // per good pixel (in the order the draws index them): which counter a draw of it bumps, and by how much:
+    // low byte = word inside the sample's row, high byte = shift of the increment
+    uint16_t* entry = reinterpret_cast<uint16_t*>(hist + kBootstrap * kHistStride);   // nspat
+    __shared__ int failed;
     const int c = blockIdx.x, f = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int nwarps = kColThreads / 32;
@@ -643,86 +781,76 @@ sky_column_kernel(const uint16_t* __restrict__ stream, SegLayout lay, int nspat,
         return;
     }
     const double* srt = sorted + col * nspat;
+    const int lo = max(0, n / 2 - window / 2);     // ranks [lo, lo + window) are histogrammed
     if (n > 1) {
-        const int rw = boot_row_words(n);
-        uint16_t* slots16 = reinterpret_cast<uint16_t*>(sh.slots);
-        for (int i = tid; i < n; i += kColThreads) sh.ranks[i] = rank_of[col * nspat + i];
+        for (int i = tid; i < kBootstrap * kHistStride; i += kColThreads) hist[i] = 0u;
+        for (int i = tid; i < n; i += kColThreads) {
+            const int r = (int)rank_of[col * nspat + i] - lo;
+            const bool in = (unsigned)r < (unsigned)window;
+            entry[i] = in ? (uint16_t)((r >> 2) | ((8 * (r & 3)) << 8)) : (uint16_t)(r < 0 ? kHistWords : kHistWords + 1);
+        }
+        if (tid == 0) failed = 0;
         __syncthreads();
-        const uint16_t* s = stream + (size_t)f * lay.stream_len;
-        const uint32_t* subs = sub_have + (size_t)f * lay.sub_len;
-        const uint32_t P = col_start[col], Pend = col_end[col];
-        const int need = n * kBootstrap;
-        const uint32_t mask = rejection_mask((uint32_t)n), top = (uint32_t)(n - 1);
-        const unsigned lanes_below = (1u << lane) - 1u;
-        if (Pend > P) {
-            const uint32_t first = P >> kSubLog2, last = (Pend - 1) >> kSubLog2;
-            for (uint32_t sub = first + warp; sub <= last; sub += nwarps) {
-                const uint32_t sb = sub << kSubLog2;
-                const uint32_t start = max(P, sb), end = min(Pend, sb + (uint32_t)kSubChunk);
-                int ord0 = (sb > P) ? (int)subs[sub] : 0;
-                // four rows (512 words) of loads in flight per warp: the stream comes from HBM / L2
-                for (uint32_t row0 = start & ~127u; row0 < end; row0 += 512) {
-                    uint2 raw4[4];
+        column_draws(stream + (size_t)f * lay.stream_len, sub_have + (size_t)f * lay.sub_len, col_start[col], col_end[col], n,
+                     lane, warp, nwarps, [&](int ord, unsigned m4, const uint32_t (&v)[4]) {
+                         int smp = ord % kBootstrap;
+                         uint32_t* row = hist + smp * kHistStride;
 #pragma unroll
-                    for (int r = 0; r < 4; ++r) raw4[r] = __ldg(reinterpret_cast<const uint2*>(s + row0 + 128u * r + 4u * lane));
+                         for (int e = 0; e < 4; ++e) {
+                             if (m4 & (1u << e)) {
+                                 const uint32_t en = entry[v[e]];
+                                 atomicAdd(row + (en & 0xffu), 1u << (en >> 8));      // one shared-memory atomic per draw
+                                 row += kHistStride;
+                                 if (++smp == kBootstrap) { smp = 0; row = hist; }
+                             }
+                         }
+                     });
+        __syncthreads();
+        const int k1 = (n - 1) / 2, k2 = n / 2;
+        for (int smp = warp; smp < kBootstrap; smp += nwarps) {
+            const uint32_t* row = hist + smp * kHistStride;
+            const uint32_t w0 = row[2 * lane], w1 = row[2 * lane + 1];
+            const int mine = (int)(__vsadu4(w0, 0u) + __vsadu4(w1, 0u));          // draws in this lane's 8 bins
+            int incl = mine;
 #pragma unroll
-                    for (int r = 0; r < 4; ++r) {
-                        const uint32_t row = row0 + 128u * r;
-                        if (row >= end) break;
-                        const uint32_t pos = row + 4u * lane;
-                        const uint2 raw = raw4[r];
-                        const uint32_t v[4] = {raw.x & mask, (raw.x >> 16) & mask, raw.y & mask, (raw.y >> 16) & mask};
-                        // this lane's four words, in stream order: bit e of m4 = word e is an accepted draw
-                        unsigned m4 = (unsigned)(v[0] <= top) | ((unsigned)(v[1] <= top) << 1) |
-                                      ((unsigned)(v[2] <= top) << 2) | ((unsigned)(v[3] <= top) << 3);
-                        if (row < start || row + 128u > end) {           // first / last row of the piece
-                            unsigned inside = 0;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            const int inside = __shfl_sync(0xffffffffu, incl, 31);
+            const int nb = (int)row[kHistWords], na = (int)row[kHistWords + 1];
+            const bool ok = (nb + inside + na == n) && (k1 >= nb) && (k2 < nb + inside);
+            if (!ok) {
+                if (lane == 0) failed = 1;
+                continue;
+            }
+            // order statistics k1 and k2 of the sample: bin of the (k - nb)-th draw inside the window
+            const int t1 = k1 - nb, t2 = k2 - nb, excl = incl - mine;
+            int x1 = -1, x2 = -1;
+            if ((t1 >= excl && t1 < incl) || (t2 >= excl && t2 < incl)) {
+                int seen = excl;
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) inside |= (unsigned)(pos + e >= start && pos + e < end) << e;
-                            m4 &= inside;
-                        }
-                        const int cnt = __popc(m4);
-                        // ordinal of the lane's first accept: accepts of the lower lanes (count <= 4: three ballots)
-                        const unsigned c0 = __ballot_sync(0xffffffffu, cnt & 1), c1 = __ballot_sync(0xffffffffu, cnt & 2),
-                                       c2 = __ballot_sync(0xffffffffu, cnt & 4);
-                        const int before = __popc(c0 & lanes_below) + 2 * __popc(c1 & lanes_below) + 4 * __popc(c2 & lanes_below);
-                        const int total = __popc(c0) + 2 * __popc(c1) + 4 * __popc(c2);
-                        if (ord0 + total <= need) {                       // always, unless walk and column disagree
-                            const int ord = ord0 + before;
-                            const int pix = ord / kBootstrap;
-                            int smp = ord - pix * kBootstrap;
-                            int at = smp * (2 * rw) + pix;                // slot of ordinal ord; the next one is a row down
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                if (m4 & (1u << e)) {
-                                    slots16[at] = sh.ranks[v[e]];
-                                    at += 2 * rw;
-                                    if (++smp == kBootstrap) { smp = 0; at -= kBootstrap * 2 * rw - 1; }
-                                }
-                            }
-                        }
-                        ord0 += total;
-                    }
+                for (int bin = 0; bin < 8; ++bin) {
+                    const int cnt = (int)(((bin < 4 ? w0 : w1) >> (8 * (bin & 3))) & 0xffu);
+                    if (t1 >= seen && t1 < seen + cnt) x1 = lo + 8 * lane + bin;
+                    if (t2 >= seen && t2 < seen + cnt) x2 = lo + 8 * lane + bin;
+                    seen += cnt;
                 }
             }
+            x1 = __reduce_max_sync(0xffffffffu, x1);
+            x2 = __reduce_max_sync(0xffffffffu, x2);
+            if (lane == 0) meds[smp] = (k1 == k2) ? srt[x1] : (srt[x1] + srt[x2]) * 0.5;
         }
-        __syncthreads();
-        column_medians(sh, n, rw, srt, lane, warp, nwarps);
     } else {
-        for (int smp = tid; smp < kBootstrap; smp += kColThreads) sh.meds[smp] = srt[0];
+        if (tid == 0) failed = 0;
+        for (int smp = tid; smp < kBootstrap; smp += kColThreads) meds[smp] = srt[0];
     }
     __syncthreads();
-    // np.nanmean / np.std of the 100 medians in numpy's summation order (sky.py:40-41)
-    if (warp == 0) {
-        const double mean = warp_numpy_sum100(sh.meds, lane) / (double)kBootstrap;
-        for (int smp = lane; smp < kBootstrap; smp += 32) { const double d = sh.meds[smp] - mean; sh.sq[smp] = d * d; }
-        __syncwarp();
-        const double var = warp_numpy_sum100(sh.sq, lane) / (double)kBootstrap;
-        if (lane == 0) {
-            sky[col] = mean;
-            sky_err[col] = sqrt(var) / kSqrt99;
-        }
+    if (failed) {
+        if (tid == 0) list[atomicAdd(list_count, 1u)] = (frame0 + (uint32_t)f) * (uint32_t)ndisp + (uint32_t)c;
+        return;
     }
+    if (warp == 0) column_mean_std(meds, sq, lane, sky + col, sky_err + col);
 }
 
 // ---- export -----------------------------------------------------------------------------------
