@@ -143,6 +143,62 @@ bins_kernel(const uint8_t* __restrict__ qual, size_t qual_stride, const double* 
 // 8 for the usual 16-column bins); wider bins fall back to radix selection straight from the frame.
 constexpr int kProfWarps = 8;
 constexpr int kProfStage = 512;
+constexpr int kProfFast = 16;                   // bin width with a thread-per-median kernel (the default binning)
+
+// Bins of exactly 16 columns (what get_bins produces on any source bright enough for the default S/N
+// limits): one THREAD per (bin, row) median - 16 keys in registers, a bitonic network, the middle one or
+// two valid keys.  Adjacent threads take adjacent bins of one row, i.e. adjacent 128-byte runs of the frame.
+__global__ void __launch_bounds__(128)
+bin_profile16_kernel(const double* __restrict__ data, size_t frame_stride, int nspat, int ndisp,
+                     const uint8_t* __restrict__ gap, const int32_t* __restrict__ bins_i, const int32_t* __restrict__ nbins,
+                     int cap, double* __restrict__ profiles /* [F][cap][nspat] */) {
+    const int f = blockIdx.y;
+    const int nb = nbins[f];
+    const long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (item >= (long long)nb * nspat) return;
+    const int row = (int)(item / nb), b = (int)(item % nb);
+    const int first = bins_i[((size_t)f * cap + b) * 2], last = bins_i[((size_t)f * cap + b) * 2 + 1];
+    if (last - first != kProfFast) return;
+    const double* p = data + (size_t)f * frame_stride + (size_t)row * ndisp + first;
+    const uint8_t* g = gap + (size_t)f * ndisp + first;
+    unsigned long long k[kProfFast];
+    int n = 0;
+#pragma unroll
+    for (int i = 0; i < kProfFast; ++i) {
+        k[i] = g[i] ? kKeyExcluded : key_or_excluded(p[i]);
+        n += (k[i] != kKeyExcluded);
+    }
+#pragma unroll
+    for (int size = 2; size <= kProfFast; size <<= 1) {
+#pragma unroll
+        for (int d = size >> 1; d > 0; d >>= 1) {
+#pragma unroll
+            for (int i = 0; i < kProfFast; ++i) {
+                const int j = i ^ d;
+                if (j > i) {
+                    const bool up = (i & size) == 0;
+                    const unsigned long long a = k[i], c = k[j];
+                    const bool sw = (a > c) == up;
+                    k[i] = sw ? c : a;
+                    k[j] = sw ? a : c;
+                }
+            }
+        }
+    }
+    double med = NAN;
+    if (n > 0) {
+        const int k1 = (n - 1) / 2, k2 = n / 2;
+        unsigned long long a1 = 0, a2 = 0;
+#pragma unroll
+        for (int i = 0; i < kProfFast; ++i) {
+            if (i == k1) a1 = k[i];
+            if (i == k2) a2 = k[i];
+        }
+        med = (k1 == k2) ? value_of(a1) : (value_of(a1) + value_of(a2)) * 0.5;
+    }
+    profiles[((size_t)f * cap + b) * nspat + row] = med;
+}
+
 __global__ void __launch_bounds__(kProfWarps * 32)
 bin_profile_kernel(const double* __restrict__ data, size_t frame_stride, int nspat, int ndisp,
                    const uint8_t* __restrict__ gap, const int32_t* __restrict__ bins_i, const int32_t* __restrict__ nbins,
@@ -153,16 +209,17 @@ bin_profile_kernel(const double* __restrict__ data, size_t frame_stride, int nsp
     const int warp = threadIdx.x >> 5;
     WarpScope sc{(int)(threadIdx.x & 31)};
     const int f = blockIdx.y;
-    const long long item = (long long)blockIdx.x * kProfWarps + warp;
-    const int b = (int)(item / nspat), row = (int)(item % nspat);
+    const int b = blockIdx.x;                   // one CTA per bin, its warps stride over the rows
     if (b >= nbins[f]) return;
     const int first = bins_i[((size_t)f * cap + b) * 2], last = bins_i[((size_t)f * cap + b) * 2 + 1];
     const int w = last - first;
+    if (w == kProfFast) return;                 // done by bin_profile16_kernel
     struct BinKeys {
         const double* p;
         const uint8_t* g;
         __device__ unsigned long long operator()(int i) const { return g[i] ? kKeyExcluded : key_or_excluded(p[i]); }
     };
+    for (int row = warp; row < nspat; row += kProfWarps) {
     BinKeys keys{data + (size_t)f * frame_stride + (size_t)row * ndisp + first, gap + (size_t)f * ndisp + first};
     double med;
     if (w <= kProfStage) {
@@ -198,6 +255,8 @@ bin_profile_kernel(const double* __restrict__ data, size_t frame_stride, int nsp
         med = median_of(sc, keys, w, n_valid, hist_all[warp], &cells[warp]);
     }
     if (sc.tid == 0) profiles[((size_t)f * cap + b) * nspat + row] = med;
+    __syncwarp();
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

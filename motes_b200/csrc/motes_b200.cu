@@ -233,8 +233,10 @@ static int stage_bins(motes_handle* h, Batch& b, const uint8_t* qual, size_t qua
 static int stage_bin_profiles(motes_handle* h, Batch& b, const double* data, size_t frame_stride, int set) {
     StageTimer timer(h, ST_BIN_PROFILES);
     long long items = (long long)b.cap * b.nspat;
-    int gx = (int)((items + kProfWarps - 1) / kProfWarps);
-    bin_profile_kernel<<<dim3(gx, b.F), kProfWarps * 32, 0, h->stream>>>(data, frame_stride, b.nspat, b.ndisp, b.gap,
+    bin_profile16_kernel<<<dim3((unsigned)((items + 127) / 128), b.F), 128, 0, h->stream>>>(
+        data, frame_stride, b.nspat, b.ndisp, b.gap, b.bins_i[set], b.nbins[set], b.cap, b.profiles);
+    MOTES_LAUNCHED(h);
+    bin_profile_kernel<<<dim3(b.cap, b.F), kProfWarps * 32, 0, h->stream>>>(data, frame_stride, b.nspat, b.ndisp, b.gap,
                                                                          b.bins_i[set], b.nbins[set], b.cap, b.profiles);
     MOTES_LAUNCHED(h);
     return MOTES_OK;
