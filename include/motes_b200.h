@@ -115,6 +115,14 @@ int motes_run_frames_host(motes_handle* h, double* data, double* errs, const uin
 int motes_run_frames_dev(motes_handle* h, double* data, double* errs, const uint8_t* qual, int nframes,
                          int nspat, int ndisp, int cap, const motes_params* params, const double* seeing,
                          const double* pixres, uint32_t* rng_states, const motes_outputs* out);
+/* motes_run_frames_host without the final wait: uploads, kernels and downloads are queued on the handle's
+ * streams and the call returns.  Every host buffer (inputs, rng_states, outputs; pinned memory for real
+ * overlap) must stay untouched until motes_synchronize(h) returns.  A caller with a stream of batches
+ * alternates between two handles, so that the upload of batch k+1 runs under the kernels of batch k
+ * (the reference has no counterpart: core.motes processes one file at a time, core.py:28-275). */
+int motes_run_frames_host_async(motes_handle* h, double* data, double* errs, const uint8_t* qual, int nframes,
+                                int nspat, int ndisp, int cap, const motes_params* params, const double* seeing,
+                                const double* pixres, uint32_t* rng_states, int copy_back, const motes_outputs* out);
 /* float64 {0,1} quality frame -> uint8 on the device (harvesters produce float64, io/gmosio.py:50-52) */
 int motes_qual_pack_dev(motes_handle* h, const double* qual, size_t count, uint8_t* out);
 

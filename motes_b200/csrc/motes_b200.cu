@@ -719,6 +719,8 @@ int motes_set_stream(motes_handle* h, void* cuda_stream) {
 
 int motes_synchronize(motes_handle* h) {
     if (!h) return fail_arg("null handle");
+    MOTES_CUDA(cudaStreamSynchronize(h->copy_stream));
+    MOTES_CUDA(cudaStreamSynchronize(h->lane1_stream));
     MOTES_CUDA(cudaStreamSynchronize(h->stream));
     return MOTES_OK;
 }
@@ -811,9 +813,9 @@ int motes_run_frames_dev(motes_handle* h, double* data, double* errs, const uint
     return run_frames_chunked(h, data, errs, qual, nframes, nspat, ndisp, cap, p, seeing, pixres, rng_states, upload, emit);
 }
 
-int motes_run_frames_host(motes_handle* h, double* data, double* errs, const uint8_t* qual, int nframes, int nspat,
-                          int ndisp, int cap, const motes_params* params, const double* seeing, const double* pixres,
-                          uint32_t* rng_states, int copy_back, const motes_outputs* out) {
+static int run_frames_host_enqueue(motes_handle* h, double* data, double* errs, const uint8_t* qual, int nframes, int nspat,
+                                   int ndisp, int cap, const motes_params* params, const double* seeing, const double* pixres,
+                                   uint32_t* rng_states, int copy_back, const motes_outputs* out) {
     MOTES_TRY(check_run_args(h, data, errs, qual, nframes, nspat, ndisp, cap, params, seeing, pixres, rng_states, out));
     MOTES_CUDA(cudaSetDevice(h->device));
     const motes_params p = *params;
@@ -850,13 +852,30 @@ int motes_run_frames_host(motes_handle* h, double* data, double* errs, const uin
         }
         return MOTES_OK;
     };
-    int rc = run_frames_chunked(h, d_data, d_errs, d_qual, nframes, nspat, ndisp, cap, p, d_seeing, d_pixres, d_rng,
-                                upload_chunk, emit);
+    return run_frames_chunked(h, d_data, d_errs, d_qual, nframes, nspat, ndisp, cap, p, d_seeing, d_pixres, d_rng,
+                              upload_chunk, emit);
+}
+
+int motes_run_frames_host(motes_handle* h, double* data, double* errs, const uint8_t* qual, int nframes, int nspat,
+                          int ndisp, int cap, const motes_params* params, const double* seeing, const double* pixres,
+                          uint32_t* rng_states, int copy_back, const motes_outputs* out) {
+    int rc = run_frames_host_enqueue(h, data, errs, qual, nframes, nspat, ndisp, cap, params, seeing, pixres, rng_states,
+                                     copy_back, out);
     // the caller's buffers must not be touched after return, whatever happened
-    cudaStreamSynchronize(h->copy_stream);
-    cudaStreamSynchronize(h->lane1_stream);
-    MOTES_CUDA(cudaStreamSynchronize(h->stream));
+    if (h) {
+        cudaStreamSynchronize(h->copy_stream);
+        cudaStreamSynchronize(h->lane1_stream);
+        cudaError_t e = cudaStreamSynchronize(h->stream);
+        if (rc == MOTES_OK && e != cudaSuccess) return fail_cuda(e, "cudaStreamSynchronize", __FILE__, __LINE__);
+    }
     return rc;
+}
+
+int motes_run_frames_host_async(motes_handle* h, double* data, double* errs, const uint8_t* qual, int nframes, int nspat,
+                                int ndisp, int cap, const motes_params* params, const double* seeing, const double* pixres,
+                                uint32_t* rng_states, int copy_back, const motes_outputs* out) {
+    return run_frames_host_enqueue(h, data, errs, qual, nframes, nspat, ndisp, cap, params, seeing, pixres, rng_states,
+                                   copy_back, out);
 }
 
 // ------------------------------------------------------------------------------------------ stage entry points
