@@ -354,7 +354,7 @@ static int stage_bootstrap_segmented(motes_handle* h, Batch& b, uint32_t* rng, b
     uint32_t* col_end = col_start + (size_t)wave * b.ndisp;
     uint32_t* retry_list = col_end + (size_t)wave * b.ndisp;          // columns the histogram kernel hands to the exact one
     uint32_t* retry_count = retry_list + (size_t)wave * b.ndisp;
-    static const int col_mode = getenv("MOTES_B200_COLUMN") ? atoi(getenv("MOTES_B200_COLUMN")) : 256;   // 0: exact kernel only; else window
+    const int col_mode = h->column_window;      // 0: exact kernel only; else the histogram window
     const size_t colh_smem = sky_colh_smem(b.nspat);
     MOTES_CUDA(cudaFuncSetAttribute(sky_column_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)colh_smem));
     const uint32_t* polys = h->jump_polys.as<uint32_t>();
@@ -670,6 +670,8 @@ int motes_create(int device, motes_handle** out) {
     // A/B switches: "classic" = one CTA walks a frame's whole stream, "ws" = its warp-specialised variant
     const char* boot = getenv("MOTES_B200_BOOTSTRAP");
     h->boot_mode = (boot && strcmp(boot, "classic") == 0) ? 1 : (boot && strcmp(boot, "ws") == 0) ? 2 : 0;
+    const char* colw = getenv("MOTES_B200_COLUMN");
+    if (colw) h->column_window = atoi(colw);
     const char* fitm = getenv("MOTES_B200_FIT");              // "warp": round-1 one-warp-per-fit kernel
     h->fit_mode = (fitm && strcmp(fitm, "warp") == 0) ? 1 : 0;
     const char* budget = getenv("MOTES_B200_STREAM_GB");

@@ -324,7 +324,8 @@ __device__ __forceinline__ int walk_count8_from(const uint4& d, uint32_t pos0, u
 
 constexpr int kWalkThreads = 1024;
 constexpr int kWalkWarps = kWalkThreads / 32;
-constexpr int kSubPerChunk = kWalkChunk / kSubChunk;       // 4
+constexpr int kSubPerChunk = kWalkChunk / kSubChunk;
+constexpr int kPieceRows = kSubChunk / 256;                // 256 words per warp-wide 16-byte load
 
 // One CTA per frame.  Per column: every warp counts the accepted draws of one 2048-word piece of
 // the range the column is expected to span (100 (mask + 1) words, +1 piece: > 10 sigma), one
@@ -407,15 +408,15 @@ sky_walk_kernel(const uint16_t* __restrict__ stream, SegLayout lay, const uint32
                                                                   (size_t)((sb - first) % kWalkChunk) * 2);
                 if (packed_ok && sb >= P && sb + kSubChunk <= limit) {
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) cnt += walk_count8_packed(src[k * 32 + lane], mask2, kk2);
+                    for (int k = 0; k < kPieceRows; ++k) cnt += walk_count8_packed(src[k * 32 + lane], mask2, kk2);
                 } else if (packed_ok && sb + kSubChunk <= limit) {
 #pragma unroll
-                    for (int k = 0; k < 8; ++k)
+                    for (int k = 0; k < kPieceRows; ++k)
                         cnt += walk_count8_from(src[k * 32 + lane], sb + (uint32_t)(k * 256 + lane * 8), P, limit, mask, top,
                                                 mask2, kk2);
                 } else {
 #pragma unroll
-                    for (int k = 0; k < 8; ++k)
+                    for (int k = 0; k < kPieceRows; ++k)
                         cnt += walk_count8(src[k * 32 + lane], sb + (uint32_t)(k * 256 + lane * 8), P, limit, mask, top);
                 }
 #pragma unroll
@@ -448,7 +449,7 @@ sky_walk_kernel(const uint16_t* __restrict__ stream, SegLayout lay, const uint32
                     const int stage = (int)(chunk % kWalkStages);
                     const uint4* src = reinterpret_cast<const uint4*>(walk_smem + (size_t)stage * kWalkChunkBytes +
                                                                       (size_t)((sb - first) % kWalkChunk) * 2);
-                    for (int k = 0; k < 8; ++k) {
+                    for (int k = 0; k < kPieceRows; ++k) {
                         const uint4 d = src[k * 32 + lane];
                         const uint32_t pos0 = sb + (uint32_t)(k * 256 + lane * 8);
                         const uint32_t mine = (packed_ok && sb + kSubChunk <= limit)
