@@ -155,3 +155,22 @@ extern "C" int hostsim_sky_poly(double* data, double* errs, int nspat, int ndisp
     for (int c = 0; c < ndisp; ++c) motes::sky_apply_column_poly(data, errs, nspat, ndisp, c, flag[c], model, model_err);
     return 0;
 }
+
+// MT19937 jump-ahead polynomials (csrc/mtjump.hpp, host code of the product): the window reached by the
+// polynomial jump of 2^log2_stride words against the window reached by running the recurrence that far.
+// Returns the number of differing words (word 0: top bit only), or -1 when the table could not be built.
+#include "../../motes_b200/csrc/mtjump.hpp"
+extern "C" int hostsim_jump_mismatches(uint32_t seed, int log2_stride) {
+    const motes::JumpTable& table = motes::jump_table();
+    if (!table.ok || log2_stride < 0 || log2_stride > 24) return -1;
+    motes::jump_detail::HostMt gen(seed);
+    const size_t stride = (size_t)1 << log2_stride;
+    std::vector<uint32_t> w(624 + stride + 624);
+    for (int i = 0; i < 624; ++i) w[i] = gen.mt[i];
+    for (size_t n = 624; n < w.size(); ++n) w[n] = gen.next_raw();
+    uint32_t out[624];
+    motes::jump_window_host(table.poly(log2_stride), w.data(), out);
+    int bad = ((out[0] ^ w[stride]) & 0x80000000u) ? 1 : 0;
+    for (int j = 1; j < 624; ++j) bad += out[j] != w[stride + j];
+    return bad;
+}

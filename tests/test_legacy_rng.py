@@ -47,3 +47,16 @@ def test_legacy_gauss():
     g = LegacyGauss(MT19937(4242))
     got = np.concatenate([g.normal(3.0, 2.5, 100), g.normal(-1.0, 0.5, 100)])
     assert np.array_equal(ref, got)
+
+
+def test_jump_polynomials_reach_the_same_generator_window():
+    """The jump-ahead table the segmented bootstrap uploads (csrc/mtjump.hpp: characteristic polynomial by
+    Berlekamp-Massey, x^(2^s) by repeated squaring): jumping 2^s words equals running the recurrence 2^s words."""
+    import ctypes, os, subprocess
+    from conftest import ROOT
+    d = os.path.join(ROOT, "tests", "hostsim")
+    subprocess.check_call(["make", "-s", "-C", d])
+    lib = ctypes.CDLL(os.path.join(d, "libmotes_hostsim.so"))
+    lib.hostsim_jump_mismatches.argtypes = [ctypes.c_uint32, ctypes.c_int]
+    for seed, s in ((1234, 0), (1, 3), (5489, 10), (2024, 16), (7, 18), (4242, 20)):
+        assert lib.hostsim_jump_mismatches(seed, s) == 0, (seed, s)
