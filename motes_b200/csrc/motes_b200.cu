@@ -175,9 +175,22 @@ static int stage_fit(motes_handle* h, const FitBatch& fb) {
     // small groups are latency-bound (few fits in flight): spread each step over an 8-lane team; large groups are
     // throughput-bound: one thread per step costs an eighth of the instructions (B200, 128 frames: 79 vs 102 ms)
     const bool team_step = group < 16;
+    // CTAs per SM: registers allow 4 (128 regs), 5 (96) or 6 (80); shared memory then caps the group size
+    static const int occ_env = getenv("MOTES_B200_FIT_OCC") ? atoi(getenv("MOTES_B200_FIT_OCC")) : 0;
+    int occ = occ_env >= 4 && occ_env <= 6 ? occ_env : 4;
+    if (!team_step) {
+        const int gcap = fit_group_for_occupancy(fb.m, (size_t)228 * 1024, occ);
+        if (gcap < 8) occ = 4;
+        else if (group > gcap) group = gcap;
+    } else {
+        occ = 4;
+    }
     const size_t smem = fit_group_smem(fb.m, (int)group);
     if (smem > h->smem_optin) return fail_arg("nspat too large for the shared-memory fit slab");
-    auto kernel = team_step ? moffat_fit_group_kernel<true> : moffat_fit_group_kernel<false>;
+    auto kernel = team_step ? moffat_fit_group_kernel<true, 4>
+                  : occ == 6 ? moffat_fit_group_kernel<false, 6>
+                  : occ == 5 ? moffat_fit_group_kernel<false, 5>
+                             : moffat_fit_group_kernel<false, 4>;
     MOTES_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     MOTES_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kFitThreads, smem));

@@ -215,6 +215,7 @@ MOTES_HD void linearize(const Ctx& ctx, int m, const double* profile, double sca
     for (int k = 0; k < n; ++k) inv_dx[k] = 1.0 / dx[k];
     const double c1 = x[1] + h[1], a1 = x[2] + h[2];
     const double aa = x[2] * x[2], aa1 = a1 * a1;
+    const double inv_aa = 1.0 / aa, inv_aa1 = 1.0 / aa1;
     double gp[n] = {0, 0, 0, 0, 0, 0};
     for (int i = ctx.lane; i < m; i += Ctx::kLanes) {
         const double r = (double)i;
@@ -223,12 +224,13 @@ MOTES_HD void linearize(const Ctx& ctx, int m, const double* profile, double sca
         // the shifted pow is the base pow times (s'/s)^-beta resp. s^-h, evaluated from the small
         // relative change of s = 1 + q (shifted_unit); a full pow only when the step is not small.
         const double off = r - x[1], off1 = r - c1;
-        const double q = (off * off) / aa;
+        // (reciprocal multiplies: the differences q' - q below only need each q to a relative 1e-16)
+        const double q = (off * off) * inv_aa;
         const double s = 1.0 + q;
         const double inv_s = 1.0 / s;
         double uc, ua, ub_;
-        if (!shifted_unit(u0, (off1 * off1) / aa, q, inv_s, x[3], &uc)) uc = moffat_unit_call(r, c1, x[2], x[3]);
-        if (!shifted_unit(u0, (off * off) / aa1, q, inv_s, x[3], &ua)) ua = moffat_unit_call(r, x[1], a1, x[3]);
+        if (!shifted_unit(u0, (off1 * off1) * inv_aa, q, inv_s, x[3], &uc)) uc = moffat_unit_call(r, c1, x[2], x[3]);
+        if (!shifted_unit(u0, (off * off) * inv_aa1, q, inv_s, x[3], &ua)) ua = moffat_unit_call(r, x[1], a1, x[3]);
         if (!shifted_unit_beta(u0, s, dx[3], &ub_)) ub_ = moffat_unit_call(r, x[1], x[2], x[3] + h[3]);
         double col[n];
         col[0] = ((moffat_value(u0, r, x[0] + h[0], x[4], x[5]) - yi) - fi) * inv_dx[0];

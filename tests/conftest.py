@@ -31,4 +31,7 @@ def golden_inputs(meta):
     spec["chip_gaps"] = tuple(tuple(g) for g in spec["chip_gaps"])
     frame, axes, header = synth.make_frame(synth.FrameSpec(**spec))
     assert synth.frame_digest(frame) == meta["input_sha256"], "synthetic generator is not bit-reproducible here"
+    if meta.get("input_dtype"):          # e.g. ">f4": the dtype the GMOS harvester hands over (gmosio.py:40-52)
+        frame["data"] = frame["data"].astype(meta["input_dtype"])
+        frame["errs"] = frame["errs"].astype(meta["input_dtype"])
     return frame, axes, header, SimpleNamespace(**meta["args"])

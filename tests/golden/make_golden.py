@@ -144,6 +144,8 @@ CASES = {
                     {"minimum_column_limit": 0, "extraction_snr_limit": 0, "sky_snr_limit": 0}, 14, False),
     "t1_faint": ("T1", {"amplitude": 25.0, "chip_gaps": ()}, {}, 15, False),
     "c1_sky0": ("C1", {}, {}, 1234, False),
+    # GMOS dtypes as harvested (gmosio.py:40-52): data / errs big-endian float32, qual float64
+    "t1_f32": ("T1", {"input_dtype": ">f4"}, {}, 16, False),
 }
 
 
@@ -155,10 +157,15 @@ def main():
     for name, (config, spec_over, args_over, seed, keep_frames) in CASES.items():
         if only and name not in only:
             continue
+        spec_over = dict(spec_over)
+        input_dtype = spec_over.pop("input_dtype", None)
         spec = synth.config_spec(config, seed=seed, **spec_over)
         args = synth.default_args(**args_over)
         frame, axes, header = synth.make_frame(spec)
         digest = synth.frame_digest(frame)
+        if input_dtype:
+            frame["data"] = frame["data"].astype(input_dtype)
+            frame["errs"] = frame["errs"].astype(input_dtype)
         out = run_reference(tracing, sky, extraction, recorder, copy.deepcopy(frame), axes,
                             dict(header), args, seed)
         # self-noise control: same pipeline, inputs moved by one ulp
@@ -172,7 +179,7 @@ def main():
             out.pop("data_after")
             out.pop("errs_after")
         meta = dict(case=name, config=config, spec=synth.spec_to_dict(spec), args=vars(args),
-                    rng_seed=seed, input_sha256=digest,
+                    rng_seed=seed, input_sha256=digest, input_dtype=input_dtype,
                     versions=dict(numpy=np.__version__, scipy=__import__("scipy").__version__))
         path = os.path.join(HERE, name + ".npz")
         np.savez_compressed(path, meta=json.dumps(meta), **out)

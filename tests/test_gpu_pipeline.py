@@ -53,7 +53,7 @@ def _check_frame(name, out, g, nspat, sky_exact=True):
     print(name, report)
 
 
-@pytest.mark.parametrize("name", ["t1_sky0", "t1_nosky", "t2_cr_sky0", "t1_faint", "t2_unbinned", "c1_sky0", "t1_sky2"])
+@pytest.mark.parametrize("name", ["t1_sky0", "t1_nosky", "t2_cr_sky0", "t1_faint", "t2_unbinned", "c1_sky0", "t1_sky2", "t1_f32"])
 def test_whole_path_matches_reference(name):
     from motes_b200 import pipeline
     meta, g = load_golden(name)

@@ -7,7 +7,7 @@ import pytest
 from conftest import load_golden, golden_inputs
 from oracle import motes_oracle as mo
 
-FAST = ["t1_sky0", "t1_nosky", "t2_cr_sky0", "t1_faint", "t2_unbinned", "t1_sky2"]
+FAST = ["t1_sky0", "t1_nosky", "t2_cr_sky0", "t1_faint", "t2_unbinned", "t1_sky2", "t1_f32"]
 STAGES = ["median_profile", "median_params", "scale", "seeing_px", "bin_rows", "sky_bins", "sky_params",
           "sky_limits", "sky_model", "sky_uncertainty", "ext_bins", "ext_params", "ext_limit_table",
           "ext_profiles", "ext_limits", "data_after", "errs_after", "optimal", "optimal_err",
