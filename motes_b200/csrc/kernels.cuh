@@ -349,20 +349,8 @@ MOTES_HD size_t fit_group_smem(int m, int group) {
     return (fit_sweep_doubles(m) + FitBlockCtx::kRedDoubles + kFitStepScratch) * sizeof(double) +
            (size_t)group * sizeof(FitState);
 }
-// largest group that lets `ctas` CTAs share an SM's shared memory (0: not even one fit)
-MOTES_HD int fit_group_for_occupancy(int m, size_t smem_per_sm, int ctas) {
-    const size_t per_cta = smem_per_sm / (size_t)ctas;
-    const size_t fixed = fit_group_smem(m, 0) + 1024;            // + the per-CTA reservation of the runtime
-    if (per_cta <= fixed) return 0;
-    const size_t g = (per_cta - fixed) / sizeof(FitState);
-    return (int)(g > (size_t)kFitGroupMax ? (size_t)kFitGroupMax : g);
-}
-
-// out of line: the step logic is long, runs once per round and must not bloat the sweep loop's registers
-__device__ __noinline__ bool fit_propose_call(int m, FitState* st) { return fit_propose(m, *st); }
-
-template <bool TEAM_STEP, int MINB>
-__global__ void __launch_bounds__(kFitThreads, MINB)
+template <bool TEAM_STEP>
+__global__ void __launch_bounds__(kFitThreads, 4)
 moffat_fit_group_kernel(FitBatch fb, int group, unsigned int* __restrict__ queue) {
     extern __shared__ __align__(16) double fitb_smem[];
     __shared__ unsigned int s_item;

@@ -164,6 +164,12 @@ static int stage_fit_warp(motes_handle* h, const FitBatch& fb) {
 }
 
 // Groups of fits advanced in lock step by one CTA each (kernels.cuh: moffat_fit_group_kernel).
+//
+// Measured on B200 (128 frames of 4096 x 400, 65.7 k fits, 76 ms) and NOT adopted: 5 or 6 CTAs per SM (96 / 80
+// registers, group state in global memory): 76 ms; groups of 64 / 128 fits with one step-phase thread each on all
+// four warps: 75-76 ms; one warp per group of 8 / 16 / 32 fits with warp-wide sweeps and no CTA barriers: 96-106 ms;
+// a single Householder body instead of six specialisations: 81 ms.  ncu: instruction-cache hit rate 62 %, FP64 pipe
+// 19 %, issue 25 % - the kernel streams ~110 KB of mostly straight-line FP64 code per fit and round.
 static int stage_fit(motes_handle* h, const FitBatch& fb) {
     if (fb.nframes <= 0 || fb.bound <= 0) return MOTES_OK;
     if (h->fit_mode == 1) return stage_fit_warp(h, fb);
@@ -173,24 +179,11 @@ static int stage_fit(motes_handle* h, const FitBatch& fb) {
     if (group < 1) group = 1;
     if (group > kFitGroupMax) group = kFitGroupMax;
     // small groups are latency-bound (few fits in flight): spread each step over an 8-lane team; large groups are
-    // throughput-bound: one thread per step costs an eighth of the instructions (B200, 128 frames: 79 vs 102 ms)
+    // throughput-bound: one thread per step costs an eighth of the instructions (B200, 128 frames: 76 vs 102 ms)
     const bool team_step = group < 16;
-    // CTAs per SM: registers allow 4 (128 regs), 5 (96) or 6 (80); shared memory then caps the group size
-    static const int occ_env = getenv("MOTES_B200_FIT_OCC") ? atoi(getenv("MOTES_B200_FIT_OCC")) : 0;
-    int occ = occ_env >= 4 && occ_env <= 6 ? occ_env : 4;
-    if (!team_step) {
-        const int gcap = fit_group_for_occupancy(fb.m, (size_t)228 * 1024, occ);
-        if (gcap < 8) occ = 4;
-        else if (group > gcap) group = gcap;
-    } else {
-        occ = 4;
-    }
     const size_t smem = fit_group_smem(fb.m, (int)group);
     if (smem > h->smem_optin) return fail_arg("nspat too large for the shared-memory fit slab");
-    auto kernel = team_step ? moffat_fit_group_kernel<true, 4>
-                  : occ == 6 ? moffat_fit_group_kernel<false, 6>
-                  : occ == 5 ? moffat_fit_group_kernel<false, 5>
-                             : moffat_fit_group_kernel<false, 4>;
+    auto kernel = team_step ? moffat_fit_group_kernel<true> : moffat_fit_group_kernel<false>;
     MOTES_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     MOTES_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kFitThreads, smem));

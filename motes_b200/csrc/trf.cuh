@@ -62,10 +62,21 @@ MOTES_HD FitScratch carve_fit_scratch(double* slab, int m) {
 
 namespace trf_detail {
 
+// The step-selection logic runs once per fit and round on one thread (or one 8-lane team): its dozens of FP64
+// divisions and square roots are issued out of line so that the fit kernel's instruction footprint stays within
+// the instruction cache (ncu on B200: 62 % hit rate with everything inlined).  Same IEEE operations, same bits.
+#if defined(__CUDA_ARCH__)
+__device__ __noinline__ double ool_div(double a, double b) { return a / b; }
+__device__ __noinline__ double ool_sqrt(double a) { return sqrt(a); }
+#else
+inline double ool_div(double a, double b) { return a / b; }
+inline double ool_sqrt(double a) { return sqrt(a); }
+#endif
+
 MOTES_HD double norm6(const double* x) {
     double s = 0.0;
     for (int i = 0; i < kParams; ++i) s += x[i] * x[i];
-    return sqrt(s);
+    return ool_sqrt(s);
 }
 MOTES_HD double dot6(const double* a, const double* b) {
     double s = 0.0;
@@ -118,7 +129,7 @@ MOTES_HD double stride_to_bound(const double* x, const double* s, const double* 
     double t = INFINITY;
     for (int i = 0; i < kParams; ++i) {
         steps[i] = INFINITY;
-        if (s[i] != 0.0) steps[i] = fmax((lb[i] - x[i]) / s[i], (ub[i] - x[i]) / s[i]);
+        if (s[i] != 0.0) steps[i] = fmax(ool_div(lb[i] - x[i], s[i]), ool_div(ub[i] - x[i], s[i]));
         // numpy.min propagates NaN
         if (steps[i] < t || steps[i] != steps[i]) t = steps[i];
     }
@@ -153,7 +164,7 @@ MOTES_HD void line_minimum(double a, double b, double lo, double hi, double c, d
     double y = hi * (a * hi + b) + c;
     if (y < yb) { yb = y; tb = hi; }
     if (a != 0.0) {
-        double vertex = -0.5 * b / a;
+        double vertex = ool_div(-0.5 * b, a);
         if (lo < vertex && vertex < hi) {
             y = vertex * (a * vertex + b) + c;
             if (y < yb) { yb = y; tb = vertex; }
@@ -170,7 +181,7 @@ MOTES_HD void more_step(int m, const double* s, const double* suf, const double*
     double tmp[kParams];
     bool full_rank = (m >= kParams) && (s[kParams - 1] > kEps * m * s[0]);
     if (full_rank) {
-        for (int j = 0; j < kParams; ++j) tmp[j] = (suf[j] / s[j]) / s[j];   // uf / s
+        for (int j = 0; j < kParams; ++j) tmp[j] = ool_div(ool_div(suf[j], s[j]), s[j]);   // uf / s
         for (int i = 0; i < kParams; ++i) {
             double acc = 0.0;
             for (int j = 0; j < kParams; ++j) acc += V[i * kParams + j] * tmp[j];
@@ -178,46 +189,47 @@ MOTES_HD void more_step(int m, const double* s, const double* suf, const double*
         }
         if (norm6(p_h) <= radius) { *alpha_io = 0.0; return; }
     }
-    double upper = norm6(suf) / radius;
+    double upper = ool_div(norm6(suf), radius);
     double lower = 0.0;
     if (full_rank) {
         double pn = 0.0, dsum = 0.0;
         for (int j = 0; j < kParams; ++j) {
             double den = s[j] * s[j];
-            double q = suf[j] / den;
+            double q = ool_div(suf[j], den);
             pn += q * q;
-            dsum += (suf[j] * suf[j]) / (den * den * den);
+            dsum += ool_div(suf[j] * suf[j], den * den * den);
         }
-        pn = sqrt(pn);
-        double phi = pn - radius, dphi = -dsum / pn;
-        lower = -phi / dphi;
+        pn = ool_sqrt(pn);
+        double phi = pn - radius, dphi = ool_div(-dsum, pn);
+        lower = ool_div(-phi, dphi);
     }
     double alpha = *alpha_io;
-    if (!full_rank && alpha == 0.0) alpha = fmax(0.001 * upper, sqrt(lower * upper));
+    if (!full_rank && alpha == 0.0) alpha = fmax(0.001 * upper, ool_sqrt(lower * upper));
+#pragma unroll 1
     for (int it = 0; it < 10; ++it) {
-        if (alpha < lower || alpha > upper) alpha = fmax(0.001 * upper, sqrt(lower * upper));
+        if (alpha < lower || alpha > upper) alpha = fmax(0.001 * upper, ool_sqrt(lower * upper));
         double pn = 0.0, dsum = 0.0;
         for (int j = 0; j < kParams; ++j) {
             double den = s[j] * s[j] + alpha;
-            double q = suf[j] / den;
+            double q = ool_div(suf[j], den);
             pn += q * q;
-            dsum += (suf[j] * suf[j]) / (den * den * den);
+            dsum += ool_div(suf[j] * suf[j], den * den * den);
         }
-        pn = sqrt(pn);
-        double phi = pn - radius, dphi = -dsum / pn;
+        pn = ool_sqrt(pn);
+        double phi = pn - radius, dphi = ool_div(-dsum, pn);
         if (phi < 0.0) upper = alpha;
-        double ratio = phi / dphi;
+        double ratio = ool_div(phi, dphi);
         lower = fmax(lower, alpha - ratio);
-        alpha -= (phi + radius) * ratio / radius;
+        alpha -= ool_div((phi + radius) * ratio, radius);
         if (fabs(phi) < 0.01 * radius) break;
     }
-    for (int j = 0; j < kParams; ++j) tmp[j] = suf[j] / (s[j] * s[j] + alpha);
+    for (int j = 0; j < kParams; ++j) tmp[j] = ool_div(suf[j], s[j] * s[j] + alpha);
     for (int i = 0; i < kParams; ++i) {
         double acc = 0.0;
         for (int j = 0; j < kParams; ++j) acc += V[i * kParams + j] * tmp[j];
         p_h[i] = -acc;
     }
-    double scale = radius / norm6(p_h);
+    double scale = ool_div(radius, norm6(p_h));
     for (int i = 0; i < kParams; ++i) p_h[i] *= scale;
     *alpha_io = alpha;
 }
@@ -246,16 +258,16 @@ MOTES_HD double choose_step(const double* x, const double* R, const double* g_h,
     double to_tr;
     {
         double a = dot6(r_h, r_h), b = dot6(p_h, r_h), c = dot6(p_h, p_h) - radius * radius;
-        double disc = sqrt(b * b - a * c);
+        double disc = ool_sqrt(b * b - a * c);
         double q = -(b + copysign(disc, b));
-        double t1 = q / a, t2 = c / q;
+        double t1 = ool_div(q, a), t2 = ool_div(c, q);
         to_tr = (t1 < t2) ? t2 : t1;
     }
     double to_bound = stride_to_bound(x_on, r, lb, ub, nullptr);
     double r_stride = fmin(to_bound, to_tr);
     double r_lo, r_hi;
     if (r_stride > 0.0) {
-        r_lo = (1.0 - theta) * p_stride / r_stride;
+        r_lo = ool_div((1.0 - theta) * p_stride, r_stride);
         r_hi = (r_stride == to_bound) ? theta * to_bound : to_tr;
     } else {
         r_lo = 0.0;
@@ -282,7 +294,7 @@ MOTES_HD double choose_step(const double* x, const double* R, const double* g_h,
 
     double ag_h[kParams], ag[kParams];
     for (int i = 0; i < kParams; ++i) { ag_h[i] = -g_h[i]; ag[i] = d[i] * ag_h[i]; }
-    double ag_to_tr = radius / norm6(ag_h);
+    double ag_to_tr = ool_div(radius, norm6(ag_h));
     double ag_to_bound = stride_to_bound(x, ag, lb, ub, nullptr);
     double ag_stride = (ag_to_bound < ag_to_tr) ? theta * ag_to_bound : ag_to_tr;
     double ag_value;
@@ -348,11 +360,11 @@ MOTES_HD void jacobi_svd6(const Ctx& ctx, const double* R, const double* z, doub
                     a += wp[r] * wp[r]; b += wq[r] * wq[r]; c += wp[r] * wq[r];
                 }
                 ctx.sync();
-                if (c != 0.0 && fabs(c) > kEps * sqrt(a * b)) {
+                if (c != 0.0 && fabs(c) > kEps * trf_detail::ool_sqrt(a * b)) {
                     rotated = 1;
-                    double zeta = (b - a) / (2.0 * c);
-                    double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-                    double cs = 1.0 / sqrt(1.0 + t * t);
+                    double zeta = trf_detail::ool_div(b - a, 2.0 * c);
+                    double t = trf_detail::ool_div(copysign(1.0, zeta), fabs(zeta) + trf_detail::ool_sqrt(1.0 + zeta * zeta));
+                    double cs = trf_detail::ool_div(1.0, trf_detail::ool_sqrt(1.0 + t * t));
                     double sn = cs * t;
                     if (ctx.lane == 0) {
                         for (int r = 0; r < n; ++r) {
@@ -374,7 +386,7 @@ MOTES_HD void jacobi_svd6(const Ctx& ctx, const double* R, const double* z, doub
     for (int j = 0; j < n; ++j) {
         double nn = 0.0, zz = 0.0;
         for (int r = 0; r < n; ++r) { nn += w[r * n + j] * w[r * n + j]; zz += w[r * n + j] * z[r]; }
-        sv[j] = sqrt(nn);
+        sv[j] = trf_detail::ool_sqrt(nn);
         sz[j] = zz;
         order[j] = j;
     }

@@ -363,7 +363,7 @@ MOTES_HD bool propose_begin(const FitState* st, ProposeVars& pv, bool write, Fit
     if (first) {
         double t[n];
 #pragma unroll
-        for (int i = 0; i < n; ++i) t[i] = pv.x[i] / sqrt(v[i]);
+        for (int i = 0; i < n; ++i) t[i] = ool_div(pv.x[i], ool_sqrt(v[i]));
         pv.radius = norm6(t);
         if (pv.radius == 0.0) pv.radius = 1.0;
         pv.alpha = 0.0;
@@ -378,7 +378,7 @@ MOTES_HD bool propose_begin(const FitState* st, ProposeVars& pv, bool write, Fit
         return false;
     }
 #pragma unroll
-    for (int i = 0; i < n; ++i) { pv.d[i] = sqrt(v[i]); pv.g_h[i] = pv.d[i] * pv.g[i]; }
+    for (int i = 0; i < n; ++i) { pv.d[i] = ool_sqrt(v[i]); pv.g_h[i] = pv.d[i] * pv.g[i]; }
     pv.theta = fmax(0.995, 1.0 - g_norm);
     return true;
 }
