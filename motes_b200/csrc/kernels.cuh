@@ -349,6 +349,9 @@ MOTES_HD size_t fit_group_smem(int m, int group) {
     return (fit_sweep_doubles(m) + FitBlockCtx::kRedDoubles + kFitStepScratch) * sizeof(double) +
            (size_t)group * sizeof(FitState);
 }
+// out of line: the step logic is long, runs once per round and must not bloat the sweep loop's registers
+__device__ __noinline__ bool fit_propose_call(int m, FitState* st) { return fit_propose(m, *st); }
+
 template <bool TEAM_STEP>
 __global__ void __launch_bounds__(kFitThreads, 4)
 moffat_fit_group_kernel(FitBatch fb, int group, unsigned int* __restrict__ queue) {
