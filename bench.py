@@ -397,8 +397,16 @@ def run_b200_arm(a):
             dur = stage_ms[dominant]["ms_per_step"] * 1e-3
             launches_dom = max(1.0, stage_ms[dominant]["launches_per_step"])
             achieved = alg_bytes_per_col * F * nd / dur / 1e9
+            traffic = None                  # DRAM bytes per launch of that kernel from the committed ncu capture
+            try:
+                tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+                w = tj["workload"]
+                if (w["frames_per_gpu"], w["nspat"], w["ndisp"]) == (F, ns, nd):
+                    traffic = tj["dram_bytes_per_launch"].get(dominant)
+            except Exception:
+                pass
             roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                        "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                        "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                         "algorithmic_bytes_per_column": alg_bytes_per_col,
                         "kernel_ms_per_launch": 1e3 * dur / launches_dom,
                         "note": "whole-path algorithmic bytes (17*nspat+80 per column) over the dominant stage's "
