@@ -307,6 +307,26 @@ def run_b200_arm(a):
             stage_ms[name] = {"ms_per_step": buf[i] / a.profile_steps, "launches_per_step": cnt[i] / a.profile_steps}
     fence()
 
+    # ---- BASELINE.json configs[1] as stated: ONE 4096 x 400 frame on one B200 (latency of a single-frame call)
+    def single_step():
+        data[:1].copy_(data0[:1])
+        errs[:1].copy_(errs0[:1])
+        states[:1].copy_(states0[:1])
+        _lib.check(_lib.lib.motes_run_frames_dev(h.raw, data.data_ptr(), errs.data_ptr(), qual.data_ptr(), 1, ns, nd, cap,
+                                                 ctypes.byref(p), seeing.data_ptr(), pixres.data_ptr(),
+                                                 states.data_ptr(), ctypes.byref(ostruct)))
+    for _ in range(2):
+        single_step()
+    torch.cuda.synchronize(device)
+    sv0, sv1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sv0.record(stream)
+    for _ in range(5):
+        single_step()
+    sv1.record(stream)
+    torch.cuda.synchronize(device)
+    single_ms = sv0.elapsed_time(sv1) / 5.0
+    fence()
+
     # ---- end-to-end leg: pinned host buffers -> H2D -> path -> D2H of the spectra, through the host C ABI
     hd = torch.empty((F, ns, nd), dtype=torch.float64).pin_memory()
     he = torch.empty((F, ns, nd), dtype=torch.float64).pin_memory()
@@ -431,6 +451,8 @@ def run_b200_arm(a):
                     "one_call_at_a_time": {"value": e2e_sync_value, "steps": e2e_steps,
                                            "api": "motes_run_frames_host (H2D + path + D2H, then return)"}},
             "gpu_launches": int(launches),
+            "single_frame": {"ms": single_ms, "columns_per_s": nd / (single_ms * 1e-3),
+                             "note": "BASELINE.json configs[1] as stated: one 4096x400 frame per call on one GPU, device-resident"},
             "roofline": roofline,
             "stage_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in stage_ms.items()},
             "stage_share": {k: round(v["ms_per_step"] / total_stage, 4) for k, v in stage_ms.items()},

@@ -103,7 +103,7 @@ struct motes_handle {
     bool profiling = false;
     int fit_mode = 0;            // MOTES_B200_FIT: 0 batched persistent grid (default), 1 one warp per fit
     int column_window = 256;     // MOTES_B200_COLUMN: histogram window of the bootstrap column kernel (0 = exact slot kernel only)
-    int boot_mode = 0;           // MOTES_B200_BOOTSTRAP: 0 segmented (default), 1 classic (one CTA per frame), 2 warp-specialised
+    int boot_mode = 0;           // MOTES_B200_BOOTSTRAP: 0 segmented (default), 1 classic (one CTA per frame)
     motes::Scratch jump_polys;   // device copy of the MT19937 jump polynomial table (mtjump.hpp)
     bool jump_ready = false;
     size_t stream_budget = 0;    // bytes the segmented bootstrap may use for generator streams (0 = auto)

@@ -747,28 +747,6 @@ sky_bootstrap_kernel(uint32_t* __restrict__ rng /* [F][625]: 624 state words + p
                         rank_of + base * nspat, (size_t)nspat, sky + base, sky_err + base, sh);
 }
 
-// Warp-specialised order-0 bootstrap: 8 consumer warps + 2 generator warps per frame.
-__global__ void __launch_bounds__(kWsThreads)
-sky_bootstrap_ws_kernel(uint32_t* __restrict__ rng, int nspat, int ndisp, const int32_t* __restrict__ n_good,
-                        const int32_t* __restrict__ flag, const double* __restrict__ sorted,
-                        const uint16_t* __restrict__ rank_of, double* __restrict__ sky, double* __restrict__ sky_err,
-                        const FrameState* __restrict__ st) {
-    extern __shared__ __align__(16) unsigned char sb_smem[];
-    BootShared sh;
-    sh.meds = reinterpret_cast<double*>(sb_smem);
-    sh.sq = sh.meds + kBootstrap;
-    sh.ring = reinterpret_cast<uint32_t*>(sh.sq + kBootstrap);
-    sh.counts = sh.ring + kRing;
-    sh.ctl = reinterpret_cast<int*>(sh.counts + 64);
-    sh.hist = reinterpret_cast<uint32_t*>(sh.ctl + 4);
-    sh.ranks = reinterpret_cast<uint16_t*>(sh.hist + (size_t)kBootstrap * boot_row_words(nspat));
-    const int f = blockIdx.x;
-    if (st[f].status != 0) return;
-    const size_t base = (size_t)f * ndisp;
-    sky_bootstrap_frame_ws(rng + (size_t)f * 625, ndisp, n_good + base, flag + base, sorted + base * nspat,
-                           rank_of + base * nspat, (size_t)nspat, sky + base, sky_err + base, sh);
-}
-
 // Bootstrap polynomial sky (sky_order > 0): one CTA per frame, columns in order.
 __global__ void __launch_bounds__(kBootThreads)
 sky_bootstrap_poly_kernel(uint32_t* __restrict__ rng, int nspat, int ndisp, int order, int spatial_floor,

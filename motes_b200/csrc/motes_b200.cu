@@ -442,15 +442,9 @@ static int stage_sky(motes_handle* h, Batch& b, double* data, double* errs, size
             if (!done) {
                 StageTimer timer(h, ST_SKY_BOOTSTRAP);
                 smem = sky_boot_smem(b.nspat);
-                if (h->boot_mode != 2) {
-                    MOTES_CUDA(cudaFuncSetAttribute(sky_bootstrap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                    sky_bootstrap_kernel<<<b.F, kBootThreads, smem, h->stream>>>(rng, b.nspat, b.ndisp, b.n_good, b.sky_flag,
-                                                                                 b.sorted, b.rank_of, b.sky, b.sky_err, b.st);
-                } else {
-                    MOTES_CUDA(cudaFuncSetAttribute(sky_bootstrap_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                    sky_bootstrap_ws_kernel<<<b.F, kWsThreads, smem, h->stream>>>(rng, b.nspat, b.ndisp, b.n_good, b.sky_flag,
-                                                                                 b.sorted, b.rank_of, b.sky, b.sky_err, b.st);
-                }
+                MOTES_CUDA(cudaFuncSetAttribute(sky_bootstrap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                sky_bootstrap_kernel<<<b.F, kBootThreads, smem, h->stream>>>(rng, b.nspat, b.ndisp, b.n_good, b.sky_flag,
+                                                                             b.sorted, b.rank_of, b.sky, b.sky_err, b.st);
                 MOTES_LAUNCHED(h);
             }
         }
@@ -673,9 +667,9 @@ int motes_create(int device, motes_handle** out) {
     if (e != cudaSuccess) { delete h; return fail_cuda(e, "cudaGetDeviceProperties", __FILE__, __LINE__); }
     h->sm_count = prop.multiProcessorCount;
     h->smem_optin = prop.sharedMemPerBlockOptin;
-    // A/B switches: "classic" = one CTA walks a frame's whole stream, "ws" = its warp-specialised variant
+    // A/B and cross-check switch: "classic" = one CTA walks a frame's whole stream (the literal replay)
     const char* boot = getenv("MOTES_B200_BOOTSTRAP");
-    h->boot_mode = (boot && strcmp(boot, "classic") == 0) ? 1 : (boot && strcmp(boot, "ws") == 0) ? 2 : 0;
+    h->boot_mode = (boot && strcmp(boot, "classic") == 0) ? 1 : 0;
     const char* colw = getenv("MOTES_B200_COLUMN");
     if (colw) h->column_window = atoi(colw);
     const char* fitm = getenv("MOTES_B200_FIT");              // "warp": round-1 one-warp-per-fit kernel

@@ -450,273 +450,6 @@ MOTES_HD void sky_bootstrap_frame(const Scope& sc, uint32_t* state /* 625 words,
     sc.sync();
 }
 
-#if defined(__CUDACC__)
-// ---- 2a. warp-specialised variant of the order-0 bootstrap (device only) ---------------------
-// Same arithmetic as sky_bootstrap_frame, different choreography: 2 producer warps run the
-// MT19937 recurrence ahead of the consumers (one 227-word sweep per 64-thread named barrier) and
-// publish the generated count; 8 consumer warps test 4 outputs per thread per round, scan the
-// accepts and fill the rank slots, synchronising only among themselves.  The generator chain
-// (one barrier + shared-memory round trip per 227 words) thus overlaps with the acceptance scan
-// and with the per-column median search instead of alternating with them.
-constexpr int kWsConsumers = 256;
-constexpr int kWsProducers = 64;
-constexpr int kWsThreads = kWsConsumers + kWsProducers;
-
-__device__ __forceinline__ void named_barrier(int id, int count) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
-}
-__device__ __forceinline__ uint32_t ld_shared_volatile(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
-__device__ __forceinline__ void st_shared_volatile(uint32_t* p, uint32_t v) { *reinterpret_cast<volatile uint32_t*>(p) = v; }
-
-// sh.ctl[0]: boundary cursor, ctl[1]: gen published, ctl[2]: used published, ctl[3]: done
-__device__ void sky_bootstrap_frame_ws(uint32_t* state, int ncol, const int* n_good, const int* flag,
-                                       const double* sorted, const uint16_t* rank_of, size_t cs, double* sky,
-                                       double* sky_err, const BootShared& sh) {
-    const int tid = threadIdx.x;
-    uint32_t* ring = sh.ring;
-    uint32_t* gen_pub = reinterpret_cast<uint32_t*>(sh.ctl + 1);
-    uint32_t* used_pub = reinterpret_cast<uint32_t*>(sh.ctl + 2);
-    uint32_t* done_pub = reinterpret_cast<uint32_t*>(sh.ctl + 3);
-    for (int i = tid; i < kMtN; i += blockDim.x) ring[i] = state[i];
-    if (tid == 0) { *gen_pub = kMtN; *used_pub = state[kMtN]; *done_pub = 0; }
-    __syncthreads();
-    const uint32_t used0 = state[kMtN];
-    uint32_t used = used0;
-    unsigned long long used_total = used0;
-    uint32_t gen = kMtN;
-
-    if (tid >= kWsConsumers) {
-        // ------------------------------------------------------------------ producers
-        const int pt = tid - kWsConsumers;
-        while (true) {
-            // flow control (one thread polls, the group follows): keep 700 words of history behind
-            // the consumers -- the state export at the end needs the 624-word block around `used`
-            if (pt == 0) {
-                uint32_t stop = 0;
-                while (true) {
-                    if (ld_shared_volatile(done_pub)) { stop = 1; break; }
-                    const uint32_t u = ld_shared_volatile(used_pub);
-                    if ((uint32_t)(gen + kSweep - u) <= (uint32_t)(kRing - 700)) break;
-                    __nanosleep(40);
-                }
-                sh.counts[16] = stop;
-            }
-            named_barrier(2, kWsProducers);
-            if (sh.counts[16] != 0u) break;
-            for (int j = pt; j < kSweep; j += kWsProducers) {
-                const uint32_t w = gen + (uint32_t)j;
-                ring[w & (kRing - 1)] = mt_mix(ring[(w - kMtN) & (kRing - 1)], ring[(w - kMtN + 1) & (kRing - 1)],
-                                               ring[(w - kSweep) & (kRing - 1)]);
-            }
-            gen += (uint32_t)kSweep;
-            named_barrier(2, kWsProducers);
-            if (pt == 0) {
-                __threadfence_block();
-                st_shared_volatile(gen_pub, gen);
-            }
-        }
-    } else {
-        // ------------------------------------------------------------------ consumers
-        const int lane = tid & 31, warp = tid >> 5;
-        unsigned char* counts8 = reinterpret_cast<unsigned char*>(sh.counts);
-        const unsigned long long below_mask = (1ull << (8 * warp)) - 1ull;
-        int parity = 0;
-        for (int c = 0; c < ncol; ++c) {
-            if (flag[c] != kSkyModelled) {
-                if (tid == 0) { sky[c] = 0.0; sky_err[c] = 0.0; }
-                continue;
-            }
-            const int n = n_good[c];
-            const double* srt = sorted + (size_t)c * cs;
-            if (n == 0) {
-                if (tid == 0) { sky[c] = NAN; sky_err[c] = NAN; }
-                continue;
-            }
-            if (n > 1) {
-                const int rw = boot_row_words(n);
-                uint16_t* slots = reinterpret_cast<uint16_t*>(sh.hist);
-                for (int i = tid; i < n; i += kWsConsumers) sh.ranks[i] = rank_of[(size_t)c * cs + i];
-                named_barrier(1, kWsConsumers);
-                const int need = n * kBootstrap;
-                const uint32_t mask = rejection_mask((uint32_t)n);
-                const uint32_t top = (uint32_t)(n - 1);
-                const uint32_t used_at_start = used;
-                int have = 0;
-                while (have < need) {
-                    const uint32_t want = (uint32_t)(kSlabs * kWsConsumers);
-                    while ((uint32_t)(ld_shared_volatile(gen_pub) - used) < want) __nanosleep(20);
-                    __threadfence_block();
-                    int acc[kSlabs], off[kSlabs];
-                    uint32_t v[kSlabs];
-                    unsigned ballot[kSlabs];
-#pragma unroll
-                    for (int k = 0; k < kSlabs; ++k) {
-                        v[k] = mt_temper(ring[(used + (uint32_t)(k * kWsConsumers + tid)) & (kRing - 1)]) & mask;
-                        acc[k] = (v[k] <= top);
-                        ballot[k] = __ballot_sync(0xffffffffu, acc[k]);
-                        if (lane == 0) counts8[parity * 32 + k * 8 + warp] = (unsigned char)__popc(ballot[k]);
-                    }
-                    named_barrier(1, kWsConsumers);
-                    const uint4 c4 = *reinterpret_cast<const uint4*>(counts8 + parity * 32);
-                    const uint4 c5 = *reinterpret_cast<const uint4*>(counts8 + parity * 32 + 16);
-                    const unsigned lo_w[kSlabs] = {c4.x, c4.z, c5.x, c5.z}, hi_w[kSlabs] = {c4.y, c4.w, c5.y, c5.w};
-                    const unsigned lanes_below = (1u << lane) - 1u;
-                    int total = 0;
-#pragma unroll
-                    for (int k = 0; k < kSlabs; ++k) {
-                        const unsigned long long all = ((unsigned long long)hi_w[k] << 32) | lo_w[k];
-                        const unsigned long long low = all & below_mask;
-                        off[k] = total + (int)(__vsadu4((unsigned)low, 0u) + __vsadu4((unsigned)(low >> 32), 0u)) +
-                                 __popc(ballot[k] & lanes_below);
-                        total += (int)(__vsadu4(lo_w[k], 0u) + __vsadu4(hi_w[k], 0u));
-                    }
-                    parity ^= 1;
-                    int last_at = 0;
-#pragma unroll
-                    for (int k = 0; k < kSlabs; ++k) {
-                        const int ord = have + off[k];
-                        if (acc[k] && ord < need) {
-                            const int pix = ord / kBootstrap, smp = ord - pix * kBootstrap;
-                            slots[smp * (2 * rw) + pix] = sh.ranks[v[k]];
-                            if (ord == need - 1) last_at = k * kWsConsumers + tid + 1;
-                        }
-                    }
-                    if (have + total >= need) {
-                        if (last_at) sh.ctl[0] = last_at;
-                        named_barrier(1, kWsConsumers);
-                        used += (uint32_t)sh.ctl[0];
-                        have = need;
-                        named_barrier(1, kWsConsumers);
-                    } else {
-                        have += total;
-                        used += want;
-                    }
-                    if (tid == 0) st_shared_volatile(used_pub, used);
-                }
-                used_total += (unsigned long long)(used - used_at_start);
-                named_barrier(1, kWsConsumers);
-                // packed median search (n <= 512) or the generic counting loop
-                const int k1 = (n - 1) / 2, k2 = n / 2;
-                int nbits = 1;
-                while ((1 << nbits) < n) ++nbits;
-                const int nwords = (n + 1) >> 1;
-                for (int smp = warp; smp < kBootstrap; smp += kWsConsumers / 32) {
-                    int x1 = 0, x2;
-                    if (n <= 64 * kPackWords) {
-                        const uint32_t* row = sh.hist + smp * rw;
-                        uint32_t reg[kPackWords];
-#pragma unroll
-                        for (int t = 0; t < kPackWords; ++t) {
-                            const int wd = lane + 32 * t;
-                            uint32_t wv = 0x7fff7fffu;
-                            if (wd < nwords) {
-                                wv = row[wd];
-                                if (2 * wd + 1 >= n) wv = (wv & 0xffffu) | 0x7fff0000u;
-                            }
-                            reg[t] = wv;
-                        }
-                        const int slots_total = 64 * kPackWords;
-                        for (int bit = nbits - 1; bit >= 0; --bit) {
-                            const int cand = x1 | (1 << bit);
-                            const uint32_t kk = (uint32_t)(0x8000 - cand) * 0x00010001u;
-                            uint32_t ge = 0;
-#pragma unroll
-                            for (int t = 0; t < kPackWords; ++t) ge += ((reg[t] + kk) >> 15) & 0x00010001u;
-                            const int ge_all = __reduce_add_sync(0xffffffffu, (int)((ge & 0xffffu) + (ge >> 16)));
-                            if (slots_total - ge_all <= k1) x1 = cand;
-                        }
-                        x2 = x1;
-                        if (k2 != k1) {
-                            const uint32_t kk = (uint32_t)(0x8000 - (x1 + 1)) * 0x00010001u;
-                            uint32_t ge = 0;
-                            int nxt = 0x7fff;
-#pragma unroll
-                            for (int t = 0; t < kPackWords; ++t) {
-                                ge += ((reg[t] + kk) >> 15) & 0x00010001u;
-                                const int h0 = (int)(reg[t] & 0xffffu), h1 = (int)(reg[t] >> 16);
-                                if (h0 > x1 && h0 < nxt) nxt = h0;
-                                if (h1 > x1 && h1 < nxt) nxt = h1;
-                            }
-                            const int le = slots_total - __reduce_add_sync(0xffffffffu, (int)((ge & 0xffffu) + (ge >> 16)));
-                            nxt = __reduce_min_sync(0xffffffffu, nxt);
-                            if (le <= k2) x2 = nxt;
-                        }
-                    } else {
-                        const uint16_t* row = slots + smp * (2 * rw);
-                        for (int bit = nbits - 1; bit >= 0; --bit) {
-                            const int cand = x1 | (1 << bit);
-                            int cnt = 0;
-                            for (int j = lane; j < n; j += 32) cnt += ((int)row[j] < cand);
-                            cnt = __reduce_add_sync(0xffffffffu, cnt);
-                            if (cnt <= k1) x1 = cand;
-                        }
-                        x2 = x1;
-                        if (k2 != k1) {
-                            int le = 0, nxt = 0x7fffffff;
-                            for (int j = lane; j < n; j += 32) {
-                                const int r = (int)row[j];
-                                le += (r <= x1);
-                                if (r > x1 && r < nxt) nxt = r;
-                            }
-                            le = __reduce_add_sync(0xffffffffu, le);
-                            nxt = __reduce_min_sync(0xffffffffu, nxt);
-                            if (le <= k2) x2 = nxt;
-                        }
-                    }
-                    if (lane == 0) sh.meds[smp] = (k1 == k2) ? srt[x1] : (srt[x1] + srt[x2]) * 0.5;
-                }
-            } else {
-                for (int smp = tid; smp < kBootstrap; smp += kWsConsumers) sh.meds[smp] = srt[0];
-            }
-            named_barrier(1, kWsConsumers);
-            // np.nanmean / np.std in numpy's summation order; warp 0 computes, everybody waits
-            if (warp == 0) {
-                const WarpScope w0{lane};
-                struct Blk { int tid; __device__ int size() const { return 32; } } blk{lane};
-                double mean = numpy_sum100(blk, sh.meds) / (double)kBootstrap;
-                mean = __shfl_sync(0xffffffffu, mean, 0);
-                for (int smp = lane; smp < kBootstrap; smp += 32) { double d = sh.meds[smp] - mean; sh.sq[smp] = d * d; }
-                __syncwarp();
-                double var = numpy_sum100(blk, sh.sq) / (double)kBootstrap;
-                if (lane == 0) {
-                    sky[c] = mean;
-                    sky_err[c] = sqrt(var) / kSqrt99;
-                }
-                (void)w0;
-            }
-            named_barrier(1, kWsConsumers);
-        }
-        if (tid == 0) {
-            __threadfence_block();
-            st_shared_volatile(done_pub, 1u);
-        }
-    }
-    __syncthreads();
-    // every thread needs the consumers' final position
-    if (tid == 0) { sh.counts[17] = (uint32_t)(used_total & 0xffffffffu); sh.counts[18] = (uint32_t)(used_total >> 32); sh.counts[19] = used; }
-    __syncthreads();
-    used_total = ((unsigned long long)sh.counts[18] << 32) | sh.counts[17];
-    used = sh.counts[19];
-    gen = ld_shared_volatile(gen_pub);
-    __syncthreads();
-    const unsigned long long block = (used_total > 0) ? ((used_total - 1) / kMtN) * kMtN : 0;
-    const uint32_t into_block = (uint32_t)(used_total - block);
-    const uint32_t block32 = used - into_block;
-    while ((uint32_t)(gen - block32) < (uint32_t)kMtN) {
-        for (int j = tid; j < kSweep; j += blockDim.x) {
-            const uint32_t w = gen + (uint32_t)j;
-            ring[w & (kRing - 1)] = mt_mix(ring[(w - kMtN) & (kRing - 1)], ring[(w - kMtN + 1) & (kRing - 1)],
-                                           ring[(w - kSweep) & (kRing - 1)]);
-        }
-        gen += (uint32_t)kSweep;
-        __syncthreads();
-    }
-    __syncthreads();
-    for (int i = tid; i < kMtN; i += blockDim.x) state[i] = ring[(block32 + (uint32_t)i) & (kRing - 1)];
-    if (tid == 0) state[kMtN] = into_block;
-}
-#endif
-
 // ---- 2b. bootstrap polynomial sky (sky.sky_polynomial, sky.py:177-254) ------------------------
 // Per column: every good sky pixel j is replaced 100 times by N(pixel_j, err_j) drawn with numpy's
 // legacy polar Gaussian (np.random.normal: two 53-bit uniforms per attempt, accept 0 < r2 < 1,
