@@ -63,7 +63,10 @@ MOTES_HD ColumnStats column_stats(const double* data, const double* errs, int ns
 // Greedy centre-outward scan for one frame by one thread scope.
 //   qual      nspat x ndisp, 1 = good, 0 = bad (uint8)
 //   S, V      per-column sums from column_stats
-//   counts    scratch, nspat ints shared by the scope
+//   allgood   optional, per column: 1 when every row of the column has qual == 1.  Such a column adds one to
+//             every row's counter, which is kept as a common offset, so the scan touches the nspat counters
+//             (and reads a qual column, a stride-ndisp gather) only for columns with a bad pixel
+//   counts    scratch, nspat ints shared by the scope;  cell: one shared 64-bit word
 //   bins_i    out, [2*maxbins] first/last column of each bin, sorted by first
 //   bins_snr  out, [maxbins]
 //   tmp_i / tmp_snr  scratch of the same sizes (blue-ward bins are produced in reverse order)
@@ -71,7 +74,8 @@ MOTES_HD ColumnStats column_stats(const double* data, const double* errs, int ns
 template <class Scope>
 MOTES_HD int snr_bins_scan(const Scope& sc, const uint8_t* qual, const double* S, const double* V, int nspat,
                            int ndisp, double snr_limit, double min_cols, int* counts, int32_t* bins_i,
-                           double* bins_snr, int32_t* tmp_i, double* tmp_snr) {
+                           double* bins_snr, int32_t* tmp_i, double* tmp_snr, const uint8_t* allgood = nullptr,
+                           unsigned long long* cell = nullptr) {
     const int centre = ndisp / 2;
     int n_blue = 0, n_red = 0;
     for (int dir = 0; dir < 2; ++dir) {
@@ -80,6 +84,7 @@ MOTES_HD int snr_bins_scan(const Scope& sc, const uint8_t* qual, const double* S
             double snr = 0.0;
             Accum sum_s, sum_v;
             for (int r = sc.tid; r < nspat; r += sc.size()) counts[r] = 0;
+            int common = 0, least = 0;          // counter of row r = common + counts[r]; least = min over r of counts[r]
             sc.sync();
             while (snr <= snr_limit) {
                 width += 1;
@@ -88,15 +93,24 @@ MOTES_HD int snr_bins_scan(const Scope& sc, const uint8_t* qual, const double* S
                     break;
                 }
                 int col = (dir == 0) ? edge - width : edge + width - 1;
-                int is_short = 0;
-                for (int r = sc.tid; r < nspat; r += sc.size()) {
-                    int cnt = counts[r] + (int)qual[(size_t)r * ndisp + col];
-                    counts[r] = cnt;
-                    is_short |= ((double)cnt <= min_cols);
+                bool any_short;
+                if (allgood && allgood[col]) {
+                    common += 1;
+                    any_short = ((double)(common + least) <= min_cols);
+                } else {
+                    int is_short = 0, mine = 0x7fffffff;
+                    for (int r = sc.tid; r < nspat; r += sc.size()) {
+                        int cnt = counts[r] + (int)qual[(size_t)r * ndisp + col];
+                        counts[r] = cnt;
+                        mine = cnt < mine ? cnt : mine;
+                        is_short |= ((double)(common + cnt) <= min_cols);
+                    }
+                    if (allgood) least = (int)sc.umin((unsigned long long)(unsigned)mine, cell);
+                    any_short = sc.any(is_short) != 0;
                 }
                 sum_s.add(S[col]);
                 sum_v.add(V[col]);
-                if (sc.any(is_short)) continue;
+                if (any_short) continue;
                 snr = sum_s.value() / sqrt(sum_v.value());
             }
             if (sc.tid == 0) {

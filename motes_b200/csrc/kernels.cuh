@@ -122,18 +122,31 @@ column_stats_kernel(const double* __restrict__ data, const double* __restrict__ 
     gap[(size_t)f * ndisp + c] = cs.gap;
 }
 
+// per column: does every row carry qual == 1?  (thread per column, coalesced over the columns)
+__global__ void __launch_bounds__(128)
+qual_columns_kernel(const uint8_t* __restrict__ qual, size_t qual_stride, int nspat, int ndisp, uint8_t* __restrict__ allgood) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x, f = blockIdx.y;
+    if (c >= ndisp) return;
+    const uint8_t* q = qual + (size_t)f * qual_stride + c;
+    int good = 1;
+    for (int r = 0; r < nspat; ++r) good &= (q[(size_t)r * ndisp] == 1);
+    allgood[(size_t)f * ndisp + c] = (uint8_t)good;
+}
+
 // a5: greedy S/N binning, one CTA per frame (tracing.py:114-254).
 __global__ void __launch_bounds__(1024)
-bins_kernel(const uint8_t* __restrict__ qual, size_t qual_stride, const double* __restrict__ S,
+bins_kernel(const uint8_t* __restrict__ qual, size_t qual_stride, const uint8_t* __restrict__ allgood, const double* __restrict__ S,
             const double* __restrict__ V, int nspat, int ndisp, double snr_limit, double min_cols, int cap,
             int32_t* __restrict__ bins_i /* [F][2*cap] */, double* __restrict__ bins_snr /* [F][cap] */,
             int32_t* __restrict__ tmp_i, double* __restrict__ tmp_snr, int32_t* __restrict__ nbins) {
     extern __shared__ __align__(16) int bins_counts[];
+    __shared__ unsigned long long cell;
     BlockScope sc{(int)threadIdx.x};
     const int f = blockIdx.x;
     int nb = snr_bins_scan(sc, qual + (size_t)f * qual_stride, S + (size_t)f * ndisp, V + (size_t)f * ndisp, nspat,
                            ndisp, snr_limit, min_cols, bins_counts, bins_i + (size_t)f * 2 * cap,
-                           bins_snr + (size_t)f * cap, tmp_i + (size_t)f * 2 * cap, tmp_snr + (size_t)f * cap);
+                           bins_snr + (size_t)f * cap, tmp_i + (size_t)f * 2 * cap, tmp_snr + (size_t)f * cap,
+                           allgood + (size_t)f * ndisp, &cell);
     if (threadIdx.x == 0) nbins[f] = nb;
 }
 

@@ -18,6 +18,7 @@ struct Batch {
     double *medprof, *fit0_params, *S, *V;
     int32_t* fit0_status;
     uint8_t* gap;
+    uint8_t* allgood;           // per column: every row has qual == 1
     // two bin sets: [0] sky localisation, [1] extraction
     int32_t* bins_i[2];
     double* bins_snr[2];
@@ -99,8 +100,9 @@ static int make_batch(motes_handle* h, Batch& b, int F, int nspat, int ndisp, in
     carve_f64(b, h->work[W_F64].ptr);
     MOTES_TRY(h->work[W_I32].ensure(carve_i32(b, nullptr)));
     carve_i32(b, h->work[W_I32].ptr);
-    MOTES_TRY(h->work[W_U8].ensure((size_t)F * ndisp + 256));
+    MOTES_TRY(h->work[W_U8].ensure((size_t)2 * F * ndisp + 512));
     b.gap = h->work[W_U8].as<uint8_t>();
+    b.allgood = b.gap + (((size_t)F * ndisp + 255) & ~(size_t)255);
     MOTES_TRY(h->work[W_PROFILES].ensure((size_t)F * cap * nspat * sizeof(double)));
     b.profiles = h->work[W_PROFILES].as<double>();
     if (need_sky) {
@@ -229,7 +231,9 @@ static int stage_bins(motes_handle* h, Batch& b, const uint8_t* qual, size_t qua
     int threads = ((b.nspat + 31) / 32) * 32;
     if (threads > 1024) threads = 1024;
     size_t smem = (size_t)b.nspat * sizeof(int);
-    bins_kernel<<<b.F, threads, smem, h->stream>>>(qual, qual_stride, b.S, b.V, b.nspat, b.ndisp, snr_limit, min_cols,
+    qual_columns_kernel<<<dim3((b.ndisp + 127) / 128, b.F), 128, 0, h->stream>>>(qual, qual_stride, b.nspat, b.ndisp, b.allgood);
+    MOTES_LAUNCHED(h);
+    bins_kernel<<<b.F, threads, smem, h->stream>>>(qual, qual_stride, b.allgood, b.S, b.V, b.nspat, b.ndisp, snr_limit, min_cols,
                                                    b.cap, b.bins_i[set], b.bins_snr[set], b.tmp_i, b.tmp_snr,
                                                    b.nbins[set]);
     MOTES_LAUNCHED(h);

@@ -55,9 +55,17 @@ extern "C" int hostsim_snr_bins(const double* data, const double* errs, const ui
         V[c] = st.sum_var;
         gap[c] = st.gap;
     }
+    // the per-column "every row is good" flags the GPU path computes in qual_columns_kernel
+    std::vector<uint8_t> allgood(ndisp);
+    for (int c = 0; c < ndisp; ++c) {
+        int good = 1;
+        for (int r = 0; r < nspat; ++r) good &= (qual[(size_t)r * ndisp + c] == 1);
+        allgood[c] = (uint8_t)good;
+    }
+    unsigned long long cell = 0;
     motes::SeqScope sc;
     return motes::snr_bins_scan(sc, qual, S.data(), V.data(), nspat, ndisp, snr_limit, min_cols, counts.data(),
-                                bins_i, bins_snr, tmp_i.data(), tmp_snr.data());
+                                bins_i, bins_snr, tmp_i.data(), tmp_snr.data(), allgood.data(), &cell);
 }
 
 extern "C" int hostsim_interp_limits(const double* table, int nb, int ndisp, double* out_lo, double* out_hi) {
