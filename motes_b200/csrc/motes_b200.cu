@@ -381,9 +381,10 @@ static int stage_bootstrap_segmented(motes_handle* h, Batch& b, uint32_t* rng, b
         StageTimer t_jump(h, ST_BOOT_JUMP);
         seg_plan_kernel<<<nf, 256, 0, h->stream>>>(rng_w, b.ndisp, b.n_good + c0, b.sky_flag + c0, lay, seg_need);
         MOTES_LAUNCHED(h);
+        MOTES_CUDA(cudaMemsetAsync(windows, 0, (size_t)nf * lay.segs * 624 * sizeof(uint32_t), h->stream));
         for (int r = 0; (1 << r) < lay.segs; ++r) {
             const int count = ((1 << (r + 1)) <= lay.segs ? (1 << r) : lay.segs - (1 << r));
-            mt_jump_kernel<<<dim3(count, nf), kJumpThreads, jump_smem, h->stream>>>(
+            mt_jump_kernel<<<dim3(count, nf, kJumpParts), kJumpThreads, jump_smem, h->stream>>>(
                 rng_w, windows, lay.segs, r, polys + (size_t)(s + r) * kJumpWords32, seg_need);
             MOTES_LAUNCHED(h);
         }

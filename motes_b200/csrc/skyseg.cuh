@@ -76,6 +76,8 @@ seg_plan_kernel(const uint32_t* __restrict__ rng, int ndisp, const int32_t* __re
 // ---- jump -------------------------------------------------------------------------------------
 // window(dst) = XOR over set coefficients c_i of the words [i, i + 624) of the stream that starts
 // at window(src).  Word 0 of a jumped window carries only its top bit (all the recurrence reads).
+constexpr int kJumpParts = 4;        // CTAs sharing one jump: each XORs the windows of a quarter of the coefficient words
+
 __global__ void __launch_bounds__(kJumpThreads)
 mt_jump_kernel(const uint32_t* __restrict__ rng, uint32_t* __restrict__ windows, int segs, int round_log2,
                const uint32_t* __restrict__ poly, const int32_t* __restrict__ seg_need) {
@@ -89,15 +91,19 @@ mt_jump_kernel(const uint32_t* __restrict__ rng, uint32_t* __restrict__ windows,
     const uint32_t* from = (src == 0) ? rng + (size_t)f * 625 : windows + ((size_t)f * segs + src) * 624;
     for (int i = threadIdx.x; i < 624; i += blockDim.x) { w[i] = from[i]; coef[i] = poly[i]; }
     __syncthreads();
-    for (int base = 624; base < 19937 + 624; base += kSweep) {
+    // this CTA's share of the coefficient words; the stream is only needed up to its last window
+    const int part = blockIdx.z, per = 624 / kJumpParts;
+    const int iw0 = part * per, iw1 = iw0 + per;
+    const int last_word = min(19937 + 624, 32 * iw1 + 624);
+    for (int base = 624; base < last_word; base += kSweep) {
         const int n = base + (int)threadIdx.x;
-        if ((int)threadIdx.x < kSweep && n < 19937 + 624) w[n] = mt_mix(w[n - 624], w[n - 623], w[n - kSweep]);
+        if ((int)threadIdx.x < kSweep && n < last_word) w[n] = mt_mix(w[n - 624], w[n - 623], w[n - kSweep]);
         __syncthreads();
     }
     const int j = threadIdx.x;
     if (j < 624) {
         uint32_t acc = 0;
-        for (int iw = 0; iw < 624; ++iw) {
+        for (int iw = iw0; iw < iw1; ++iw) {
             uint32_t cw = coef[iw];
             const uint32_t* row = w + 32 * iw + j;
             while (cw) {                               // uniform across the CTA
@@ -106,7 +112,7 @@ mt_jump_kernel(const uint32_t* __restrict__ rng, uint32_t* __restrict__ windows,
                 acc ^= row[b];
             }
         }
-        windows[((size_t)f * segs + k) * 624 + j] = acc;
+        atomicXor(&windows[((size_t)f * segs + k) * 624 + j], acc);       // the window was zeroed before the round
     }
 }
 
@@ -130,6 +136,26 @@ __device__ __forceinline__ int stream_ring_slot(uint32_t p, uint32_t gen0) {
     return (row % kRingRows) * kRowWords + col;
 }
 
+// The recurrence and the tempering written with three-input logic ops (lop3) so that each step is one shift and
+// one logic instruction: the generator kernel is integer-issue bound (ncu: 72 % of the issue slots).
+template <int LUT>
+__device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(d) : "r"(a), "r"(b), "r"(c), "n"(LUT));
+    return d;
+}
+__device__ __forceinline__ uint32_t mt_mix_fast(uint32_t a, uint32_t b, uint32_t far) {
+    const uint32_t y = lop3<0xE4>(b, a, 0x7fffffffu);                 // (b & 0x7fffffff) | (a & 0x80000000)
+    const uint32_t mag = (uint32_t)(-(int32_t)(b & 1u)) & 0x9908b0dfu;  // y & 1 == b & 1
+    return lop3<0x96>(far, y >> 1, mag);                               // far ^ (y >> 1) ^ mag
+}
+__device__ __forceinline__ uint32_t mt_temper_fast(uint32_t y) {
+    y ^= y >> 11;
+    y = lop3<0x78>(y, y << 7, 0x9d2c5680u);                            // y ^ ((y << 7) & B)
+    y = lop3<0x78>(y, y << 15, 0xefc60000u);                           // y ^ ((y << 15) & C)
+    return y ^ (y >> 18);
+}
+
 template <int U>
 __device__ __forceinline__ void stream_round(uint32_t& far, const uint32_t* pa0, const uint32_t* pa0w, const uint32_t* pa1,
                                              const uint32_t* pa1w, const uint32_t* pb, const uint32_t* pbw, uint32_t* pw,
@@ -139,13 +165,13 @@ __device__ __forceinline__ void stream_round(uint32_t& far, const uint32_t* pa0,
     const uint32_t a1 = (U == kRingRows - 1) ? pa1w[U * kRowWords] : pa1[U * kRowWords];
     const uint32_t* b = (U == kRingRows - 1) ? pbw : pb;
     const uint32_t b0 = b[U * kRowWords], b1 = b[U * kRowWords + 1];
-    const uint32_t v0 = mt_mix(a0, a1, far);
-    const uint32_t v1 = mt_mix(b0, b1, v0);
+    const uint32_t v0 = mt_mix_fast(a0, a1, far);
+    const uint32_t v1 = mt_mix_fast(b0, b1, v0);
     uint32_t* w = (U >= kRingRows - 2) ? pww : pw;
     w[U * kRowWords] = v0;
     w[U * kRowWords + kSweep] = v1;
-    out_t[U * kRowWords] = (uint16_t)mt_temper(v0);
-    out_t[U * kRowWords + kSweep] = (uint16_t)mt_temper(v1);
+    out_t[U * kRowWords] = (uint16_t)mt_temper_fast(v0);
+    out_t[U * kRowWords + kSweep] = (uint16_t)mt_temper_fast(v1);
     far = v1;
 }
 
