@@ -398,7 +398,7 @@ moffat_fit_group_kernel(FitBatch fb, int group, unsigned int* __restrict__ queue
             const size_t idx = (size_t)f * fb.cap + slot;
             const double alpha0 = fit_frame_scalar(fb.alpha0, fb.alpha0_frame_stride, f, idx);
             const double scale = fb.scale ? fit_frame_scalar(fb.scale, fb.scale_frame_stride, f, 0) : 1.0;
-            fit_start(m, fb.profiles + idx * m, scale, alpha0, &states[j]);     // every lane writes the same values
+            fit_start_warp(lane, m, fb.profiles + idx * m, scale, alpha0, &states[j]);
         }
         __syncthreads();
         while (true) {

@@ -95,6 +95,79 @@ MOTES_HD void fit_start(int m, const double* profile, double scale, double alpha
     push_inside(st->x, lb, ub, 1e-10);
 }
 
+#if defined(__CUDACC__)
+// The same start point with the profile scan spread over a warp (the serial scan above is 400 dependent global
+// loads per fit): every lane scans its stride, the (largest, second largest) pairs, the first index of the
+// maximum, the first NaN and the NaN count are merged by shuffles.  Identical results: a multiset's two largest
+// values and np.argmax's "first occurrence" do not depend on the scan order.
+__device__ __forceinline__ void fit_start_warp(int lane, int m, const double* __restrict__ profile, double scale,
+                                               double alpha0, FitState* st) {
+    using namespace trf_detail;
+    constexpr int n = kParams;
+    double top1 = -INFINITY, top2 = -INFINITY;
+    int peak = 0x7fffffff, first_nan = 0x7fffffff, n_nan = 0;
+    for (int i = lane; i < m; i += 32) {
+        const double val = profile[i] * scale;
+        if (val != val) { ++n_nan; first_nan = min(first_nan, i); continue; }
+        if (val > top1) { top2 = top1; top1 = val; peak = i; }
+        else if (val > top2) top2 = val;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double o1 = __shfl_xor_sync(0xffffffffu, top1, o), o2 = __shfl_xor_sync(0xffffffffu, top2, o);
+        const int op = __shfl_xor_sync(0xffffffffu, peak, o);
+        n_nan += __shfl_xor_sync(0xffffffffu, n_nan, o);
+        first_nan = min(first_nan, __shfl_xor_sync(0xffffffffu, first_nan, o));
+        const double hi = fmax(top1, o1), lo = fmin(top1, o1);
+        // first occurrence of the maximum: the smaller index among equal maxima
+        peak = (o1 > top1) ? op : (o1 == top1 ? min(peak, op) : peak);
+        top2 = fmax(lo, fmax(top2, o2));
+        top1 = hi;
+    }
+    if (n_nan > 0) peak = first_nan;                              // np.argmax returns the first NaN
+    if (peak == 0x7fffffff) peak = 0;
+    double amp0;
+    if (m - n_nan >= 3 && n_nan == 0) amp0 = top2;
+    else if (n_nan == 1 && m >= 3) amp0 = (top2 + top1) * 0.5;
+    else if (n_nan == 2 && m >= 3) amp0 = top1;
+    else amp0 = (m >= 3) ? NAN : top1;
+    double ends[10];
+    int n_ends = 0;
+    for (int i = 0; i < 5 && i < m; ++i) ends[n_ends++] = profile[i] * scale;
+    for (int i = (m > 5 ? m - 5 : 0); i < m; ++i) ends[n_ends++] = profile[i] * scale;
+    bool ends_nan = false;
+    for (int i = 1; i < n_ends; ++i) {
+        double key = ends[i];
+        int j = i - 1;
+        while (j >= 0 && ends[j] > key) { ends[j + 1] = ends[j]; --j; }
+        ends[j + 1] = key;
+    }
+    for (int i = 0; i < n_ends; ++i) ends_nan = ends_nan || (ends[i] != ends[i]);
+    double level0 = (n_ends % 2) ? ends[n_ends / 2] : (ends[n_ends / 2 - 1] + ends[n_ends / 2]) * 0.5;
+    if (ends_nan) level0 = NAN;
+    if (lane != 0) return;
+    const double x0[n] = {amp0, (double)peak, alpha0, kBetaStart, level0, 0.0};
+    const double lb[n] = {0.0, (double)peak - 1.0, 0.0, 0.0, -INFINITY, -INFINITY};
+    const double ub[n] = {INFINITY, (double)peak + 1.0, 5.0 * alpha0, 5.0, INFINITY, INFINITY};
+    for (int i = 0; i < n; ++i) { st->x[i] = x0[i]; st->lb[i] = lb[i]; st->ub[i] = ub[i]; st->x_new[i] = x0[i]; st->g[i] = 0.0; }
+    st->cost = NAN;
+    st->radius = 0.0;
+    st->alpha = 0.0;
+    st->predicted = 0.0;
+    st->step_h_norm = 0.0;
+    st->step_norm = 0.0;
+    st->x_norm = 0.0;
+    st->nfev = 0;
+    st->njev = 0;
+    st->first = 1;
+    st->status = kStatusRunning;
+    for (int i = 0; i < n; ++i)
+        if (!(lb[i] < ub[i])) { st->status = kFitBadBounds; return; }
+    if (!inside(st->x, lb, ub)) { st->status = kFitX0Infeasible; return; }
+    push_inside(st->x, lb, ub, 1e-10);
+}
+#endif
+
 // ---- sweeps -----------------------------------------------------------------------------------
 template <class Ctx>
 MOTES_HD bool residual_sweep_b(const Ctx& ctx, int m, const double* profile, double scale, const double* xe,
