@@ -102,7 +102,7 @@ struct motes_handle {
     int chunks = 0;              // MOTES_B200_CHUNKS: sub-batches per call (0 = auto)
     bool profiling = false;
     int fit_mode = 0;            // MOTES_B200_FIT: 0 batched persistent grid (default), 1 one warp per fit
-    int column_window = 256;     // MOTES_B200_COLUMN: histogram window of the bootstrap column kernel (0 = exact slot kernel only)
+    int column_window = -1;      // MOTES_B200_COLUMN: histogram window of the bootstrap column kernel (-1 = auto, 0 = exact slot kernel only)
     int boot_mode = 0;           // MOTES_B200_BOOTSTRAP: 0 segmented (default), 1 classic (one CTA per frame)
     motes::Scratch jump_polys;   // device copy of the MT19937 jump polynomial table (mtjump.hpp)
     bool jump_ready = false;

@@ -300,8 +300,9 @@ static size_t sky_poly_smem(int nspat) {
 static size_t sky_col_smem(int nspat) {
     return (size_t)2 * kBootstrap * 8 + (size_t)kBootstrap * boot_row_words(nspat) * 4 + (size_t)nspat * 2 + 64;
 }
-static size_t sky_colh_smem(int nspat) {
-    return (size_t)2 * kBootstrap * 8 + (size_t)(kBootstrap * kHistStride) * 4 + (size_t)nspat * 2 + 64;
+static size_t sky_colh_smem(int nspat, bool packed) {
+    const int stride = packed ? HistLayout<true>::kStride : HistLayout<false>::kStride;
+    return (size_t)2 * kBootstrap * 8 + (size_t)(kBootstrap * stride) * 4 + (size_t)nspat * 2 + 64;
 }
 
 static int stage_bootstrap_segmented(motes_handle* h, Batch& b, uint32_t* rng, bool* done) {
@@ -364,9 +365,13 @@ static int stage_bootstrap_segmented(motes_handle* h, Batch& b, uint32_t* rng, b
     uint32_t* col_end = col_start + (size_t)wave * b.ndisp;
     uint32_t* retry_list = col_end + (size_t)wave * b.ndisp;          // columns the histogram kernel hands to the exact one
     uint32_t* retry_count = retry_list + (size_t)wave * b.ndisp;
-    const int col_mode = h->column_window;      // 0: exact kernel only; else the histogram window
-    const size_t colh_smem = sky_colh_smem(b.nspat);
-    MOTES_CUDA(cudaFuncSetAttribute(sky_column_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)colh_smem));
+    const int col_mode = h->column_window;      // 0: exact kernel only; < 0: the layout's whole window; else that window
+    // n <= nspat <= 400: the median rank of a bootstrap sample stays within 64 (6.4 sigma) of n / 2 -> plain 32-bit
+    // bins over a window of 128 ranks; wider frames: packed 8-bit bins over 256 ranks
+    const bool packed = b.nspat > 400 || col_mode > HistLayout<false>::kBins;
+    const size_t colh_smem = sky_colh_smem(b.nspat, packed);
+    auto hist_kernel = packed ? sky_column_hist_kernel<true> : sky_column_hist_kernel<false>;
+    MOTES_CUDA(cudaFuncSetAttribute(hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)colh_smem));
     const uint32_t* polys = h->jump_polys.as<uint32_t>();
     const size_t jump_smem = (size_t)(kJumpStreamWords + 624) * sizeof(uint32_t);
     MOTES_CUDA(cudaFuncSetAttribute(mt_jump_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jump_smem));
@@ -399,10 +404,11 @@ static int stage_bootstrap_segmented(motes_handle* h, Batch& b, uint32_t* rng, b
         MOTES_LAUNCHED(h);
         t_walk.stop();
         StageTimer t_col(h, ST_BOOT_COLUMN);
-        if (col_mode > 0) {
-            const int window = col_mode > 4 * kHistWords ? 4 * kHistWords : col_mode;
+        if (col_mode != 0) {
+            const int bins = packed ? HistLayout<true>::kBins : HistLayout<false>::kBins;
+            const int window = (col_mode < 0 || col_mode > bins) ? bins : col_mode;
             MOTES_CUDA(cudaMemsetAsync(retry_count, 0, sizeof(uint32_t), h->stream));
-            sky_column_hist_kernel<<<dim3(b.ndisp, nf), kColThreads, colh_smem, h->stream>>>(
+            hist_kernel<<<dim3(b.ndisp, nf), kColThreads, colh_smem, h->stream>>>(
                 stream, lay, b.nspat, b.ndisp, window, b.n_good + c0, b.sky_flag + c0, b.sorted + c0 * b.nspat,
                 b.rank_of + c0 * b.nspat, col_start, col_end, subs, b.sky + c0, b.sky_err + c0, b.st + f0, 0u, retry_list,
                 retry_count);

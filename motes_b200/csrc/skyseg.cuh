@@ -773,9 +773,18 @@ sky_column_kernel(const uint16_t* __restrict__ stream, SegLayout lay, int nspat,
 // window around n / 2 plus the number of draws below and above it; its median is read off a prefix sum.
 // A sample whose median falls outside the window (or a count that does not add up to n: a histogram byte
 // overflowed) sends the column to the exact kernel above through `list`.
-constexpr int kHistWords = 64;                      // 256 one-byte bins per sample
-constexpr int kHistStride = kHistWords + 3;         // + draws below / above the window, + 1 word of bank skew
+//
+// Two layouts of a sample's row: PACKED - 64 words of four 8-bit bins (a window of 256 ranks, for n up to ~1500);
+// plain - 128 words of one 32-bit bin each (a window of 128 ranks, enough for n <= 400: 6.4 sigma), where a draw
+// is an atomic add of the constant 1 at a table-supplied word and costs a third fewer instructions.
+template <bool PACKED>
+struct HistLayout {
+    static constexpr int kWords = PACKED ? 64 : 128;
+    static constexpr int kBins = PACKED ? 256 : 128;
+    static constexpr int kStride = kWords + 3;      // + draws below / above the window, + 1 word of bank skew
+};
 
+template <bool PACKED>
 __global__ void __launch_bounds__(kColThreads, 3)
 sky_column_hist_kernel(const uint16_t* __restrict__ stream, SegLayout lay, int nspat, int ndisp, int window,
                        const int32_t* __restrict__ n_good, const int32_t* __restrict__ flag,
@@ -784,6 +793,7 @@ sky_column_hist_kernel(const uint16_t* __restrict__ stream, SegLayout lay, int n
                        const uint32_t* __restrict__ sub_have, double* __restrict__ sky, double* __restrict__ sky_err,
                        const FrameState* __restrict__ st, uint32_t frame0, uint32_t* __restrict__ list,
                        uint32_t* __restrict__ list_count) {
+    constexpr int kHistWords = HistLayout<PACKED>::kWords, kHistStride = HistLayout<PACKED>::kStride;
     extern __shared__ __align__(16) unsigned char colh_smem[];
     double* meds = reinterpret_cast<double*>(colh_smem);
     double* sq = meds + kBootstrap;
@@ -814,7 +824,8 @@ sky_column_hist_kernel(const uint16_t* __restrict__ stream, SegLayout lay, int n
         for (int i = tid; i < n; i += kColThreads) {
             const int r = (int)rank_of[col * nspat + i] - lo;
             const bool in = (unsigned)r < (unsigned)window;
-            entry[i] = in ? (uint16_t)((r >> 2) | ((8 * (r & 3)) << 8)) : (uint16_t)(r < 0 ? kHistWords : kHistWords + 1);
+            if (PACKED) entry[i] = in ? (uint16_t)((r >> 2) | ((8 * (r & 3)) << 8)) : (uint16_t)(r < 0 ? kHistWords : kHistWords + 1);
+            else entry[i] = in ? (uint16_t)r : (uint16_t)(r < 0 ? kHistWords : kHistWords + 1);
         }
         if (tid == 0) failed = 0;
         __syncthreads();
@@ -826,7 +837,8 @@ sky_column_hist_kernel(const uint16_t* __restrict__ stream, SegLayout lay, int n
                          for (int e = 0; e < 4; ++e) {
                              if (m4 & (1u << e)) {
                                  const uint32_t en = entry[v[e]];
-                                 atomicAdd(row + (en & 0xffu), 1u << (en >> 8));      // one shared-memory atomic per draw
+                                 if (PACKED) atomicAdd(row + (en & 0xffu), 1u << (en >> 8));      // one shared-memory atomic per draw
+                                 else atomicAdd(row + en, 1u);
                                  row += kHistStride;
                                  if (++smp == kBootstrap) { smp = 0; row = hist; }
                              }
@@ -836,8 +848,20 @@ sky_column_hist_kernel(const uint16_t* __restrict__ stream, SegLayout lay, int n
         const int k1 = (n - 1) / 2, k2 = n / 2;
         for (int smp = warp; smp < kBootstrap; smp += nwarps) {
             const uint32_t* row = hist + smp * kHistStride;
-            const uint32_t w0 = row[2 * lane], w1 = row[2 * lane + 1];
-            const int mine = (int)(__vsadu4(w0, 0u) + __vsadu4(w1, 0u));          // draws in this lane's 8 bins
+            // this lane's share of the window: 8 bins (two packed words) or 4 bins (four plain words)
+            constexpr int kLaneBins = HistLayout<PACKED>::kBins / 32;
+            uint32_t cntb[kLaneBins];
+            if (PACKED) {
+                const uint32_t w0 = row[2 * lane], w1 = row[2 * lane + 1];
+#pragma unroll
+                for (int bin = 0; bin < kLaneBins; ++bin) cntb[bin] = ((bin < 4 ? w0 : w1) >> (8 * (bin & 3))) & 0xffu;
+            } else {
+#pragma unroll
+                for (int bin = 0; bin < kLaneBins; ++bin) cntb[bin] = row[kLaneBins * lane + bin];
+            }
+            int mine = 0;
+#pragma unroll
+            for (int bin = 0; bin < kLaneBins; ++bin) mine += (int)cntb[bin];
             int incl = mine;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -857,10 +881,10 @@ sky_column_hist_kernel(const uint16_t* __restrict__ stream, SegLayout lay, int n
             if ((t1 >= excl && t1 < incl) || (t2 >= excl && t2 < incl)) {
                 int seen = excl;
 #pragma unroll
-                for (int bin = 0; bin < 8; ++bin) {
-                    const int cnt = (int)(((bin < 4 ? w0 : w1) >> (8 * (bin & 3))) & 0xffu);
-                    if (t1 >= seen && t1 < seen + cnt) x1 = lo + 8 * lane + bin;
-                    if (t2 >= seen && t2 < seen + cnt) x2 = lo + 8 * lane + bin;
+                for (int bin = 0; bin < kLaneBins; ++bin) {
+                    const int cnt = (int)cntb[bin];
+                    if (t1 >= seen && t1 < seen + cnt) x1 = lo + kLaneBins * lane + bin;
+                    if (t2 >= seen && t2 < seen + cnt) x2 = lo + kLaneBins * lane + bin;
                     seen += cnt;
                 }
             }
