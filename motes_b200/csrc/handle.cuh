@@ -52,7 +52,9 @@ struct Scratch {
             ptr = nullptr;
             bytes = 0;
         }
-        size_t want = need + need / 4 + 256;
+        size_t slack = need / 4;                      // room to grow without reallocating - but not on multi-GB buffers
+        if (slack > ((size_t)64 << 20)) slack = (size_t)64 << 20;
+        size_t want = need + slack + 256;
         cudaError_t e = cudaMalloc(&ptr, want);
         if (e != cudaSuccess) {
             ptr = nullptr;

@@ -327,22 +327,6 @@ static int stage_bootstrap_segmented(motes_handle* h, Batch& b, uint32_t* rng, b
     int wave = (int)(budget / per_frame_est);
     if (wave < 1) return MOTES_OK;
     if (wave > b.F) wave = b.F;
-    const int waves = (b.F + wave - 1) / wave;
-    wave = (b.F + waves - 1) / waves;
-    // segment stride: enough CTAs to fill the machine, not more jumps than needed
-    SegLayout lay{};
-    const long long target = 8ll * h->sm_count;
-    int s = kSnapLog2;
-    while (s < 30 && (long long)wave * (long long)((bound + (1ull << s) - 1) >> s) > target) ++s;
-    lay.log2_stride = s;
-    lay.stride = 1u << s;
-    lay.segs = (int)((bound + lay.stride - 1) >> s);
-    const unsigned long long words = (unsigned long long)lay.segs << s;
-    lay.stream_len = words + 3ull * kWalkChunk;
-    lay.sub_len = (words >> kSubLog2) + 16;
-    lay.snaps = (int)(words >> kSnapLog2) + 1;
-    if (s + 10 > kJumpMaxLog2) return MOTES_OK;
-
     if (!h->jump_ready) {
         MOTES_TRY(h->jump_polys.ensure(table.words.size() * sizeof(uint32_t)));
         MOTES_CUDA(cudaMemcpyAsync(h->jump_polys.ptr, table.words.data(), table.words.size() * sizeof(uint32_t),
@@ -350,11 +334,36 @@ static int stage_bootstrap_segmented(motes_handle* h, Batch& b, uint32_t* rng, b
         MOTES_CUDA(cudaStreamSynchronize(h->stream));
         h->jump_ready = true;
     }
-    MOTES_TRY(h->work[W_STREAM].ensure((size_t)wave * lay.stream_len * sizeof(uint16_t)));
-    MOTES_TRY(h->work[W_WINDOWS].ensure((size_t)wave * lay.segs * 624 * sizeof(uint32_t)));
-    MOTES_TRY(h->work[W_SNAPS].ensure((size_t)wave * lay.snaps * 624 * sizeof(uint32_t)));
-    MOTES_TRY(h->work[W_SUBS].ensure((size_t)wave * lay.sub_len * sizeof(uint32_t)));
-    MOTES_TRY(h->work[W_SEGI].ensure(((size_t)wave * 2 + (size_t)wave * b.ndisp * 3 + 64) * sizeof(uint32_t) + 256));
+    SegLayout lay{};
+    int s = kSnapLog2;
+    while (true) {
+        const int waves = (b.F + wave - 1) / wave;
+        wave = (b.F + waves - 1) / waves;
+        // segment stride: enough CTAs to fill the machine, not more jumps than needed
+        const long long target = 8ll * h->sm_count;
+        s = kSnapLog2;
+        while (s < 30 && (long long)wave * (long long)((bound + (1ull << s) - 1) >> s) > target) ++s;
+        if (s + 10 > kJumpMaxLog2) return MOTES_OK;
+        lay.log2_stride = s;
+        lay.stride = 1u << s;
+        lay.segs = (int)((bound + lay.stride - 1) >> s);
+        const unsigned long long words = (unsigned long long)lay.segs << s;
+        lay.stream_len = words + 3ull * kWalkChunk;
+        lay.sub_len = (words >> kSubLog2) + 16;
+        lay.snaps = (int)(words >> kSnapLog2) + 1;
+        int rc = h->work[W_STREAM].ensure((size_t)wave * lay.stream_len * sizeof(uint16_t));
+        if (rc == MOTES_OK) rc = h->work[W_WINDOWS].ensure((size_t)wave * lay.segs * 624 * sizeof(uint32_t));
+        if (rc == MOTES_OK) rc = h->work[W_SNAPS].ensure((size_t)wave * lay.snaps * 624 * sizeof(uint32_t));
+        if (rc == MOTES_OK) rc = h->work[W_SUBS].ensure((size_t)wave * lay.sub_len * sizeof(uint32_t));
+        if (rc == MOTES_OK)
+            rc = h->work[W_SEGI].ensure(((size_t)wave * 2 + (size_t)wave * b.ndisp * 3 + 64) * sizeof(uint32_t) + 256);
+        if (rc == MOTES_OK) break;
+        if (rc != MOTES_E_NOMEM) return rc;
+        // the device could not give that much in one piece: half as many frames per wave, down to one
+        cudaGetLastError();
+        if (wave == 1) return MOTES_OK;                 // the caller falls back to the one-CTA-per-frame replay
+        wave = (wave + 1) / 2;
+    }
     uint16_t* stream = h->work[W_STREAM].as<uint16_t>();
     uint32_t* windows = h->work[W_WINDOWS].as<uint32_t>();
     uint32_t* snaps = h->work[W_SNAPS].as<uint32_t>();
