@@ -9,7 +9,7 @@ namespace motes {
 
 // Work-area slots inside motes_handle::work
 enum WorkSlot { W_STATE = 0, W_F64, W_I32, W_U8, W_SORTED, W_RANKS, W_PROFILES, W_GOODROW, W_YSCRATCH, W_MODEL, W_MODELERR,
-                W_STREAM, W_WINDOWS, W_SNAPS, W_SEGI, W_SUBS };
+                W_STREAM, W_WINDOWS, W_SNAPS, W_SEGI, W_SUBS, W_YPOOL };
 
 // Device-side working set of one batch.  All pointers are carved out of handle scratch.
 struct Batch {
@@ -404,7 +404,7 @@ static int stage_bootstrap_segmented(motes_handle* h, Batch& b, uint32_t* rng, b
         }
         t_jump.stop();
         StageTimer t_stream(h, ST_BOOT_STREAM);
-        mt_stream_kernel<<<dim3(lay.segs, nf), 256, 0, h->stream>>>(rng_w, windows, lay, seg_need, stream, snaps);
+        mt_stream_kernel<uint16_t><<<dim3(lay.segs, nf), 256, 0, h->stream>>>(rng_w, windows, lay, seg_need, stream, snaps);
         MOTES_LAUNCHED(h);
         t_stream.stop();
         StageTimer t_walk(h, ST_BOOT_WALK);
@@ -432,6 +432,133 @@ static int stage_bootstrap_segmented(motes_handle* h, Batch& b, uint32_t* rng, b
                 col_start, col_end, subs, b.sky + c0, b.sky_err + c0, b.st + f0, nullptr, nullptr);
             MOTES_LAUNCHED(h);
         }
+        mt_export_kernel<<<nf, 256, 0, h->stream>>>(rng_w, snaps, lay, end_pos, b.st + f0);
+        MOTES_LAUNCHED(h);
+    }
+    *done = true;
+    return MOTES_OK;
+}
+
+// Polynomial sky (sky_order > 0) over the segmented generator (skyseg.cuh).  *done = false: the layout does not fit,
+// the caller runs the one-CTA-per-frame kernel.
+static int stage_poly_segmented(motes_handle* h, Batch& b, const double* errs, size_t frame_stride, const motes_params& p,
+                                uint32_t* rng, bool* done) {
+    *done = false;
+    const JumpTable& table = jump_table();
+    if (!table.ok || h->boot_mode != 0) return MOTES_OK;
+    const unsigned long long accepts_max = (unsigned long long)(kBootstrap / 2) * b.nspat * b.ndisp;
+    const unsigned long long bound = 624ull + 4ull * (unsigned long long)((double)accepts_max * 1.2733) + kSegSlack;
+    if (bound >= 0xff000000ull) return MOTES_OK;
+    const size_t poly_smem = sky_poly_smem(b.nspat);
+    if (poly_smem > h->smem_optin) return MOTES_OK;
+    size_t budget = h->stream_budget;
+    if (budget == 0) {
+        size_t free_b = 0, total_b = 0;
+        MOTES_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        free_b += h->work[W_STREAM].bytes + h->work[W_SNAPS].bytes + h->work[W_WINDOWS].bytes + h->work[W_SUBS].bytes;
+        budget = free_b / 2;
+    }
+    const size_t per_frame_est = (size_t)(bound * 4ull + bound / 16 + (1u << 20));
+    int wave = (int)(budget / per_frame_est);
+    if (wave < 1) return MOTES_OK;
+    if (wave > b.F) wave = b.F;
+    if (!h->jump_ready) {
+        MOTES_TRY(h->jump_polys.ensure(table.words.size() * sizeof(uint32_t)));
+        MOTES_CUDA(cudaMemcpyAsync(h->jump_polys.ptr, table.words.data(), table.words.size() * sizeof(uint32_t),
+                                   cudaMemcpyHostToDevice, h->stream));
+        MOTES_CUDA(cudaStreamSynchronize(h->stream));
+        h->jump_ready = true;
+    }
+    MOTES_CUDA(cudaFuncSetAttribute(sky_poly_column_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)poly_smem));
+    int per_sm = 0;
+    MOTES_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sky_poly_column_kernel, kBootThreads, poly_smem));
+    if (per_sm < 1) return MOTES_OK;
+    const int col_grid = h->sm_count * per_sm;
+    SegLayout lay{};
+    int s = kSnapLog2;
+    size_t bitmap_len = 0, block_len = 0;
+    while (true) {
+        const int waves = (b.F + wave - 1) / wave;
+        wave = (b.F + waves - 1) / waves;
+        const long long target = 8ll * h->sm_count;
+        s = kSnapLog2;
+        while (s < 30 && (long long)wave * (long long)((bound + (1ull << s) - 1) >> s) > target) ++s;
+        if (s + 10 > kJumpMaxLog2) return MOTES_OK;
+        lay.log2_stride = s;
+        lay.stride = 1u << s;
+        lay.segs = (int)((bound + lay.stride - 1) >> s);
+        const unsigned long long words = (unsigned long long)lay.segs << s;
+        lay.stream_len = words + 1024;
+        lay.sub_len = 0;
+        lay.snaps = (int)(words >> kSnapLog2) + 1;
+        bitmap_len = (size_t)(words / 128) + 64;                       // one bit per attempt of four words
+        block_len = (size_t)(words / (4 * kAttemptBlock)) + 8;
+        int rc = h->work[W_STREAM].ensure((size_t)wave * lay.stream_len * sizeof(uint32_t));
+        if (rc == MOTES_OK) rc = h->work[W_WINDOWS].ensure((size_t)wave * lay.segs * 624 * sizeof(uint32_t));
+        if (rc == MOTES_OK) rc = h->work[W_SNAPS].ensure((size_t)wave * lay.snaps * 624 * sizeof(uint32_t));
+        if (rc == MOTES_OK) rc = h->work[W_SUBS].ensure((size_t)wave * (bitmap_len + block_len) * sizeof(uint32_t));
+        if (rc == MOTES_OK)
+            rc = h->work[W_SEGI].ensure((size_t)wave * 16 + (size_t)wave * b.ndisp * 2 * sizeof(unsigned long long) + 512);
+        if (rc == MOTES_OK) rc = h->work[W_YPOOL].ensure((size_t)col_grid * kBootstrap * b.nspat * sizeof(double));
+        if (rc == MOTES_OK) break;
+        if (rc != MOTES_E_NOMEM) return rc;
+        cudaGetLastError();
+        if (wave == 1) return MOTES_OK;
+        wave = (wave + 1) / 2;
+    }
+    uint32_t* stream = h->work[W_STREAM].as<uint32_t>();
+    uint32_t* windows = h->work[W_WINDOWS].as<uint32_t>();
+    uint32_t* snaps = h->work[W_SNAPS].as<uint32_t>();
+    uint32_t* bitmap = h->work[W_SUBS].as<uint32_t>();
+    uint32_t* block_cnt = bitmap + (size_t)wave * bitmap_len;
+    unsigned long long* col_first = h->work[W_SEGI].as<unsigned long long>();
+    unsigned long long* col_last = col_first + (size_t)wave * b.ndisp;
+    int32_t* seg_need = reinterpret_cast<int32_t*>(col_last + (size_t)wave * b.ndisp);
+    uint32_t* end_pos = reinterpret_cast<uint32_t*>(seg_need + wave);
+    double* yscratch = h->work[W_YPOOL].as<double>();
+    const uint32_t* polys = h->jump_polys.as<uint32_t>();
+    const size_t jump_smem = (size_t)(kJumpStreamWords + 624) * sizeof(uint32_t);
+    MOTES_CUDA(cudaFuncSetAttribute(mt_jump_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jump_smem));
+    MOTES_TRY(h->counters.ensure(256));
+    const unsigned long long attempts_max = ((unsigned long long)lay.segs << s) / 4ull + 1;
+
+    for (int f0 = 0; f0 < b.F; f0 += wave) {
+        const int nf = (b.F - f0 < wave) ? b.F - f0 : wave;
+        const size_t c0 = (size_t)f0 * b.ndisp;
+        uint32_t* rng_w = rng + (size_t)f0 * 625;
+        StageTimer t_jump(h, ST_BOOT_JUMP);
+        seg_plan_poly_kernel<<<nf, 256, 0, h->stream>>>(rng_w, b.ndisp, p.sky_order, b.n_good + c0, b.sky_flag + c0, lay, seg_need);
+        MOTES_LAUNCHED(h);
+        MOTES_CUDA(cudaMemsetAsync(windows, 0, (size_t)nf * lay.segs * 624 * sizeof(uint32_t), h->stream));
+        for (int r = 0; (1 << r) < lay.segs; ++r) {
+            const int count = ((1 << (r + 1)) <= lay.segs ? (1 << r) : lay.segs - (1 << r));
+            mt_jump_kernel<<<dim3(count, nf, kJumpParts), kJumpThreads, jump_smem, h->stream>>>(
+                rng_w, windows, lay.segs, r, polys + (size_t)(s + r) * kJumpWords32, seg_need);
+            MOTES_LAUNCHED(h);
+        }
+        t_jump.stop();
+        StageTimer t_stream(h, ST_BOOT_STREAM);
+        mt_stream_kernel<uint32_t><<<dim3(lay.segs, nf), 256, 0, h->stream>>>(rng_w, windows, lay, seg_need, stream, snaps);
+        MOTES_LAUNCHED(h);
+        t_stream.stop();
+        StageTimer t_walk(h, ST_BOOT_WALK);
+        MOTES_CUDA(cudaMemsetAsync(block_cnt, 0, (size_t)nf * block_len * sizeof(uint32_t), h->stream));
+        poly_attempts_kernel<<<dim3((unsigned)((attempts_max + 255) / 256), nf), 256, 0, h->stream>>>(
+            stream, lay, rng_w, seg_need, bitmap, bitmap_len, block_cnt, block_len);
+        MOTES_LAUNCHED(h);
+        poly_bounds_kernel<<<nf, 1024, 0, h->stream>>>(lay, rng_w, seg_need, b.ndisp, p.sky_order, b.n_good + c0, b.sky_flag + c0,
+                                                       bitmap, bitmap_len, block_cnt, block_len, col_first, col_last, end_pos,
+                                                       b.st + f0);
+        MOTES_LAUNCHED(h);
+        t_walk.stop();
+        StageTimer t_col(h, ST_BOOT_COLUMN);
+        MOTES_CUDA(cudaMemsetAsync(h->counters.ptr, 0, 256, h->stream));
+        sky_poly_column_kernel<<<col_grid, kBootThreads, poly_smem, h->stream>>>(
+            stream, lay, rng_w, nf, b.nspat, b.ndisp, p.sky_order, p.spatial_floor, errs + (size_t)f0 * frame_stride, frame_stride,
+            b.n_good + c0, b.sky_flag + c0, b.sorted + c0 * b.nspat, b.rank_of + c0 * b.nspat, b.good_row + c0 * b.nspat, col_first,
+            col_last, yscratch, b.model + (size_t)f0 * frame_stride, b.model_err + (size_t)f0 * frame_stride, b.st + f0,
+            h->counters.as<unsigned int>());
+        MOTES_LAUNCHED(h);
         mt_export_kernel<<<nf, 256, 0, h->stream>>>(rng_w, snaps, lay, end_pos, b.st + f0);
         MOTES_LAUNCHED(h);
     }
@@ -479,7 +606,9 @@ static int stage_sky(motes_handle* h, Batch& b, double* data, double* errs, size
     MOTES_CUDA(cudaFuncSetAttribute(sky_bootstrap_poly_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     MOTES_CUDA(cudaMemsetAsync(b.model, 0, sizeof(double) * (size_t)b.F * frame_stride, h->stream));
     MOTES_CUDA(cudaMemsetAsync(b.model_err, 0, sizeof(double) * (size_t)b.F * frame_stride, h->stream));
-    {
+    bool poly_done = false;
+    MOTES_TRY(stage_poly_segmented(h, b, errs, frame_stride, p, rng, &poly_done));
+    if (!poly_done) {
         StageTimer timer(h, ST_SKY_BOOTSTRAP);
         sky_bootstrap_poly_kernel<<<b.F, kBootThreads, smem, h->stream>>>(
             rng, b.nspat, b.ndisp, p.sky_order, p.spatial_floor, errs, frame_stride, b.n_good, b.sky_flag, b.sorted,

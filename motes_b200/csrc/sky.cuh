@@ -500,6 +500,120 @@ MOTES_HD double scope_dsum(const Scope& sc, double v, double* red) {
     return v;
 }
 
+// The fit half of sky.sky_polynomial for one column, once the 100 perturbed sky vectors y[j * 100 + s] exist:
+// QR of the column-normalised Vandermonde matrix of the good pixels (sh.rows), one projection + back-substitution
+// per sample, then per spatial pixel the median / std of the 100 polynomial values (sky.py:226-239).
+template <class Scope>
+MOTES_HD void sky_poly_fit_column(const Scope& sc, const PolyShared& sh, int n, int p, int nspat, int ndisp, int c,
+                                  int spatial_floor, const double* y, double* model, double* model_err) {
+#if defined(__CUDA_ARCH__)
+    const int lane = sc.tid & 31, warp = sc.tid >> 5;
+#endif
+    // ---- QR of the column-normalised Vandermonde matrix (np.polyfit: lhs /= sqrt((lhs*lhs).sum(0)))
+    // column k of the design holds x^(order-k) as np.vander does
+    for (int g = sc.tid; g < n; g += sc.size()) {
+        const double x = (double)((int)sh.rows[g] + spatial_floor);
+        double pw = 1.0;
+        for (int k = p - 1; k >= 0; --k) { sh.q[(size_t)g * kMaxPoly + k] = pw; pw *= x; }
+    }
+    sc.sync();
+    for (int k = 0; k < p; ++k) {
+        double part = 0.0;
+        for (int g = sc.tid; g < n; g += sc.size()) { double t = sh.q[(size_t)g * kMaxPoly + k]; part += t * t; }
+        double nrm = sqrt(scope_dsum(sc, part, sh.red));
+        if (sc.tid == 0) sh.colscale[k] = nrm;
+        for (int g = sc.tid; g < n; g += sc.size()) sh.q[(size_t)g * kMaxPoly + k] /= nrm;
+        sc.sync();
+    }
+    for (int k = 0; k < p; ++k) {
+        double part = 0.0;
+        for (int g = sc.tid; g < n; g += sc.size()) { double t = sh.q[(size_t)g * kMaxPoly + k]; part += t * t; }
+        double rkk = sqrt(scope_dsum(sc, part, sh.red));
+        if (sc.tid == 0) sh.rmat[k * kMaxPoly + k] = rkk;
+        for (int g = sc.tid; g < n; g += sc.size()) sh.q[(size_t)g * kMaxPoly + k] /= rkk;
+        sc.sync();
+        for (int j2 = k + 1; j2 < p; ++j2) {
+            part = 0.0;
+            for (int g = sc.tid; g < n; g += sc.size()) part += sh.q[(size_t)g * kMaxPoly + k] * sh.q[(size_t)g * kMaxPoly + j2];
+            double rkj = scope_dsum(sc, part, sh.red);
+            if (sc.tid == 0) sh.rmat[k * kMaxPoly + j2] = rkj;
+            for (int g = sc.tid; g < n; g += sc.size()) sh.q[(size_t)g * kMaxPoly + j2] -= rkj * sh.q[(size_t)g * kMaxPoly + k];
+            sc.sync();
+        }
+    }
+    // ---- one projection + back-substitution per bootstrap sample
+    for (int smp = sc.tid; smp < kBootstrap; smp += sc.size()) {
+        double z[kMaxPoly], cf[kMaxPoly];
+        for (int k = 0; k < p; ++k) z[k] = 0.0;
+        for (int g = 0; g < n; ++g) {
+            const double yv = y[(size_t)g * kBootstrap + smp];
+            for (int k = 0; k < p; ++k) z[k] = fma(sh.q[(size_t)g * kMaxPoly + k], yv, z[k]);
+        }
+        for (int k = p - 1; k >= 0; --k) {
+            double acc2 = z[k];
+            for (int j2 = k + 1; j2 < p; ++j2) acc2 -= sh.rmat[k * kMaxPoly + j2] * cf[j2];
+            cf[k] = acc2 / sh.rmat[k * kMaxPoly + k];
+        }
+        // un-scale and flip to ascending powers (sky.py:230)
+        for (int k = 0; k < p; ++k) sh.coef[smp * kMaxPoly + (p - 1 - k)] = cf[k] / sh.colscale[k];
+    }
+    sc.sync();
+    // ---- per spatial pixel: median and std over the 100 polynomial values (sky.py:231-239)
+#if defined(__CUDA_ARCH__)
+    const int nwarp = (sc.size() + 31) >> 5;
+    const int wid = sc.size() > 1 ? warp : 0, ln = sc.size() > 1 ? lane : 0, lanes = sc.size() > 1 ? 32 : 1;
+#else
+    const int nwarp = 1, wid = 0, ln = 0, lanes = 1;
+#endif
+    double* vals = sh.samples + (size_t)wid * kBootstrap;
+    for (int px = wid; px < nspat; px += nwarp) {
+        const double x = (double)(px + spatial_floor);
+        for (int smp = ln; smp < kBootstrap; smp += lanes) {
+            double acc2 = 0.0, pw = 1.0;
+            for (int k = 0; k < p; ++k) { acc2 += pw * sh.coef[smp * kMaxPoly + k]; pw *= x; }
+            vals[smp] = acc2;
+        }
+#if defined(__CUDA_ARCH__)
+        __syncwarp();
+#endif
+        // np.median of 100: mean of the order statistics 49 and 50
+        double m1 = 0.0, m2 = 0.0, psum = 0.0;
+        for (int e = ln; e < kBootstrap; e += lanes) {
+            const double v = vals[e];
+            int rank = 0;
+            for (int j2 = 0; j2 < kBootstrap; ++j2) { const double o = vals[j2]; rank += (o < v) || (o == v && j2 < e); }
+            if (rank == 49) m1 = v;
+            if (rank == 50) m2 = v;
+            psum += v;
+        }
+        double mean;
+#if defined(__CUDA_ARCH__)
+        if (sc.size() > 1) {
+            for (int o = 16; o > 0; o >>= 1) {
+                m1 += __shfl_xor_sync(0xffffffffu, m1, o);      // exactly one lane holds each (others 0)
+                m2 += __shfl_xor_sync(0xffffffffu, m2, o);
+                psum += __shfl_xor_sync(0xffffffffu, psum, o);
+            }
+        }
+#endif
+        mean = psum / (double)kBootstrap;
+        double sq = 0.0;
+        for (int e = ln; e < kBootstrap; e += lanes) { const double d = vals[e] - mean; sq += d * d; }
+#if defined(__CUDA_ARCH__)
+        if (sc.size() > 1)
+            for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+#endif
+        if (ln == 0) {
+            model[(size_t)px * ndisp + c] = (m1 + m2) * 0.5;
+            model_err[(size_t)px * ndisp + c] = sqrt(sq / (double)kBootstrap);
+        }
+#if defined(__CUDA_ARCH__)
+        __syncwarp();
+#endif
+    }
+    sc.sync();
+}
+
 // y: global scratch of 100 * max_good doubles for this frame, pixel-major (y[j * 100 + s]).
 // model / model_err: (nspat, ndisp) frames receiving this column's result at [pixel * ndisp + c].
 template <class Scope>
@@ -608,109 +722,7 @@ MOTES_HD void sky_bootstrap_poly_frame(const Scope& sc, uint32_t* state, int nco
         used_total += (unsigned long long)(used - used_at_start);
         sc.sync();
 
-        // ---- QR of the column-normalised Vandermonde matrix (np.polyfit: lhs /= sqrt((lhs*lhs).sum(0)))
-        // column k of the design holds x^(order-k) as np.vander does
-        for (int g = sc.tid; g < n; g += sc.size()) {
-            const double x = (double)((int)sh.rows[g] + spatial_floor);
-            double pw = 1.0;
-            for (int k = p - 1; k >= 0; --k) { sh.q[(size_t)g * kMaxPoly + k] = pw; pw *= x; }
-        }
-        sc.sync();
-        for (int k = 0; k < p; ++k) {
-            double part = 0.0;
-            for (int g = sc.tid; g < n; g += sc.size()) { double t = sh.q[(size_t)g * kMaxPoly + k]; part += t * t; }
-            double nrm = sqrt(scope_dsum(sc, part, sh.red));
-            if (sc.tid == 0) sh.colscale[k] = nrm;
-            for (int g = sc.tid; g < n; g += sc.size()) sh.q[(size_t)g * kMaxPoly + k] /= nrm;
-            sc.sync();
-        }
-        for (int k = 0; k < p; ++k) {
-            double part = 0.0;
-            for (int g = sc.tid; g < n; g += sc.size()) { double t = sh.q[(size_t)g * kMaxPoly + k]; part += t * t; }
-            double rkk = sqrt(scope_dsum(sc, part, sh.red));
-            if (sc.tid == 0) sh.rmat[k * kMaxPoly + k] = rkk;
-            for (int g = sc.tid; g < n; g += sc.size()) sh.q[(size_t)g * kMaxPoly + k] /= rkk;
-            sc.sync();
-            for (int j2 = k + 1; j2 < p; ++j2) {
-                part = 0.0;
-                for (int g = sc.tid; g < n; g += sc.size()) part += sh.q[(size_t)g * kMaxPoly + k] * sh.q[(size_t)g * kMaxPoly + j2];
-                double rkj = scope_dsum(sc, part, sh.red);
-                if (sc.tid == 0) sh.rmat[k * kMaxPoly + j2] = rkj;
-                for (int g = sc.tid; g < n; g += sc.size()) sh.q[(size_t)g * kMaxPoly + j2] -= rkj * sh.q[(size_t)g * kMaxPoly + k];
-                sc.sync();
-            }
-        }
-        // ---- one projection + back-substitution per bootstrap sample
-        for (int smp = sc.tid; smp < kBootstrap; smp += sc.size()) {
-            double z[kMaxPoly], cf[kMaxPoly];
-            for (int k = 0; k < p; ++k) z[k] = 0.0;
-            for (int g = 0; g < n; ++g) {
-                const double yv = y[(size_t)g * kBootstrap + smp];
-                for (int k = 0; k < p; ++k) z[k] = fma(sh.q[(size_t)g * kMaxPoly + k], yv, z[k]);
-            }
-            for (int k = p - 1; k >= 0; --k) {
-                double acc2 = z[k];
-                for (int j2 = k + 1; j2 < p; ++j2) acc2 -= sh.rmat[k * kMaxPoly + j2] * cf[j2];
-                cf[k] = acc2 / sh.rmat[k * kMaxPoly + k];
-            }
-            // un-scale and flip to ascending powers (sky.py:230)
-            for (int k = 0; k < p; ++k) sh.coef[smp * kMaxPoly + (p - 1 - k)] = cf[k] / sh.colscale[k];
-        }
-        sc.sync();
-        // ---- per spatial pixel: median and std over the 100 polynomial values (sky.py:231-239)
-#if defined(__CUDA_ARCH__)
-        const int nwarp = (sc.size() + 31) >> 5;
-        const int wid = sc.size() > 1 ? warp : 0, ln = sc.size() > 1 ? lane : 0, lanes = sc.size() > 1 ? 32 : 1;
-#else
-        const int nwarp = 1, wid = 0, ln = 0, lanes = 1;
-#endif
-        double* vals = sh.samples + (size_t)wid * kBootstrap;
-        for (int px = wid; px < nspat; px += nwarp) {
-            const double x = (double)(px + spatial_floor);
-            for (int smp = ln; smp < kBootstrap; smp += lanes) {
-                double acc2 = 0.0, pw = 1.0;
-                for (int k = 0; k < p; ++k) { acc2 += pw * sh.coef[smp * kMaxPoly + k]; pw *= x; }
-                vals[smp] = acc2;
-            }
-#if defined(__CUDA_ARCH__)
-            __syncwarp();
-#endif
-            // np.median of 100: mean of the order statistics 49 and 50
-            double m1 = 0.0, m2 = 0.0, psum = 0.0;
-            for (int e = ln; e < kBootstrap; e += lanes) {
-                const double v = vals[e];
-                int rank = 0;
-                for (int j2 = 0; j2 < kBootstrap; ++j2) { const double o = vals[j2]; rank += (o < v) || (o == v && j2 < e); }
-                if (rank == 49) m1 = v;
-                if (rank == 50) m2 = v;
-                psum += v;
-            }
-            double mean;
-#if defined(__CUDA_ARCH__)
-            if (sc.size() > 1) {
-                for (int o = 16; o > 0; o >>= 1) {
-                    m1 += __shfl_xor_sync(0xffffffffu, m1, o);      // exactly one lane holds each (others 0)
-                    m2 += __shfl_xor_sync(0xffffffffu, m2, o);
-                    psum += __shfl_xor_sync(0xffffffffu, psum, o);
-                }
-            }
-#endif
-            mean = psum / (double)kBootstrap;
-            double sq = 0.0;
-            for (int e = ln; e < kBootstrap; e += lanes) { const double d = vals[e] - mean; sq += d * d; }
-#if defined(__CUDA_ARCH__)
-            if (sc.size() > 1)
-                for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-#endif
-            if (ln == 0) {
-                model[(size_t)px * ndisp + c] = (m1 + m2) * 0.5;
-                model_err[(size_t)px * ndisp + c] = sqrt(sq / (double)kBootstrap);
-            }
-#if defined(__CUDA_ARCH__)
-            __syncwarp();
-#endif
-        }
-        sc.sync();
+        sky_poly_fit_column(sc, sh, n, p, nspat, ndisp, c, spatial_floor, y, model, model_err);
     }
 
     const unsigned long long block = (used_total > 0) ? ((used_total - 1) / kMtN) * kMtN : 0;

@@ -156,10 +156,10 @@ __device__ __forceinline__ uint32_t mt_temper_fast(uint32_t y) {
     return y ^ (y >> 18);
 }
 
-template <int U>
+template <int U, class OutT>
 __device__ __forceinline__ void stream_round(uint32_t& far, const uint32_t* pa0, const uint32_t* pa0w, const uint32_t* pa1,
                                              const uint32_t* pa1w, const uint32_t* pb, const uint32_t* pbw, uint32_t* pw,
-                                             uint32_t* pww, uint16_t* out_t) {
+                                             uint32_t* pww, OutT* out_t) {
     // operands of word n0: rows U / U + 1 (per thread), of word n1: row U + 1; results: row U + 2
     const uint32_t a0 = (U == kRingRows - 1) ? pa0w[U * kRowWords] : pa0[U * kRowWords];
     const uint32_t a1 = (U == kRingRows - 1) ? pa1w[U * kRowWords] : pa1[U * kRowWords];
@@ -170,26 +170,28 @@ __device__ __forceinline__ void stream_round(uint32_t& far, const uint32_t* pa0,
     uint32_t* w = (U >= kRingRows - 2) ? pww : pw;
     w[U * kRowWords] = v0;
     w[U * kRowWords + kSweep] = v1;
-    out_t[U * kRowWords] = (uint16_t)mt_temper_fast(v0);
-    out_t[U * kRowWords + kSweep] = (uint16_t)mt_temper_fast(v1);
+    out_t[U * kRowWords] = (OutT)mt_temper_fast(v0);
+    out_t[U * kRowWords + kSweep] = (OutT)mt_temper_fast(v1);
     far = v1;
 }
 
+// OutT = uint16_t: the low half of every output (order-0 bootstrap); uint32_t: whole outputs (polynomial sky).
+template <class OutT>
 __global__ void __launch_bounds__(256)
 mt_stream_kernel(const uint32_t* __restrict__ rng, const uint32_t* __restrict__ windows, SegLayout lay,
-                 const int32_t* __restrict__ seg_need, uint16_t* __restrict__ stream, uint32_t* __restrict__ snaps) {
+                 const int32_t* __restrict__ seg_need, OutT* __restrict__ stream, uint32_t* __restrict__ snaps) {
     __shared__ uint32_t ring[kRingWords];
     const int f = blockIdx.y, k = blockIdx.x;
     if (k >= seg_need[f]) return;
     const uint32_t base = (uint32_t)k << lay.log2_stride;
     const uint32_t gen0 = base + 624;
     const uint32_t* from = (k == 0) ? rng + (size_t)f * 625 : windows + ((size_t)f * lay.segs + k) * 624;
-    uint16_t* out = stream + (size_t)f * lay.stream_len;
+    OutT* out = stream + (size_t)f * lay.stream_len;
     uint32_t* snap = snaps + (size_t)f * lay.snaps * 624;
     for (int i = threadIdx.x; i < 624; i += blockDim.x) {
         const uint32_t v = from[i];
         ring[stream_ring_slot(base + i, gen0)] = v;
-        if (k == 0 || i >= 1) out[base + i] = (uint16_t)mt_temper(v);     // word 0 of a jumped window is not a stream word
+        if (k == 0 || i >= 1) out[base + i] = (OutT)mt_temper(v);     // word 0 of a jumped window is not a stream word
         if (k == 0) snap[i] = v;
     }
     __syncthreads();
@@ -219,47 +221,47 @@ mt_stream_kernel(const uint32_t* __restrict__ rng, const uint32_t* __restrict__ 
     uint32_t* pww = pw - kRingWords;
     uint32_t far = ring[kRowWords + kSweep + tt];            // word gen0 + t - 227
     uint32_t gen = gen0;
-    uint16_t* out_t = out + gen0 + tt;
+    OutT* out_t = out + gen0 + tt;
     // ---- full blocks of 18 rounds, every output inside the segment
     while (gen + (uint32_t)kRingWords <= last_out + 1u) {
         if (worker) {
-            stream_round<0>(far, pa0, pa0w, pa1, pa1w, pb, pbw, pw, pww, out_t);
+            stream_round<0, OutT>(far, pa0, pa0w, pa1, pa1w, pb, pbw, pw, pww, out_t);
         }
         __syncthreads();
-        if (worker) stream_round<1>(far, pa0, pa0w, pa1, pa1w, pb, pbw, pw, pww, out_t);
+        if (worker) stream_round<1, OutT>(far, pa0, pa0w, pa1, pa1w, pb, pbw, pw, pww, out_t);
         __syncthreads();
-        if (worker) stream_round<2>(far, pa0, pa0w, pa1, pa1w, pb, pbw, pw, pww, out_t);
+        if (worker) stream_round<2, OutT>(far, pa0, pa0w, pa1, pa1w, pb, pbw, pw, pww, out_t);
         __syncthreads();
-        if (worker) stream_round<3>(far, pa0, pa0w, pa1, pa1w, pb, pbw, pw, pww, out_t);
+        if (worker) stream_round<3, OutT>(far, pa0, pa0w, pa1, pa1w, pb, pbw, pw, pww, out_t);
         __syncthreads();
-        if (worker) stream_round<4>(far, pa0, pa0w, pa1, pa1w, pb, pbw, pw, pww, out_t);
+        if (worker) stream_round<4, OutT>(far, pa0, pa0w, pa1, pa1w, pb, pbw, pw, pww, out_t);
         __syncthreads();
-        if (worker) stream_round<5>(far, pa0, pa0w, pa1, pa1w, pb, pbw, pw, pww, out_t);
+        if (worker) stream_round<5, OutT>(far, pa0, pa0w, pa1, pa1w, pb, pbw, pw, pww, out_t);
         __syncthreads();
-        if (worker) stream_round<6>(far, pa0, pa0w, pa1, pa1w, pb, pbw, pw, pww, out_t);
+        if (worker) stream_round<6, OutT>(far, pa0, pa0w, pa1, pa1w, pb, pbw, pw, pww, out_t);
         __syncthreads();
-        if (worker) stream_round<7>(far, pa0, pa0w, pa1, pa1w, pb, pbw, pw, pww, out_t);
+        if (worker) stream_round<7, OutT>(far, pa0, pa0w, pa1, pa1w, pb, pbw, pw, pww, out_t);
         __syncthreads();
-        if (worker) stream_round<8>(far, pa0, pa0w, pa1, pa1w, pb, pbw, pw, pww, out_t);
+        if (worker) stream_round<8, OutT>(far, pa0, pa0w, pa1, pa1w, pb, pbw, pw, pww, out_t);
         __syncthreads();
         take_snapshot(gen + 9u * kRowWords);
-        if (worker) stream_round<9>(far, pa0, pa0w, pa1, pa1w, pb, pbw, pw, pww, out_t);
+        if (worker) stream_round<9, OutT>(far, pa0, pa0w, pa1, pa1w, pb, pbw, pw, pww, out_t);
         __syncthreads();
-        if (worker) stream_round<10>(far, pa0, pa0w, pa1, pa1w, pb, pbw, pw, pww, out_t);
+        if (worker) stream_round<10, OutT>(far, pa0, pa0w, pa1, pa1w, pb, pbw, pw, pww, out_t);
         __syncthreads();
-        if (worker) stream_round<11>(far, pa0, pa0w, pa1, pa1w, pb, pbw, pw, pww, out_t);
+        if (worker) stream_round<11, OutT>(far, pa0, pa0w, pa1, pa1w, pb, pbw, pw, pww, out_t);
         __syncthreads();
-        if (worker) stream_round<12>(far, pa0, pa0w, pa1, pa1w, pb, pbw, pw, pww, out_t);
+        if (worker) stream_round<12, OutT>(far, pa0, pa0w, pa1, pa1w, pb, pbw, pw, pww, out_t);
         __syncthreads();
-        if (worker) stream_round<13>(far, pa0, pa0w, pa1, pa1w, pb, pbw, pw, pww, out_t);
+        if (worker) stream_round<13, OutT>(far, pa0, pa0w, pa1, pa1w, pb, pbw, pw, pww, out_t);
         __syncthreads();
-        if (worker) stream_round<14>(far, pa0, pa0w, pa1, pa1w, pb, pbw, pw, pww, out_t);
+        if (worker) stream_round<14, OutT>(far, pa0, pa0w, pa1, pa1w, pb, pbw, pw, pww, out_t);
         __syncthreads();
-        if (worker) stream_round<15>(far, pa0, pa0w, pa1, pa1w, pb, pbw, pw, pww, out_t);
+        if (worker) stream_round<15, OutT>(far, pa0, pa0w, pa1, pa1w, pb, pbw, pw, pww, out_t);
         __syncthreads();
-        if (worker) stream_round<16>(far, pa0, pa0w, pa1, pa1w, pb, pbw, pw, pww, out_t);
+        if (worker) stream_round<16, OutT>(far, pa0, pa0w, pa1, pa1w, pb, pbw, pw, pww, out_t);
         __syncthreads();
-        if (worker) stream_round<17>(far, pa0, pa0w, pa1, pa1w, pb, pbw, pw, pww, out_t);
+        if (worker) stream_round<17, OutT>(far, pa0, pa0w, pa1, pa1w, pb, pbw, pw, pww, out_t);
         __syncthreads();
         gen += (uint32_t)kRingWords;
         out_t += kRingWords;
@@ -274,8 +276,8 @@ mt_stream_kernel(const uint32_t* __restrict__ rng, const uint32_t* __restrict__ 
             const uint32_t v1 = mt_mix(ring[stream_ring_slot(n1 - 624, gen0)], ring[stream_ring_slot(n1 - 623, gen0)], v0);
             ring[stream_ring_slot(n0, gen0)] = v0;
             ring[stream_ring_slot(n1, gen0)] = v1;
-            if (n0 <= last_out) out[n0] = (uint16_t)mt_temper(v0);
-            if (n1 <= last_out) out[n1] = (uint16_t)mt_temper(v1);
+            if (n0 <= last_out) out[n0] = (OutT)mt_temper(v0);
+            if (n1 <= last_out) out[n1] = (OutT)mt_temper(v1);
             far = v1;
         }
         __syncthreads();
@@ -902,6 +904,268 @@ sky_column_hist_kernel(const uint16_t* __restrict__ stream, SegLayout lay, int n
         return;
     }
     if (warp == 0) column_mean_std(meds, sq, lane, sky + col, sky_err + col);
+}
+
+// ---- polynomial sky (sky.sky_polynomial, sky.py:177-254) over the segmented generator ----------------------
+// np.random.normal (legacy polar method) consumes the stream four words per attempt and accepts an attempt
+// when 0 < r2 < 1 - a property of the words alone, not of the column that draws.  So, with the whole 32-bit
+// stream in HBM (mt_stream_kernel<uint32_t>): the acceptance bit of every attempt is computed in parallel
+// (poly_attempts_kernel), a prefix sum over them tells where the accept with a given ordinal sits, and a column
+// that needs 50 n accepted attempts after the 50 (n_0 + .. + n_{c-1}) of its predecessors gets its attempt range
+// from two look-ups (poly_bounds_kernel).  The columns then run independently (sky_poly_column_kernel).
+constexpr int kAttemptBlock = 1024;              // attempts per prefix-sum block (32 bitmap words)
+
+__global__ void __launch_bounds__(256)
+seg_plan_poly_kernel(const uint32_t* __restrict__ rng, int ndisp, int order, const int32_t* __restrict__ n_good,
+                     const int32_t* __restrict__ flag, SegLayout lay, int32_t* __restrict__ seg_need) {
+    __shared__ unsigned long long part[8];
+    const int f = blockIdx.x;
+    unsigned long long acc = 0;
+    for (int c = threadIdx.x; c < ndisp; c += blockDim.x) {
+        const size_t col = (size_t)f * ndisp + c;
+        const int n = n_good[col];
+        if (flag[col] == kSkyModelled && n >= order + 1) acc += (unsigned long long)n * (kBootstrap / 2);
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long accepts = 0;
+        for (int w = 0; w < 8; ++w) accepts += part[w];
+        // attempts per accept: 4 / pi = 1.2732; the sum over 1e7+ accepts is sharp, 2^20 words of slack cover it
+        unsigned long long total = rng[(size_t)f * 625 + 624] + 4ull * (unsigned long long)((double)accepts * 1.2733) + kSegSlack;
+        unsigned long long need = (total + lay.stride - 1) >> lay.log2_stride;
+        if (need > (unsigned long long)lay.segs) need = lay.segs;
+        if (need < 1) need = 1;
+        seg_need[f] = (int32_t)need;
+    }
+}
+
+// x1, x2, r2 of the attempt whose four tempered words are w[0..3]; the arithmetic of numpy's legacy_gauss
+__device__ __forceinline__ bool gauss_attempt(const uint32_t* __restrict__ w, double* x1, double* x2, double* r2) {
+    const double u1 = ((double)(w[0] >> 5) * 67108864.0 + (double)(w[1] >> 6)) / 9007199254740992.0;
+    const double u2 = ((double)(w[2] >> 5) * 67108864.0 + (double)(w[3] >> 6)) / 9007199254740992.0;
+    *x1 = 2.0 * u1 - 1.0;
+    *x2 = 2.0 * u2 - 1.0;
+    *r2 = *x1 * *x1 + *x2 * *x2;
+    return *r2 < 1.0 && *r2 != 0.0;
+}
+
+// attempt a of a frame = stream words pos0 + 4 a .. + 3.  One thread per attempt: bitmap word per warp,
+// accepted-attempt count per block of 1024 attempts.
+__global__ void __launch_bounds__(256)
+poly_attempts_kernel(const uint32_t* __restrict__ stream, SegLayout lay, const uint32_t* __restrict__ rng,
+                     const int32_t* __restrict__ seg_need, uint32_t* __restrict__ bitmap, size_t bitmap_len,
+                     uint32_t* __restrict__ block_cnt, size_t block_len) {
+    const int f = blockIdx.y;
+    const uint32_t pos0 = rng[(size_t)f * 625 + 624];
+    const uint32_t limit = ((uint32_t)seg_need[f] << lay.log2_stride) + 1u;        // stream words [0, limit) exist
+    const unsigned long long a = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long p = (unsigned long long)pos0 + 4ull * a;
+    if (((unsigned long long)blockIdx.x * blockDim.x) * 4ull + pos0 >= limit) return;            // whole CTA past the end
+    bool acc = false;
+    if (p + 3 < limit) {
+        const uint32_t* w = stream + (size_t)f * lay.stream_len + p;
+        double x1, x2, r2;
+        acc = gauss_attempt(w, &x1, &x2, &r2);
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, acc);
+    if ((threadIdx.x & 31) == 0) {
+        bitmap[(size_t)f * bitmap_len + (a >> 5)] = bal;
+        if (bal) atomicAdd(&block_cnt[(size_t)f * block_len + (a / kAttemptBlock)], (uint32_t)__popc(bal));
+    }
+}
+
+// index of the attempt that is the frame's accept number `ordinal` (0-based), from the exclusive block prefix
+__device__ __forceinline__ unsigned long long attempt_of_accept(unsigned long long ordinal, const uint32_t* __restrict__ prefix,
+                                                                int nblocks, const uint32_t* __restrict__ bitmap) {
+    int lo = 0, hi = nblocks - 1;                 // last block whose prefix <= ordinal
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if ((unsigned long long)prefix[mid] <= ordinal) lo = mid; else hi = mid - 1;
+    }
+    unsigned long long left = ordinal - prefix[lo];
+    const uint32_t* w = bitmap + (size_t)lo * (kAttemptBlock / 32);
+    for (int i = 0; i < kAttemptBlock / 32; ++i) {
+        uint32_t bits = w[i];
+        const unsigned c = (unsigned)__popc(bits);
+        if (left < c) {
+            for (unsigned k = 0; k < (unsigned)left; ++k) bits &= bits - 1;
+            return (unsigned long long)lo * kAttemptBlock + 32ull * i + (unsigned)(__ffs(bits) - 1);
+        }
+        left -= c;
+    }
+    return ~0ull;                                  // fewer accepts than planned: reported by the caller
+}
+
+// One CTA per frame: exclusive prefix of the block counts (in place), then per column the attempt range
+// [first, last) it consumes, and the generator position after the frame.
+__global__ void __launch_bounds__(1024)
+poly_bounds_kernel(SegLayout lay, const uint32_t* __restrict__ rng, const int32_t* __restrict__ seg_need, int ndisp,
+                   int order, const int32_t* __restrict__ n_good, const int32_t* __restrict__ flag,
+                   const uint32_t* __restrict__ bitmap, size_t bitmap_len, uint32_t* __restrict__ block_cnt,
+                   size_t block_len, unsigned long long* __restrict__ col_first, unsigned long long* __restrict__ col_last,
+                   uint32_t* __restrict__ end_pos, FrameState* __restrict__ st) {
+    __shared__ unsigned long long carry;
+    __shared__ unsigned long long wsum[32];
+    const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t pos0 = rng[(size_t)f * 625 + 624];
+    const uint32_t limit = ((uint32_t)seg_need[f] << lay.log2_stride) + 1u;
+    const int nblocks = (int)((((unsigned long long)(limit > pos0 ? limit - pos0 : 0) / 4ull) + kAttemptBlock - 1) / kAttemptBlock);
+    uint32_t* cnt = block_cnt + (size_t)f * block_len;
+    const uint32_t* bits = bitmap + (size_t)f * bitmap_len;
+    // ---- exclusive prefix over the blocks, 1024 at a time
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < nblocks; base += 1024) {
+        const int i = base + tid;
+        const unsigned long long v = (i < nblocks) ? cnt[i] : 0u;
+        unsigned long long incl = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        unsigned long long below = carry;
+        for (int w = 0; w < warp; ++w) below += wsum[w];
+        if (i < nblocks) cnt[i] = (uint32_t)(below + incl - v);
+        __syncthreads();
+        if (tid == 1023) carry = below + incl;
+        __syncthreads();
+    }
+    const unsigned long long total_accepts = carry;
+    // ---- columns: ordinal of each column's first accept = 50 x (good pixels of the modelled columns before it)
+    unsigned long long run = 0;
+    __syncthreads();
+    for (int base = 0; base < ndisp; base += 1024) {
+        const int c = base + tid;
+        const size_t col = (size_t)f * ndisp + c;
+        unsigned long long mine = 0;
+        if (c < ndisp && flag[col] == kSkyModelled && n_good[col] >= order + 1) mine = (unsigned long long)n_good[col] * (kBootstrap / 2);
+        unsigned long long incl = mine;
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        unsigned long long below = run;
+        for (int w = 0; w < warp; ++w) below += wsum[w];
+        unsigned long long all = run;
+        for (int w = 0; w < 32; ++w) all += wsum[w];
+        if (c < ndisp) {
+            const unsigned long long first_ord = below + incl - mine;        // accepts consumed before this column
+            unsigned long long a0 = 0, a1 = 0;
+            if (mine) {
+                if (first_ord + mine > total_accepts) {
+                    atomicMin(&st[f].status, (int)MOTES_E_INTERNAL);
+                } else {
+                    a0 = first_ord ? attempt_of_accept(first_ord - 1, cnt, nblocks, bits) + 1 : 0;
+                    a1 = attempt_of_accept(first_ord + mine - 1, cnt, nblocks, bits) + 1;
+                }
+            }
+            col_first[col] = a0;
+            col_last[col] = a1;
+        }
+        run = all;
+        __syncthreads();
+    }
+    // generator position after the frame: just behind the last attempt of the last drawing column
+    if (tid == 0) {
+        unsigned long long last = 0;
+        if (run > 0 && run <= total_accepts) last = attempt_of_accept(run - 1, cnt, nblocks, bits) + 1;
+        end_pos[f] = pos0 + (uint32_t)(4ull * last);
+    }
+}
+
+// Persistent CTAs over (frame, column) items; each owns one slot of y scratch (100 x nspat doubles).
+__global__ void __launch_bounds__(kBootThreads)
+sky_poly_column_kernel(const uint32_t* __restrict__ stream, SegLayout lay, const uint32_t* __restrict__ rng, int nframes,
+                       int nspat, int ndisp, int order, int spatial_floor, const double* __restrict__ errs,
+                       size_t frame_stride, const int32_t* __restrict__ n_good, const int32_t* __restrict__ flag,
+                       const double* __restrict__ sorted, const uint16_t* __restrict__ rank_of,
+                       const uint16_t* __restrict__ good_row, const unsigned long long* __restrict__ col_first,
+                       const unsigned long long* __restrict__ col_last, double* __restrict__ yscratch,
+                       double* __restrict__ model, double* __restrict__ model_err, const FrameState* __restrict__ st,
+                       unsigned int* __restrict__ queue) {
+    extern __shared__ __align__(16) unsigned char spc_smem[];
+    PolyShared sh;
+    sh.q = reinterpret_cast<double*>(spc_smem);
+    sh.rmat = sh.q + (size_t)nspat * kMaxPoly;
+    sh.colscale = sh.rmat + kMaxPoly * kMaxPoly;
+    sh.coef = sh.colscale + kMaxPoly;
+    sh.loc = sh.coef + kBootstrap * kMaxPoly;
+    sh.scl = sh.loc + nspat;
+    sh.red = sh.scl + nspat;
+    sh.samples = sh.red + 40;
+    sh.ring = reinterpret_cast<uint32_t*>(sh.samples + (size_t)(kBootThreads / 32) * kBootstrap);     // unused here
+    sh.counts = sh.ring;                                                                                // 16 words
+    sh.ctl = reinterpret_cast<int*>(sh.counts + 16);
+    sh.rows = reinterpret_cast<uint16_t*>(sh.ctl + 4);
+    __shared__ unsigned int s_item;
+    BlockScope sc{(int)threadIdx.x};
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned char* counts8 = reinterpret_cast<unsigned char*>(sh.counts);
+    const unsigned long long below_mask = (1ull << (8 * warp)) - 1ull;
+    double* y = yscratch + (size_t)blockIdx.x * kBootstrap * nspat;
+    const unsigned int total = (unsigned int)nframes * (unsigned int)ndisp;
+    const int p = order + 1;
+    int parity = 0;
+    while (true) {
+        if (tid == 0) s_item = atomicAdd(queue, 1u);
+        __syncthreads();
+        const unsigned int item = s_item;
+        __syncthreads();
+        if (item >= total) break;
+        const int f = item / ndisp, c = item % ndisp;
+        const size_t col = (size_t)item;
+        if (st[f].status != 0 || flag[col] != kSkyModelled) continue;
+        const int n = n_good[col];
+        double* fmodel = model + (size_t)f * frame_stride;
+        double* fmodel_err = model_err + (size_t)f * frame_stride;
+        if (n < p) {
+            for (int i = tid; i < nspat; i += kBootThreads) { fmodel[(size_t)i * ndisp + c] = NAN; fmodel_err[(size_t)i * ndisp + c] = NAN; }
+            continue;
+        }
+        for (int g = tid; g < n; g += kBootThreads) {
+            const int row = (int)good_row[col * nspat + g];
+            sh.rows[g] = (uint16_t)row;
+            sh.loc[g] = sorted[col * nspat + rank_of[col * nspat + g]];
+            sh.scl[g] = errs[(size_t)f * frame_stride + (size_t)row * ndisp + c];
+        }
+        __syncthreads();
+        // ---- the column's attempts, 256 at a time, in stream order
+        const uint32_t pos0 = rng[(size_t)f * 625 + 624];
+        const uint32_t* words = stream + (size_t)f * lay.stream_len + pos0;
+        const int need = n * (kBootstrap / 2);
+        int have = 0;
+        for (unsigned long long a = col_first[col]; a < col_last[col]; a += kBootThreads) {
+            const unsigned long long mine = a + (unsigned)tid;
+            bool acc = false;
+            double x1 = 0.0, x2 = 0.0, r2 = 0.0;
+            if (mine < col_last[col]) acc = gauss_attempt(words + 4ull * mine, &x1, &x2, &r2);
+            const unsigned ballot = __ballot_sync(0xffffffffu, acc);
+            if (lane == 0) counts8[parity * 8 + warp] = (unsigned char)__popc(ballot);
+            __syncthreads();
+            const unsigned long long all = *reinterpret_cast<const unsigned long long*>(counts8 + parity * 8);
+            const unsigned long long low = all & below_mask;
+            const int total_acc = (int)(__vsadu4((unsigned)all, 0u) + __vsadu4((unsigned)(all >> 32), 0u));
+            const int off = (int)(__vsadu4((unsigned)low, 0u) + __vsadu4((unsigned)(low >> 32), 0u)) +
+                            __popc(ballot & ((1u << lane) - 1u));
+            parity ^= 1;
+            const int ord = have + off;
+            if (acc && ord < need) {
+                const double fr = sqrt(-2.0 * log(r2) / r2);
+                const int j = ord / (kBootstrap / 2), smp = 2 * (ord % (kBootstrap / 2));
+                y[(size_t)j * kBootstrap + smp] = sh.loc[j] + sh.scl[j] * (fr * x2);         // returned first
+                y[(size_t)j * kBootstrap + smp + 1] = sh.loc[j] + sh.scl[j] * (fr * x1);     // the cached deviate
+            }
+            have += total_acc;
+        }
+        __syncthreads();
+        sky_poly_fit_column(sc, sh, n, p, nspat, ndisp, c, spatial_floor, y, fmodel, fmodel_err);
+    }
 }
 
 // ---- export -----------------------------------------------------------------------------------
