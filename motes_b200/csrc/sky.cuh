@@ -578,24 +578,56 @@ MOTES_HD void sky_poly_fit_column(const Scope& sc, const PolyShared& sh, int n, 
 #endif
         // np.median of 100: mean of the order statistics 49 and 50
         double m1 = 0.0, m2 = 0.0, psum = 0.0;
-        for (int e = ln; e < kBootstrap; e += lanes) {
-            const double v = vals[e];
-            int rank = 0;
-            for (int j2 = 0; j2 < kBootstrap; ++j2) { const double o = vals[j2]; rank += (o < v) || (o == v && j2 < e); }
-            if (rank == 49) m1 = v;
-            if (rank == 50) m2 = v;
-            psum += v;
-        }
         double mean;
 #if defined(__CUDA_ARCH__)
         if (sc.size() > 1) {
-            for (int o = 16; o > 0; o >>= 1) {
-                m1 += __shfl_xor_sync(0xffffffffu, m1, o);      // exactly one lane holds each (others 0)
-                m2 += __shfl_xor_sync(0xffffffffu, m2, o);
-                psum += __shfl_xor_sync(0xffffffffu, psum, o);
+            // warp bitonic sort of the 100 values (padded to 128 with +inf), four per lane
+            double sv[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) sv[k] = (4 * ln + k < kBootstrap) ? vals[4 * ln + k] : INFINITY;
+#pragma unroll
+            for (int size = 2; size <= 128; size <<= 1) {
+#pragma unroll
+                for (int d = size >> 1; d > 0; d >>= 1) {
+                    if (d < 4) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            if ((k & d) == 0) {
+                                const bool up = (size < 4) ? ((k & size) == 0) : ((ln & (size / 4)) == 0);
+                                const double va = sv[k], vb = sv[k | d];
+                                const bool sw = (va > vb) == up;
+                                sv[k] = sw ? vb : va;
+                                sv[k | d] = sw ? va : vb;
+                            }
+                        }
+                    } else {
+                        const int dl = d / 4;
+                        const bool up = (ln & (size / 4)) == 0 || size == 128;
+                        const bool keep_min = (((ln & dl) == 0) == up);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const double o = __shfl_xor_sync(0xffffffffu, sv[k], dl);
+                            sv[k] = keep_min ? fmin(sv[k], o) : fmax(sv[k], o);
+                        }
+                    }
+                }
+            }
+            m1 = __shfl_sync(0xffffffffu, sv[1], 12);            // sorted position 49 = lane 12, slot 1
+            m2 = __shfl_sync(0xffffffffu, sv[2], 12);            // sorted position 50
+            for (int e = ln; e < kBootstrap; e += lanes) psum += vals[e];
+            for (int o = 16; o > 0; o >>= 1) psum += __shfl_xor_sync(0xffffffffu, psum, o);
+        } else
+#endif
+        {
+            for (int e = ln; e < kBootstrap; e += lanes) {
+                const double v = vals[e];
+                int rank = 0;
+                for (int j2 = 0; j2 < kBootstrap; ++j2) { const double o = vals[j2]; rank += (o < v) || (o == v && j2 < e); }
+                if (rank == 49) m1 = v;
+                if (rank == 50) m2 = v;
+                psum += v;
             }
         }
-#endif
         mean = psum / (double)kBootstrap;
         double sq = 0.0;
         for (int e = ln; e < kBootstrap; e += lanes) { const double d = vals[e] - mean; sq += d * d; }
