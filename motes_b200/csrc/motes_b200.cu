@@ -954,8 +954,6 @@ int motes_run_frames_dev(motes_handle* h, double* data, double* errs, const uint
     MOTES_CUDA(cudaSetDevice(h->device));
     const motes_params p = *params;
     const motes_outputs o = *out;
-    cudaEvent_t ev_none;
-    MOTES_TRY(get_event(h, 0, &ev_none));
     auto upload = [&](int, int, cudaEvent_t ev) -> int {
         MOTES_CUDA(cudaEventRecord(ev, h->copy_stream));      // nothing to upload: the event is immediately reachable
         return MOTES_OK;

@@ -506,8 +506,6 @@ sky_walk_kernel(const uint16_t* __restrict__ stream, SegLayout lay, const uint32
                         }
                         target -= row_total;
                     }
-                } else {
-                    (void)__shfl_sync(0xffffffffu, incl - own, j);
                 }
                 __syncthreads();
                 P = cross;
