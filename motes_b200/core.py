@@ -1,0 +1,137 @@
+"""``core.motes`` (/root/reference/src/motes/core.py:31-306) on the GPU: read ``./inputs/reg.txt``, harvest every
+listed FITS file, run the whole extraction path on the device and, with ``save`` set, write the same product file
+the reference writes (``motes_b200.io.motesio.save_fits``).
+
+Two ways to run the frames:
+
+* ``seeds=None`` (default) - the reference's semantics: one file after the other, the bootstrap sky drawing from
+  numpy's global legacy generator exactly where the reference would (the device consumes the draws and the advanced
+  state is put back with ``np.random.set_state``).  ``np.random.seed(k); motes(args)`` therefore gives the reference's
+  sky model bit for bit.
+* ``seeds=k`` or a list - batch mode: all files of one frame shape go to the device in ONE ``run_frames`` call, file
+  ``i`` with the generator state of ``np.random.seed(seeds[i])`` (``k + i`` for an integer).  Frames are independent,
+  so each product equals what a sequential run with that seed gives.
+
+Diagnostics plots, per-file log switching and the command line stay in the reference (out of scope).
+"""
+
+from __future__ import annotations
+
+import copy
+import logging
+import os
+
+import numpy as np
+
+from . import pipeline, sky as _sky
+from .io import motesio
+
+logger = logging.getLogger("motes")
+
+
+def _frame_products(res, i, frame_dict, header_parameters, motes_args):
+    """Per-file view of batch result ``res[.][i]`` in the shapes ``core.motes`` hands to ``save_fits``; leaves
+    ``frame_dict`` / ``header_parameters`` as the reference leaves them (core.py:257-259, tracing.py:449, sky.py:383-399)."""
+    pipeline.raise_for_status(int(res["frame_status"][i]))
+    ne, ns = int(res["n_ext_bins"][i]), int(res["n_sky_bins"][i])
+    nspat = res["data"].shape[1]
+    header_parameters["seeing"] = float(res["seeing_px"][i])
+    out = {
+        "moffat_profile_parameters": list(res["median_params"][i]),
+        "data_scaling_factor": float(res["scale"][i]),
+        "moffat_parameters_all_bins": np.array(res["ext_params"][i, :ne]),
+        "final_extraction_limits": np.array(res["ext_limits"][i]),
+        "extracted": [np.array(res["spectra"][i, k]) for k in range(4)],
+        "moffat_parameters_all_sky_bins": None,
+        "sky_extraction_limits": None,
+    }
+    if motes_args.subtract_sky:
+        modelled = res["sky_flag"][i] == 0
+        out["moffat_parameters_all_sky_bins"] = np.array(res["sky_params"][i, :ns])
+        out["sky_extraction_limits"] = [np.array(res["sky_limits"][i, 0]), np.array(res["sky_limits"][i, 1])]
+        if int(motes_args.sky_order) == 0:
+            frame_dict["sky_model"] = np.tile(res["sky_model"][i][modelled], (nspat, 1))
+            frame_dict["sky_uncertainty"] = np.tile(res["sky_uncertainty"][i][modelled], (nspat, 1))
+        else:
+            frame_dict["sky_model"] = np.ascontiguousarray(res["sky_model"][i][:, modelled])
+            frame_dict["sky_uncertainty"] = np.ascontiguousarray(res["sky_uncertainty"][i][:, modelled])
+    frame_dict["data"] = res["data"][i].T          # the reference ends with the frames transposed (core.py:257-259)
+    frame_dict["errs"] = res["errs"][i].T
+    frame_dict["qual"] = np.asarray(frame_dict["qual"]).T
+    return out
+
+
+def extract_frames(frames, motes_args, rng_states=None, seeds=None, handle=None):
+    """``frames``: list of ``(frame_dict, axes_dict, header_parameters)`` of ONE shape and ONE region offset.
+    Returns one product dictionary per frame (see ``_frame_products``)."""
+    data = np.ascontiguousarray(np.stack([np.asarray(f[0]["data"], dtype=np.float64) for f in frames]))
+    errs = np.ascontiguousarray(np.stack([np.asarray(f[0]["errs"], dtype=np.float64) for f in frames]))
+    qual = np.stack([np.asarray(f[0]["qual"]) for f in frames])
+    res = pipeline.run_frames(data, errs, qual, motes_args, [f[2]["seeing"] for f in frames],
+                              [f[2]["pixel_resolution"] for f in frames], seeds=seeds, rng_states=rng_states,
+                              axes_dict=frames[0][1], copy_back=True, handle=handle)
+    products = [_frame_products(res, i, f[0], f[2], motes_args) for i, f in enumerate(frames)]
+    if "rng_states" in res:
+        for i, p in enumerate(products):
+            p["rng_state"] = res["rng_states"][i]       # numpy's RandomState after the frame
+    return products
+
+
+def _save(entry_name, harvested, products, motes_args):
+    header_parameters, frame_dict, axes_dict, original_hdu_list = harvested
+    motesio.save_fits(original_hdu_list, axes_dict, header_parameters, products["extracted"], motes_args, entry_name,
+                      products["moffat_profile_parameters"], frame_dict, products["moffat_parameters_all_bins"],
+                      products["final_extraction_limits"], products["moffat_parameters_all_sky_bins"],
+                      products["sky_extraction_limits"])
+
+
+def motes(motes_args, seeds=None, handle=None):
+    """Process every file of ``./inputs/reg.txt``.  Returns ``{input_file_name: products}``."""
+    cwd = os.getcwd()
+    logger.info("Current working directory is " + cwd)
+    files_and_regions = motesio.read_regions(cwd)
+    harvested = []
+    for entry in files_and_regions:
+        logger.info("Begin MOTES processing for ./inputs/" + entry[-1])
+        h = motesio.data_harvest(cwd + "/inputs/" + entry[-1], entry[:4])
+        h[1]["original_data"] = copy.deepcopy(h[1]["data"])
+        h[1]["original_errs"] = copy.deepcopy(h[1]["errs"])
+        harvested.append(h)
+    results = {}
+
+    if seeds is None:                                  # reference semantics: sequential, global generator
+        for entry, h in zip(files_and_regions, harvested):
+            header_parameters, frame_dict, axes_dict, _ = h
+            state = rest = None
+            if motes_args.subtract_sky:
+                state, rest = _sky._take_global_rng()
+                if int(motes_args.sky_order) > 0 and rest[1]:
+                    raise ValueError("np.random holds a cached Gaussian deviate; seed the generator before a polynomial sky fit")
+            products = extract_frames([(frame_dict, axes_dict, header_parameters)], motes_args,
+                                      rng_states=None if state is None else state[None].copy(), handle=handle)[0]
+            if state is not None:
+                _sky._put_global_rng(products["rng_state"], rest)
+            results[entry[-1][:-5]] = products
+            if motes_args.save:
+                _save(entry[-1][:-5], h, products, motes_args)
+        logger.info("MOTES Processing completed.")
+        return results
+
+    seeds = [int(seeds) + i for i in range(len(harvested))] if np.isscalar(seeds) else [int(s) for s in seeds]
+    if len(seeds) != len(harvested):
+        raise ValueError("one seed per line of reg.txt is required")
+    groups = {}
+    for i, h in enumerate(harvested):
+        key = (h[1]["data"].shape, h[2]["data_spatial_floor"], int(h[2]["wavelength_start"]))
+        groups.setdefault(key, []).append(i)
+    for members in groups.values():
+        frames = [(harvested[i][1], harvested[i][2], harvested[i][0]) for i in members]
+        outs = extract_frames(frames, motes_args, seeds=[seeds[i] for i in members] if motes_args.subtract_sky else None,
+                              handle=handle)
+        for i, products in zip(members, outs):
+            name = files_and_regions[i][-1][:-5]
+            results[name] = products
+            if motes_args.save:
+                _save(name, harvested[i], products, motes_args)
+    logger.info("MOTES Processing completed.")
+    return results

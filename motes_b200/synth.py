@@ -173,6 +173,33 @@ def default_args(**over) -> SimpleNamespace:
     return ns
 
 
+def write_gmos_fits(path, spec: FrameSpec, dtype=">f8", crval=500.0, step=0.1, raw_iq="70-percentile", flipped=False):
+    """Write ``make_frame(spec)`` as a GMOS-style multi-extension FITS file (primary + MDF + SCI + VAR + DQ, the layout
+    ``harvest_gmos`` reads, /root/reference/src/motes/io/gmosio.py:38-42): SCI = data, VAR = errs**2, DQ = 16 in chip
+    gaps, 1 on other bad pixels.  ``flipped`` stores the planes red to blue with CD1_1 < 0 (DRAGONS).  Real GMOS
+    planes are float32 (``dtype=">f4"``); float64 keeps the frame bit for bit.  Returns the frame dictionaries."""
+    from .io import fits
+    frame, axes, header = make_frame(spec)
+    gap = np.zeros(frame["data"].shape, dtype=bool)
+    for first, width in spec.chip_gaps:
+        gap[:, first:first + width] = True
+    dq = np.where(gap, 16, np.where(frame["qual"] == 0, 1, 0)).astype(np.int16)
+    sci, var = frame["data"].astype(dtype), (frame["errs"] * frame["errs"]).astype(dtype)
+    if flipped:
+        sci, var, dq = (np.ascontiguousarray(np.flip(a, axis=1)) for a in (sci, var, dq))
+    primary = fits.PrimaryHDU()
+    for key, value in (("INSTRUME", "GMOS-S"), ("OBJECT", "synthetic target"), ("EXPTIME", 300.0), ("RAWIQ", raw_iq)):
+        primary.header[key] = value
+    mdf = fits.BinTableHDU(fits.Table(np.array([[1.0, 2.0]]), names=("slitpos_mx", "slitpos_my"), dtype=("f4", "f4")), name="MDF")
+    planes = [fits.ImageHDU(sci, name="SCI"), fits.ImageHDU(var, name="VAR"), fits.ImageHDU(dq, name="DQ")]
+    wcs = (("CRPIX1", float(spec.ndisp) if flipped else 1.0), ("CRVAL1", float(crval)), ("CD1_1", -float(step) if flipped else float(step)),
+           ("CUNIT1", "nm"), ("BUNIT", "electron"), ("PIXSCALE", float(spec.pixel_resolution)))
+    for key, value in wcs:
+        planes[0].header[key] = value
+    fits.HDUList([primary, mdf] + planes).writeto(path, overwrite=True)
+    return frame, axes, header
+
+
 def frame_digest(frame_dict: dict) -> str:
     """sha256 over the bytes of data, errs and qual (little-endian float64)."""
     h = hashlib.sha256()

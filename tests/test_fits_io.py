@@ -1,0 +1,165 @@
+"""FITS shim and the harvest / save mirrors - CPU only.
+
+* the shim writes standard-conforming files (2880-byte blocks, fixed-format cards, big-endian data) and reads back
+  what it wrote: images of every BITPIX, the unsigned convention, BSCALE/BZERO, binary tables, long strings, HIERARCH;
+* ``motes_b200.io.gmosio.harvest_gmos`` / ``motesio.data_harvest`` / ``motesio.save_fits`` behave like the reference's
+  functions of the same name; where ``/root/reference`` exists (the build container) they are run side by side on the
+  same files and must agree bit for bit (the product file byte for byte, but for the UT timestamp card).
+"""
+import copy
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from motes_b200.io import fits
+
+REFERENCE_SRC = "/root/reference/src"
+
+
+def test_blocks_cards_and_round_trip(tmp_path):
+    h = fits.Header()
+    h["INSTRUME"] = ("GMOS-S", "instrument")
+    h["EXPTIME"] = 300.0
+    h["FLAG"] = True
+    h["UNDEF"] = None
+    h["TINY"] = 1e-7
+    h["NEG"] = (-42, "an integer")
+    h["LONGSTR"] = "a'b" * 40
+    h["HIERARCH ESO TEL AMBI FWHM START"] = (0.81, "seeing")
+    h["COMMENT"] = "free text"
+    images = {"F4": np.linspace(-1, 1, 12, dtype=">f4").reshape(3, 4), "F8": np.arange(6.0).reshape(2, 3),
+              "I2": np.arange(-3, 3, dtype=np.int16).reshape(2, 3), "I4": np.array([[2 ** 31 - 1, -2 ** 31]], dtype=np.int32),
+              "I8": np.array([[2 ** 62, -1]], dtype=np.int64), "U1": np.array([[0, 255]], dtype=np.uint8),
+              "U2": np.array([[0, 1, 65535]], dtype=np.uint16), "U4": np.array([[0, 2 ** 32 - 1]], dtype=np.uint32)}
+    hdus = [fits.PrimaryHDU(header=h)] + [fits.ImageHDU(a, name=n) for n, a in images.items()]
+    table = fits.Table(np.array([[1.5, 2, 3], [4.5, 5, 6]]), names=("a", "b", "c"), dtype=("f8", "i4", "i2"))
+    table["s"] = np.array(["xy", "z"])
+    hdus.append(fits.BinTableHDU(table, name="TAB"))
+    path = tmp_path / "a.fits"
+    fits.HDUList(hdus).writeto(path)
+    raw = path.read_bytes()
+    assert len(raw) % 2880 == 0
+    assert raw[:30] == b"SIMPLE  =                    T"                      # fixed format: value ends in column 30
+    assert b"INSTRUME= 'GMOS-S  '           / instrument" in raw[:2880]
+    assert b"HIERARCH ESO TEL AMBI FWHM START = 0.81 / seeing" in raw[:2880]
+    with pytest.raises(OSError):
+        fits.HDUList(hdus).writeto(path)                                      # no silent overwrite (astropy's rule)
+
+    with fits.open(path) as hdul:
+        p = hdul[0].header
+        assert (p["INSTRUME"], p["EXPTIME"], p["FLAG"], p["UNDEF"], p["TINY"], p["NEG"]) == ("GMOS-S", 300.0, True, None, 1e-7, -42)
+        assert p["LONGSTR"] == "a'b" * 40 and p["ESO TEL AMBI FWHM START"] == 0.81 and p["COMMENT"] == ["free text"]
+        assert p.comments["NEG"] == "an integer"
+        for name, arr in images.items():
+            got = hdul[name].data
+            assert got.shape == arr.shape and np.array_equal(got, arr), name
+            assert got.dtype.kind == arr.dtype.kind and got.dtype.itemsize == arr.dtype.itemsize, name
+        assert hdul["F4"].data.dtype == np.dtype(">f4")                       # big-endian, as astropy hands it over
+        t = hdul["TAB"].data
+        assert np.array_equal(t["a"], [1.5, 4.5]) and np.array_equal(t["b"], [2, 5]) and np.array_equal(t["c"], [3, 6])
+        assert [x.decode().strip() for x in t["s"]] == ["xy", "z"]
+        assert (hdul["TAB"].header["TFORM1"], hdul["TAB"].header["TFORM2"], hdul["TAB"].header["TFORM3"]) == ("D", "J", "I")
+
+        # pass-through: untouched HDUs go back byte for byte, renamed ones keep their data
+        clone = copy.deepcopy(hdul)
+        clone["I2"].header["EXTNAME"] = "ORIG_I2"
+        fits.HDUList([fits.PrimaryHDU(), clone["ORIG_I2"], clone["TAB"]]).writeto(tmp_path / "b.fits")
+    with fits.open(tmp_path / "b.fits") as again:
+        assert np.array_equal(again["ORIG_I2"].data, images["I2"])
+        assert np.array_equal(again["TAB"].data["a"], [1.5, 4.5])
+
+
+def test_scaled_integers_are_read_as_physical_values(tmp_path):
+    hdu = fits.ImageHDU(np.array([[0, 100, -100]], dtype=np.int16), name="SCALED")
+    blob = bytearray(hdu.tobytes(primary=False))
+    text = blob[:2880].decode()
+    cards = [text[i:i + 80] for i in range(0, 2880, 80)]
+    end = next(i for i, c in enumerate(cards) if c.startswith("END"))
+    cards[end:end] = [f"{'BSCALE  =                  0.5':<80}", f"{'BZERO   =                 10.0':<80}"]
+    head = "".join(cards)[:2880]
+    path = tmp_path / "s.fits"
+    path.write_bytes(fits.PrimaryHDU().tobytes(primary=True) + head.encode() + bytes(blob[2880:]))
+    with fits.open(path) as hdul:
+        assert np.allclose(hdul["SCALED"].data, [[10.0, 60.0, -40.0]])
+        assert "BSCALE" not in hdul["SCALED"].header
+
+
+def _reference_io():
+    if not os.path.isdir(REFERENCE_SRC):
+        pytest.skip("the reference tree is only present in the build container")
+    from motes_b200.io import standin
+    standin.install()
+    if REFERENCE_SRC not in sys.path:
+        sys.path.insert(0, REFERENCE_SRC)
+    import motes.io.motesio as ref_motesio
+    import motes.io.gmosio as ref_gmosio
+    return ref_motesio, ref_gmosio
+
+
+@pytest.mark.parametrize("dtype,flipped", [(">f8", False), (">f4", True)])
+def test_harvest_matches_reference(tmp_path, dtype, flipped):
+    ref_motesio, _ = _reference_io()
+    from motes_b200 import synth
+    from motes_b200.io import motesio
+    path = str(tmp_path / "in.fits")
+    frame, _, _ = synth.write_gmos_fits(path, synth.config_spec("T1", seed=5), dtype=dtype, flipped=flipped)
+    region = [3, 2, 505, 560]
+    want = ref_motesio.data_harvest(path, region)
+    got = motesio.data_harvest(path, region)
+    assert got[0] == want[0]                                                  # header_dict
+    for key in ("data", "errs", "qual"):
+        assert got[1][key].dtype == want[1][key].dtype and np.array_equal(got[1][key], want[1][key], equal_nan=True), key
+    for key, val in want[2].items():
+        assert np.array_equal(got[2][key], val), key
+    if dtype == ">f8" and not flipped:                                        # float64 planes carry the frame bit for bit
+        cols = slice(int(want[2]["wavelength_start"]), int(want[2]["wavelength_end"]) + 1)
+        assert np.array_equal(got[1]["data"], frame["data"][3:95, cols])
+
+
+def test_save_fits_matches_reference_byte_for_byte(tmp_path, monkeypatch):
+    ref_motesio, _ = _reference_io()
+    from motes_b200 import synth
+    from motes_b200.io import motesio
+    path = str(tmp_path / "in.fits")
+    synth.write_gmos_fits(path, synth.config_spec("T2", seed=6))
+    rng = np.random.default_rng(3)
+    outputs = {}
+    for label, mod in (("reference", ref_motesio), ("mirror", motesio)):
+        header, frame, axes, original = mod.data_harvest(path, [0, 0, 501, 539])
+        nd, ns = axes["dispersion_axis_length"], frame["data"].shape[0]
+        gen = np.random.default_rng(3)
+        extracted = [gen.normal(size=nd) for _ in range(4)]
+        bins = np.column_stack([gen.normal(size=(5, 6)), np.arange(5) * 10.0, np.arange(5) * 10.0 + 10])
+        frame["sky_model"], frame["sky_uncertainty"] = gen.normal(size=(ns, nd)), gen.normal(size=(ns, nd))
+        header["seeing"] = 4.321
+        work = tmp_path / label
+        work.mkdir()
+        monkeypatch.chdir(work)
+        mod.save_fits(original, axes, header, extracted, synth.default_args(save=True), "in", list(gen.normal(size=6)), frame,
+                      bins.copy(), gen.normal(size=(2, nd)), bins.copy(), [gen.normal(size=nd), gen.normal(size=nd)])
+        files = [f for f in os.listdir(work) if f.endswith(".fits")]
+        assert files == ["min_501:539_0:64.fits"]
+        outputs[label] = (work / files[0]).read_bytes()
+    a, b = outputs["reference"], outputs["mirror"]
+    assert len(a) == len(b)
+    diff = np.flatnonzero(np.frombuffer(a, dtype=np.uint8) != np.frombuffer(b, dtype=np.uint8))
+    cards = {int(i) // 80 for i in diff}
+    assert all(a[c * 80:c * 80 + 8] == b"UTXTIME " for c in cards), [a[c * 80:c * 80 + 80] for c in cards][:3]
+
+
+def test_read_regions_checks(tmp_path, monkeypatch):
+    from motes_b200.io import motesio
+    monkeypatch.chdir(tmp_path)
+    with pytest.raises(FileNotFoundError):
+        motesio.read_regions(str(tmp_path))
+    (tmp_path / "inputs").mkdir()
+    reg = tmp_path / "inputs" / "reg.txt"
+    reg.write_text("3,2,505,560,b.fits\n0,0,400,900,a.fits\n3,2,505,560,b.fits\n")
+    assert motesio.read_regions(str(tmp_path)) == [[3, 2, 505, 560, "b.fits"], [0, 0, 400, 900, "a.fits"]]
+    for bad, exc in (("3,2,505,560,b.fit", RuntimeError), ("3,2,505,b.fits", RuntimeError), ("3,,505,560,b.fits", RuntimeError),
+                     ("3,x,505,560,b.fits", ValueError)):
+        reg.write_text(bad + "\n")
+        with pytest.raises(exc):
+            motesio.read_regions(str(tmp_path))
