@@ -195,7 +195,7 @@ def run_reference_arm(a):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
@@ -463,14 +463,33 @@ def run_b200_arm(a):
         if not a.no_cpu_baseline and world == 1:
             crop = a.cpu_sample_columns or 2048
             line["cpu_baseline"] = cpu_baseline_single(ns, nd, min(crop, nd))
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+RESULT_FD = None
+
+
+def emit(line: dict) -> None:
+    """The one JSON line of the run, on the process's original stdout."""
+    text = (json.dumps(line) + "\n").encode()
+    if RESULT_FD is None:
+        sys.stdout.write(text.decode())
+        sys.stdout.flush()
+    else:
+        os.write(RESULT_FD, text)
+
+
 def main():
+    global RESULT_FD
     a = parse()
+    # Native libraries write to file descriptor 1 as well (NCCL prints its version banner there): point fd 1 at
+    # stderr for the run and keep the original for the result line, so stdout carries exactly one JSON line.
+    sys.stdout.flush()
+    RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     if a.impl == "reference":
         run_reference_arm(a)
     else:

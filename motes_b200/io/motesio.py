@@ -14,7 +14,7 @@ import os
 
 import numpy as np
 
-from . import gmosio
+from . import gmosio, instruments
 
 if os.environ.get("MOTES_B200_FITS", "") == "shim":
     from . import fits
@@ -29,11 +29,14 @@ else:
 
 logger = logging.getLogger("motes")
 
-# INSTRUME value -> (harvest, save hook).  Upstream also lists FORS2, X-shooter and FLOYDS, whose harvesters still
-# have the pre-1.0 two-argument signature and cannot be called by data_harvest.
+# INSTRUME value -> (harvest, save hook), the two dispatch tables of the reference (motesio.py:52-59, 509-516).
 INSTRUMENTS = {
+    "en06": (instruments.harvest_floyds, instruments.save_passthrough),
+    "en12": (instruments.harvest_floyds, instruments.save_passthrough),
+    "FORS2": (instruments.harvest_fors2, instruments.save_passthrough),
     "GMOS-N": (gmosio.harvest_gmos, gmosio.save_gmos),
     "GMOS-S": (gmosio.harvest_gmos, gmosio.save_gmos),
+    "XSHOOTER": (instruments.harvest_xshoo, instruments.save_passthrough),
 }
 
 BIN_COLUMNS = ("amplitude", "center", "alpha", "beta", "background_level", "background_grad", "bin_limit_lo", "bin_limit_hi")

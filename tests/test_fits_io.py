@@ -163,3 +163,58 @@ def test_read_regions_checks(tmp_path, monkeypatch):
         reg.write_text(bad + "\n")
         with pytest.raises(exc):
             motesio.read_regions(str(tmp_path))
+
+
+def _instrument_file(tmp_path, instrument):
+    """A small synthetic frame in the layout the instrument's harvester reads."""
+    rng = np.random.default_rng(11)
+    data = rng.normal(100.0, 5.0, size=(12, 40))
+    primary = fits.Header()
+    primary["INSTRUME"] = instrument
+    primary["OBJECT"] = "some target"
+    primary["CRVAL1"] = 3300.5
+    if instrument == "FORS2":
+        for key, value in (("HIERARCH ESO DET WIN1 BINY", 2), ("HIERARCH ESO INS COLL NAME", "COLL_SR"),
+                           ("HIERARCH ESO INS SHUT EXPTIME", 600.0), ("HIERARCH ESO TEL AMBI FWHM START", 0.71),
+                           ("HIERARCH ESO TEL AMBI FWHM END", 0.93), ("BUNIT", "adu"), ("CD1_1", 3.3)):
+            primary[key] = value
+        hdus = [fits.PrimaryHDU(data.astype(">f4"), header=primary), fits.ImageHDU((data * 0.04).astype(">f4"))]
+    elif instrument == "XSHOOTER":
+        for key, value in (("CDELT2", 0.16), ("EXPTIME", 900.0), ("HIERARCH ESO TEL AMBI FWHM START", 0.8),
+                           ("HIERARCH ESO TEL AMBI FWHM END", 1.0), ("BUNIT", "erg/s/cm2/Angstrom"), ("CDELT1", 0.06)):
+            primary[key] = value
+        data[3, 4] = np.nan
+        flags = np.zeros(data.shape, dtype=np.int32)
+        flags[0, :6] = (4194304, 8388608, 16777216, 1, 4194304 + 1, 1073741824)
+        hdus = [fits.PrimaryHDU(data, header=primary), fits.ImageHDU(np.abs(data) ** 0.5), fits.ImageHDU(flags)]
+    else:
+        for key, value in (("RDNOISE", 3.7), ("DARKCURR", 0.2), ("PIXSCALE", 0.337), ("EXPTIME", 1800.0), ("AGFWHM", 1.9),
+                           ("WAT2_001", "wtype=linear label=Wavelength units=Angstroms"), ("CD1_1", 3.51)):
+            primary[key] = value
+        hdus = [fits.PrimaryHDU(np.abs(data), header=primary)]
+    path = str(tmp_path / f"{instrument}.fits")
+    fits.HDUList(hdus).writeto(path)
+    return path
+
+
+@pytest.mark.parametrize("instrument,module,function", [("FORS2", "forsio", "harvest_fors2"), ("XSHOOTER", "xshooio", "harvest_xshoo"),
+                                                        ("en06", "floydsio", "harvest_floyds")])
+def test_other_harvesters_match_upstream_code(tmp_path, instrument, module, function, capsys):
+    """Upstream's FORS2 / X-shooter / FLOYDS harvesters still take (hdul, primary_header) and return six values; the
+    one-argument versions here must hand over the same frames, dictionary and axis."""
+    _reference_io()
+    import importlib
+    from motes_b200.io import motesio
+    stale = getattr(importlib.import_module(f"motes.io.{module}"), function)
+    path = _instrument_file(tmp_path, instrument)
+    with fits.open(path) as hdul:
+        data, errs, qual, _original_qual, header_dict, axis = stale(hdul, hdul[0].header)
+    with fits.open(path) as hdul:
+        got = motesio.INSTRUMENTS[instrument][0](hdul)
+    assert got[3] == header_dict
+    assert np.array_equal(got[4], axis)
+    for a, b in zip(got[:3], (data, errs, qual)):
+        assert a.dtype == b.dtype and np.array_equal(a, b, equal_nan=True)
+    # and through data_harvest, which the upstream functions cannot be reached from
+    header, frame, axes, _ = motesio.data_harvest(path, [1, 1, float(axis[2]), float(axis[-3])])
+    assert frame["data"].shape == (11, len(axis) - 4) and axes["wavelength_start"] == 2 and header["object"] == "some_target"
