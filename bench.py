@@ -421,17 +421,19 @@ def run_b200_arm(a):
             launches_dom = max(1.0, stage_ms[dominant]["launches_per_step"])
             achieved = alg_bytes_per_col * F * nd / dur / 1e9
             traffic = None                  # DRAM bytes per launch of that kernel from the committed ncu capture
+            ncu_util = None                 # issue-slot / FP64-pipe utilisation of that kernel, same capture
             try:
                 tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
                 w = tj["workload"]
                 if (w["frames_per_gpu"], w["nspat"], w["ndisp"]) == (F, ns, nd):
                     traffic = tj["dram_bytes_per_launch"].get(dominant)
+                    ncu_util = tj.get("ncu_utilisation", {}).get(dominant)
             except Exception:
                 pass
             roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                         "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                         "algorithmic_bytes_per_column": alg_bytes_per_col,
-                        "kernel_ms_per_launch": 1e3 * dur / launches_dom,
+                        "kernel_ms_per_launch": 1e3 * dur / launches_dom, "ncu_utilisation": ncu_util,
                         "note": "whole-path algorithmic bytes (17*nspat+80 per column) over the dominant stage's "
                                 "CUDA-event time; the path is FP64/integer-latency bound, not HBM bound (DESIGN.md)"}
         total_stage = sum(v["ms_per_step"] for v in stage_ms.values()) or 1.0
