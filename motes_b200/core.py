@@ -23,7 +23,7 @@ import os
 
 import numpy as np
 
-from . import pipeline, sky as _sky
+from . import common, pipeline, sky as _sky, tracing
 from .io import motesio
 
 logger = logging.getLogger("motes")
@@ -58,7 +58,25 @@ def _frame_products(res, i, frame_dict, header_parameters, motes_args):
     frame_dict["data"] = res["data"][i].T          # the reference ends with the frames transposed (core.py:257-259)
     frame_dict["errs"] = res["errs"][i].T
     frame_dict["qual"] = np.asarray(frame_dict["qual"]).T
+    out["frame_dict"], out["header_parameters"] = frame_dict, header_parameters
     return out
+
+
+def fit_diagnostics(data, axes_dict, bin_parameters, handle=None):
+    """The numbers behind the reference's ``-dm`` plots (core.py:214-229, diagnostics.plot_fitted_spatial_profile), without
+    the plotting: per bin the median spatial profile the fit saw (device, ``tracing.bin_profiles``) and the fitted
+    Moffat curve on the 5x oversampled spatial axis.  ``data`` is the ``(nspat, ndisp)`` frame the bins were fitted on
+    (the harvested frame for sky bins, the sky-subtracted one for extraction bins); ``bin_parameters`` is the
+    ``(nbins, 8)`` table with the bin edges in columns 6-7."""
+    bin_parameters = np.asarray(bin_parameters)
+    edges = (bin_parameters[:, 6:8] - int(axes_dict["wavelength_start"])).astype(np.int32)
+    return {
+        "bin_edges": edges,
+        "spatial_axis": axes_dict["spatial_axis"] + axes_dict["data_spatial_floor"],
+        "bin_profiles": tracing.bin_profiles(data, edges, handle=handle),
+        "hi_resolution_spatial_axis": axes_dict["hi_resolution_spatial_axis"] + axes_dict["data_spatial_floor"],
+        "fitted_curves": np.array([common.moffat(row[:6], axes_dict["hi_resolution_spatial_axis"]) for row in bin_parameters]),
+    }
 
 
 def extract_frames(frames, motes_args, rng_states=None, seeds=None, handle=None):
@@ -71,6 +89,8 @@ def extract_frames(frames, motes_args, rng_states=None, seeds=None, handle=None)
                               [f[2]["pixel_resolution"] for f in frames], seeds=seeds, rng_states=rng_states,
                               axes_dict=frames[0][1], copy_back=True, handle=handle)
     products = [_frame_products(res, i, f[0], f[2], motes_args) for i, f in enumerate(frames)]
+    for p, f in zip(products, frames):
+        p["axes_dict"] = f[1]
     if "rng_states" in res:
         for i, p in enumerate(products):
             p["rng_state"] = res["rng_states"][i]       # numpy's RandomState after the frame

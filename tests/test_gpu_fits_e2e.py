@@ -129,3 +129,26 @@ def test_batch_mode_equals_sequential_runs(tmp_path, monkeypatch):
         for k in range(4):
             assert np.array_equal(batch[n]["extracted"][k], single["extracted"][k], equal_nan=True), (n, k)
         assert np.array_equal(batch[n]["moffat_parameters_all_bins"], single["moffat_parameters_all_bins"])
+
+
+def test_fit_diagnostics_numbers(tmp_path, monkeypatch):
+    """The arrays behind the reference's -dm plots: per-bin median profiles (chip-gap columns left out,
+    tracing.py:505-507) and the fitted curves on the oversampled axis."""
+    import make_golden_fits as mg
+    from motes_b200 import common, core
+    args = mg.write_case_inputs(str(tmp_path), "gmos_t1")
+    args.save = False
+    monkeypatch.chdir(tmp_path)
+    np.random.seed(1)
+    out = core.motes(args)["gmos_t1"]
+    frame, axes = out["frame_dict"], out["axes_dict"]
+    for table, data in ((out["moffat_parameters_all_bins"], frame["data"].T), (out["moffat_parameters_all_sky_bins"], frame["original_data"])):
+        diag = core.fit_diagnostics(data, axes, table)
+        assert diag["bin_profiles"].shape == (len(table), axes["spataxislen"])
+        data = np.asarray(data, dtype=np.float64)
+        for k in (0, len(table) // 2, len(table) - 1):
+            lo, hi = diag["bin_edges"][k]
+            cols = data[:, lo:hi]
+            cols = cols[:, np.nanmedian(cols, axis=0) != 1]
+            assert np.array_equal(diag["bin_profiles"][k], np.nanmedian(cols, axis=1))
+            assert np.array_equal(diag["fitted_curves"][k], common.moffat(table[k][:6], axes["hi_resolution_spatial_axis"]))
