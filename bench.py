@@ -435,7 +435,9 @@ def run_b200_arm(a):
                         "algorithmic_bytes_per_column": alg_bytes_per_col,
                         "kernel_ms_per_launch": 1e3 * dur / launches_dom, "ncu_utilisation": ncu_util,
                         "note": "whole-path algorithmic bytes (17*nspat+80 per column) over the dominant stage's "
-                                "CUDA-event time; the path is FP64/integer-latency bound, not HBM bound (DESIGN.md)"}
+                                "CUDA-event time (stage times are taken in separate profiling steps, each kernel alone: the "
+                                "timed steps overlap the generator with the localisation stages); the path is "
+                                "FP64/integer-latency bound, not HBM bound (DESIGN.md)"}
         total_stage = sum(v["ms_per_step"] for v in stage_ms.values()) or 1.0
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,

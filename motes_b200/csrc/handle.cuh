@@ -83,6 +83,24 @@ enum Stage { ST_ROW_MEDIAN = 0, ST_MEDIAN_FIT, ST_COLUMN_STATS, ST_BINS, ST_BIN_
 struct StageSpan { cudaEvent_t a, b; int stage; };
 }  // namespace motes
 
+namespace motes {
+struct SegLayout {                 // segmented generator replay (skyseg.cuh): per call, host-computed
+    int log2_stride;
+    uint32_t stride;               // words per segment
+    int segs;                      // segments allocated per frame (K)
+    unsigned long long stream_len; // 16-bit words per frame (padded for the walk's prefetch)
+    unsigned long long sub_len;    // running-count entries per frame
+    int snaps;                     // snapshots per frame
+};
+struct BootPlan {                  // how a batch's order-0 bootstrap is laid out (motes_b200.cu: boot_plan)
+    bool ok = false;
+    bool hoisted = false;          // the generator part is already running on the second stream
+    SegLayout lay{};
+    int wave = 0;                  // frames per wave
+    int log2_stride = 0;
+};
+}  // namespace motes
+
 struct motes_handle {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -109,6 +127,9 @@ struct motes_handle {
     motes::Scratch jump_polys;   // device copy of the MT19937 jump polynomial table (mtjump.hpp)
     bool jump_ready = false;
     size_t stream_budget = 0;    // bytes the segmented bootstrap may use for generator streams (0 = auto)
+    bool hoist = true;           // MOTES_B200_HOIST=0: generate the bootstrap stream where it is consumed
+    motes::BootPlan boot;
+    cudaEvent_t ev_hoist[2] = {nullptr, nullptr};
     std::vector<motes::StageSpan> spans;
     double stage_ms[motes::ST_COUNT] = {0};
     long long stage_launches[motes::ST_COUNT] = {0};
@@ -119,7 +140,7 @@ struct StageTimer {
     motes_handle* h;
     int idx = -1;
     StageTimer(motes_handle* handle, int stage) : h(handle) {
-        if (!h->profiling) return;
+        if (!h->profiling || stage < 0) return;
         StageSpan s;
         s.stage = stage;
         if (cudaEventCreate(&s.a) != cudaSuccess || cudaEventCreate(&s.b) != cudaSuccess) return;

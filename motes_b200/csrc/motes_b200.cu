@@ -305,16 +305,19 @@ static size_t sky_colh_smem(int nspat, bool packed) {
     return (size_t)2 * kBootstrap * 8 + (size_t)(kBootstrap * stride) * 4 + (size_t)nspat * 2 + 64;
 }
 
-static int stage_bootstrap_segmented(motes_handle* h, Batch& b, uint32_t* rng, bool* done) {
-    *done = false;
+// Layout of the segmented replay for a batch: frames per wave, segment stride, buffers (all from the a-priori bound
+// 100 * ndisp * 2^ceil(log2 nspat) words per frame, so it can be fixed before the sky pixels are known).
+// plan->ok = false: the layout does not fit (the caller falls back to the one-CTA-per-frame replay).
+static int boot_plan(motes_handle* h, const Batch& b, BootPlan* plan) {
+    plan->ok = false;
+    plan->hoisted = false;
     const JumpTable& table = jump_table();
     if (!table.ok) return MOTES_OK;
     unsigned long long p2 = 1;
     while (p2 < (unsigned long long)b.nspat) p2 <<= 1;
     const unsigned long long bound = 624ull + 100ull * (unsigned long long)b.ndisp * p2 + kSegSlack;
     if (bound >= 0xff000000ull) return MOTES_OK;
-    const size_t col_smem = sky_col_smem(b.nspat);
-    if (col_smem > h->smem_optin) return MOTES_OK;
+    if (sky_col_smem(b.nspat) > h->smem_optin) return MOTES_OK;
     // per-frame footprint is dominated by the 16-bit stream: 2 bytes per generator word
     size_t budget = h->stream_budget;
     if (budget == 0) {
@@ -364,8 +367,85 @@ static int stage_bootstrap_segmented(motes_handle* h, Batch& b, uint32_t* rng, b
         if (wave == 1) return MOTES_OK;                 // the caller falls back to the one-CTA-per-frame replay
         wave = (wave + 1) / 2;
     }
+    plan->lay = lay;
+    plan->wave = wave;
+    plan->log2_stride = s;
+    plan->ok = true;
+    return MOTES_OK;
+}
+
+// Generator part of the replay for frames [f0, f0 + nf) on stream `cs`: which segments are needed (`b` = nullptr: all
+// of them - the sky pixels are not known yet), the segment windows by jump-ahead, the 16-bit stream and its snapshots.
+static int boot_generate(motes_handle* h, cudaStream_t cs, const Batch* b, int ndisp, const BootPlan& plan, uint32_t* rng_w,
+                         int f0, int nf, bool timed) {
+    const SegLayout& lay = plan.lay;
     uint16_t* stream = h->work[W_STREAM].as<uint16_t>();
     uint32_t* windows = h->work[W_WINDOWS].as<uint32_t>();
+    uint32_t* snaps = h->work[W_SNAPS].as<uint32_t>();
+    int32_t* seg_need = h->work[W_SEGI].as<int32_t>();
+    const uint32_t* polys = h->jump_polys.as<uint32_t>();
+    const size_t jump_smem = (size_t)(kJumpStreamWords + 624) * sizeof(uint32_t);
+    MOTES_CUDA(cudaFuncSetAttribute(mt_jump_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jump_smem));
+    {
+        StageTimer t_jump(h, timed ? ST_BOOT_JUMP : -1);
+        if (b) {
+            const size_t c0 = (size_t)f0 * ndisp;
+            seg_plan_kernel<<<nf, 256, 0, cs>>>(rng_w, ndisp, b->n_good + c0, b->sky_flag + c0, lay, seg_need);
+        } else {
+            seg_plan_all_kernel<<<(nf + 255) / 256, 256, 0, cs>>>(nf, lay, seg_need);
+        }
+        MOTES_LAUNCHED(h);
+        MOTES_CUDA(cudaMemsetAsync(windows, 0, (size_t)nf * lay.segs * 624 * sizeof(uint32_t), cs));
+        for (int r = 0; (1 << r) < lay.segs; ++r) {
+            const int count = ((1 << (r + 1)) <= lay.segs ? (1 << r) : lay.segs - (1 << r));
+            mt_jump_kernel<<<dim3(count, nf, kJumpParts), kJumpThreads, jump_smem, cs>>>(
+                rng_w, windows, lay.segs, r, polys + (size_t)(plan.log2_stride + r) * kJumpWords32, seg_need);
+            MOTES_LAUNCHED(h);
+        }
+    }
+    StageTimer t_stream(h, timed ? ST_BOOT_STREAM : -1);
+    mt_stream_kernel<uint16_t><<<dim3(lay.segs, nf), 256, 0, cs>>>(rng_w, windows, lay, seg_need, stream, snaps);
+    MOTES_LAUNCHED(h);
+    return MOTES_OK;
+}
+
+// Start the generator of a batch on the second stream before anything is known about its sky pixels: the stream only
+// depends on the frames' generator states, and its kernels (integer issue bound) share the SMs with the latency-bound
+// localisation stages that run meanwhile on the main stream.  Only when one wave covers the batch.
+static int boot_hoist(motes_handle* h, const Batch& b, uint32_t* rng) {
+    h->boot.ok = false;
+    h->boot.hoisted = false;
+    if (!h->hoist || h->profiling || h->boot_mode != 0 || h->chunks > 1 || !rng) return MOTES_OK;
+    BootPlan plan;
+    MOTES_TRY(boot_plan(h, b, &plan));
+    if (!plan.ok || plan.wave != b.F) return MOTES_OK;
+    if (!h->ev_hoist[0]) {
+        MOTES_CUDA(cudaEventCreateWithFlags(&h->ev_hoist[0], cudaEventDisableTiming));
+        MOTES_CUDA(cudaEventCreateWithFlags(&h->ev_hoist[1], cudaEventDisableTiming));
+    }
+    MOTES_CUDA(cudaEventRecord(h->ev_hoist[0], h->stream));                // the generator states are on the device
+    MOTES_CUDA(cudaStreamWaitEvent(h->lane1_stream, h->ev_hoist[0], 0));
+    MOTES_TRY(boot_generate(h, h->lane1_stream, nullptr, b.ndisp, plan, rng, 0, b.F, false));
+    MOTES_CUDA(cudaEventRecord(h->ev_hoist[1], h->lane1_stream));
+    plan.hoisted = true;
+    h->boot = plan;
+    return MOTES_OK;
+}
+
+static int stage_bootstrap_segmented(motes_handle* h, Batch& b, uint32_t* rng, bool* done) {
+    *done = false;
+    BootPlan plan = h->boot;
+    if (plan.hoisted) {
+        MOTES_CUDA(cudaStreamWaitEvent(h->stream, h->ev_hoist[1], 0));
+        h->boot.hoisted = false;
+    } else {
+        MOTES_TRY(boot_plan(h, b, &plan));
+        if (!plan.ok) return MOTES_OK;
+    }
+    const SegLayout lay = plan.lay;
+    const int wave = plan.wave;
+    const size_t col_smem = sky_col_smem(b.nspat);
+    uint16_t* stream = h->work[W_STREAM].as<uint16_t>();
     uint32_t* snaps = h->work[W_SNAPS].as<uint32_t>();
     uint32_t* subs = h->work[W_SUBS].as<uint32_t>();
     int32_t* seg_need = h->work[W_SEGI].as<int32_t>();
@@ -381,9 +461,6 @@ static int stage_bootstrap_segmented(motes_handle* h, Batch& b, uint32_t* rng, b
     const size_t colh_smem = sky_colh_smem(b.nspat, packed);
     auto hist_kernel = packed ? sky_column_hist_kernel<true> : sky_column_hist_kernel<false>;
     MOTES_CUDA(cudaFuncSetAttribute(hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)colh_smem));
-    const uint32_t* polys = h->jump_polys.as<uint32_t>();
-    const size_t jump_smem = (size_t)(kJumpStreamWords + 624) * sizeof(uint32_t);
-    MOTES_CUDA(cudaFuncSetAttribute(mt_jump_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jump_smem));
     MOTES_CUDA(cudaFuncSetAttribute(sky_column_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)col_smem));
     const size_t walk_smem = (size_t)kWalkStages * kWalkChunkBytes;
     MOTES_CUDA(cudaFuncSetAttribute(sky_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)walk_smem));
@@ -392,21 +469,7 @@ static int stage_bootstrap_segmented(motes_handle* h, Batch& b, uint32_t* rng, b
         const int nf = (b.F - f0 < wave) ? b.F - f0 : wave;
         const size_t c0 = (size_t)f0 * b.ndisp;
         uint32_t* rng_w = rng + (size_t)f0 * 625;
-        StageTimer t_jump(h, ST_BOOT_JUMP);
-        seg_plan_kernel<<<nf, 256, 0, h->stream>>>(rng_w, b.ndisp, b.n_good + c0, b.sky_flag + c0, lay, seg_need);
-        MOTES_LAUNCHED(h);
-        MOTES_CUDA(cudaMemsetAsync(windows, 0, (size_t)nf * lay.segs * 624 * sizeof(uint32_t), h->stream));
-        for (int r = 0; (1 << r) < lay.segs; ++r) {
-            const int count = ((1 << (r + 1)) <= lay.segs ? (1 << r) : lay.segs - (1 << r));
-            mt_jump_kernel<<<dim3(count, nf, kJumpParts), kJumpThreads, jump_smem, h->stream>>>(
-                rng_w, windows, lay.segs, r, polys + (size_t)(s + r) * kJumpWords32, seg_need);
-            MOTES_LAUNCHED(h);
-        }
-        t_jump.stop();
-        StageTimer t_stream(h, ST_BOOT_STREAM);
-        mt_stream_kernel<uint16_t><<<dim3(lay.segs, nf), 256, 0, h->stream>>>(rng_w, windows, lay, seg_need, stream, snaps);
-        MOTES_LAUNCHED(h);
-        t_stream.stop();
+        if (!plan.hoisted) MOTES_TRY(boot_generate(h, h->stream, &b, b.ndisp, plan, rng_w, f0, nf, true));
         StageTimer t_walk(h, ST_BOOT_WALK);
         sky_walk_kernel<<<nf, kWalkThreads, walk_smem, h->stream>>>(stream, lay, rng_w, seg_need, b.ndisp, b.n_good + c0, b.sky_flag + c0,
                                                    col_start, col_end, subs, end_pos, b.st + f0);
@@ -667,6 +730,7 @@ static int run_frames_core(motes_handle* h, Batch& b, double* data, double* errs
                                  cudaMemcpyDeviceToDevice, h->stream));
     MOTES_CUDA(cudaMemcpy2DAsync(&b.st->pixres, sizeof(FrameState), pixres_dev, sizeof(double), sizeof(double), b.F,
                                  cudaMemcpyDeviceToDevice, h->stream));
+    if (p.subtract_sky && p.sky_order == 0) MOTES_TRY(boot_hoist(h, b, rng));
     MOTES_TRY(stage_median_fit(h, b, data, frame_stride));
     if (p.subtract_sky) {
         MOTES_TRY(stage_localise(h, b, data, errs, frame_stride, qual, frame_stride, p.sky_snr_limit, p, 0));
@@ -825,6 +889,8 @@ int motes_create(int device, motes_handle** out) {
     h->fit_mode = (fitm && strcmp(fitm, "warp") == 0) ? 1 : 0;
     const char* budget = getenv("MOTES_B200_STREAM_GB");
     if (budget && atof(budget) > 0.0) h->stream_budget = (size_t)(atof(budget) * 1073741824.0);
+    const char* hoist = getenv("MOTES_B200_HOIST");            // "0": generate the bootstrap stream where it is consumed
+    h->hoist = !(hoist && atoi(hoist) == 0);
     const char* chunks = getenv("MOTES_B200_CHUNKS");
     if (chunks && atoi(chunks) > 0) h->chunks = atoi(chunks);
     e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);

@@ -38,15 +38,6 @@ constexpr int kJumpThreads = 640;
 constexpr int kJumpStreamWords = 19937 + 624 + 15;
 constexpr int kColThreads = 512;
 
-struct SegLayout {                 // per call, host-computed
-    int log2_stride;
-    uint32_t stride;               // words per segment
-    int segs;                      // segments allocated per frame (K)
-    unsigned long long stream_len; // 16-bit words per frame (padded for the walk's prefetch)
-    unsigned long long sub_len;    // running-count entries per frame
-    int snaps;                     // snapshots per frame
-};
-
 // ---- plan -------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 seg_plan_kernel(const uint32_t* __restrict__ rng, int ndisp, const int32_t* __restrict__ n_good,
@@ -71,6 +62,12 @@ seg_plan_kernel(const uint32_t* __restrict__ rng, int ndisp, const int32_t* __re
         if (need < 1) need = 1;
         seg_need[f] = (int32_t)need;
     }
+}
+
+// Every segment of every frame (the generator is started before the sky pixels are known).
+__global__ void seg_plan_all_kernel(int nframes, SegLayout lay, int32_t* __restrict__ seg_need) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f < nframes) seg_need[f] = lay.segs;
 }
 
 // ---- jump -------------------------------------------------------------------------------------
