@@ -128,6 +128,7 @@ struct motes_handle {
     bool jump_ready = false;
     size_t stream_budget = 0;    // bytes the segmented bootstrap may use for generator streams (0 = auto)
     bool hoist = true;           // MOTES_B200_HOIST=0: generate the bootstrap stream where it is consumed
+    int hoist_ctas = 8;          // MOTES_B200_HOIST_CTAS: generator CTAs per SM when it runs beside the localisation stages
     motes::BootPlan boot;
     cudaEvent_t ev_hoist[2] = {nullptr, nullptr};
     std::vector<motes::StageSpan> spans;

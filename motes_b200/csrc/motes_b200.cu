@@ -308,7 +308,7 @@ static size_t sky_colh_smem(int nspat, bool packed) {
 // Layout of the segmented replay for a batch: frames per wave, segment stride, buffers (all from the a-priori bound
 // 100 * ndisp * 2^ceil(log2 nspat) words per frame, so it can be fixed before the sky pixels are known).
 // plan->ok = false: the layout does not fit (the caller falls back to the one-CTA-per-frame replay).
-static int boot_plan(motes_handle* h, const Batch& b, BootPlan* plan) {
+static int boot_plan(motes_handle* h, const Batch& b, BootPlan* plan, int ctas_per_sm = 8) {
     plan->ok = false;
     plan->hoisted = false;
     const JumpTable& table = jump_table();
@@ -343,7 +343,7 @@ static int boot_plan(motes_handle* h, const Batch& b, BootPlan* plan) {
         const int waves = (b.F + wave - 1) / wave;
         wave = (b.F + waves - 1) / waves;
         // segment stride: enough CTAs to fill the machine, not more jumps than needed
-        const long long target = 8ll * h->sm_count;
+        const long long target = (long long)ctas_per_sm * h->sm_count;
         s = kSnapLog2;
         while (s < 30 && (long long)wave * (long long)((bound + (1ull << s) - 1) >> s) > target) ++s;
         if (s + 10 > kJumpMaxLog2) return MOTES_OK;
@@ -412,12 +412,15 @@ static int boot_generate(motes_handle* h, cudaStream_t cs, const Batch* b, int n
 // Start the generator of a batch on the second stream before anything is known about its sky pixels: the stream only
 // depends on the frames' generator states, and its kernels (integer issue bound) share the SMs with the latency-bound
 // localisation stages that run meanwhile on the main stream.  Only when one wave covers the batch.
+// Generator CTAs per SM (MOTES_B200_HOIST_CTAS), 128 frames of 4096 x 400 on B200: 8 -> 182.4 ms per step, 4 -> 185.5,
+// 3 -> 186.3, 2 -> 185.8, 1 -> 214.1 (un-hoisted 189.4): leaving the fit kernel more room does not pay, the
+// generator just takes longer.
 static int boot_hoist(motes_handle* h, const Batch& b, uint32_t* rng) {
     h->boot.ok = false;
     h->boot.hoisted = false;
     if (!h->hoist || h->profiling || h->boot_mode != 0 || h->chunks > 1 || !rng) return MOTES_OK;
     BootPlan plan;
-    MOTES_TRY(boot_plan(h, b, &plan));
+    MOTES_TRY(boot_plan(h, b, &plan, h->hoist_ctas));
     if (!plan.ok || plan.wave != b.F) return MOTES_OK;
     if (!h->ev_hoist[0]) {
         MOTES_CUDA(cudaEventCreateWithFlags(&h->ev_hoist[0], cudaEventDisableTiming));
@@ -891,6 +894,8 @@ int motes_create(int device, motes_handle** out) {
     if (budget && atof(budget) > 0.0) h->stream_budget = (size_t)(atof(budget) * 1073741824.0);
     const char* hoist = getenv("MOTES_B200_HOIST");            // "0": generate the bootstrap stream where it is consumed
     h->hoist = !(hoist && atoi(hoist) == 0);
+    const char* hoist_ctas = getenv("MOTES_B200_HOIST_CTAS");
+    if (hoist_ctas && atoi(hoist_ctas) > 0) h->hoist_ctas = atoi(hoist_ctas);
     const char* chunks = getenv("MOTES_B200_CHUNKS");
     if (chunks && atoi(chunks) > 0) h->chunks = atoi(chunks);
     e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
