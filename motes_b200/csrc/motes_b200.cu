@@ -802,11 +802,11 @@ static int get_event(motes_handle* h, size_t i, cudaEvent_t* ev) {
     return MOTES_OK;
 }
 
-// Sub-batches per call (MOTES_B200_CHUNKS, default 1).  Measured on B200 with 128 frames of 4096 x 400:
-// 1 -> 253 ms, 2 -> 253 ms, 4 -> 308 ms, 8 -> 395 ms per step, and the host entry point loses more than the
-// overlapped upload gains: the throughput-bound kernels fill every SM, so the other lane's latency-bound
-// kernels queue behind them instead of running beside them, while every per-frame serial stage is paid
-// once per sub-batch.  The mechanism stays for callers whose batches exceed device memory.
+// Sub-batches per call (MOTES_B200_CHUNKS, default 1).  Measured on B200 with 128 frames of 4096 x 400 (round-1
+// final kernels): 1 -> 182.4 ms, 2 -> 194.6 ms per step (earlier in the round 253 / 253 / 308 / 395 ms for 1 / 2 / 4 / 8):
+// the throughput-bound kernels fill every SM, so the other lane's latency-bound kernels queue behind them instead of
+// running beside them, while every per-frame serial stage is paid once per sub-batch.  The mechanism stays for
+// callers whose batches exceed device memory.
 static int chunk_frames(const motes_handle* h, int nframes) {
     int chunks = h->chunks > 0 ? h->chunks : 1;
     if (chunks > nframes) chunks = nframes;
