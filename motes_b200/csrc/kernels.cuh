@@ -778,7 +778,7 @@ sky_bootstrap_poly_kernel(uint32_t* __restrict__ rng, int nspat, int ndisp, int 
     sh.scl = sh.loc + nspat;
     sh.red = sh.scl + nspat;
     sh.samples = sh.red + 40;
-    sh.ring = reinterpret_cast<uint32_t*>(sh.samples + (size_t)(kBootThreads / 32) * kBootstrap);
+    sh.ring = reinterpret_cast<uint32_t*>(sh.samples + (size_t)(kBootThreads / 32) * (kBootstrap + 4));
     sh.counts = sh.ring + kRing;
     sh.ctl = reinterpret_cast<int*>(sh.counts + 16);
     sh.rows = reinterpret_cast<uint16_t*>(sh.ctl + 4);

@@ -290,7 +290,7 @@ static size_t sky_boot_smem(int nspat) {
 
 static size_t sky_poly_smem(int nspat) {
     return ((size_t)nspat * kMaxPoly + kMaxPoly * kMaxPoly + kMaxPoly + kBootstrap * kMaxPoly + 2 * (size_t)nspat + 40 +
-            (size_t)(kBootThreads / 32) * kBootstrap) * 8 + kRing * 4 + 16 * 4 + 4 * 4 + (size_t)nspat * 2 + 64;
+            (size_t)(kBootThreads / 32) * (kBootstrap + 4)) * 8 + kRing * 4 + 16 * 4 + 4 * 4 + (size_t)nspat * 2 + 64;
 }
 
 

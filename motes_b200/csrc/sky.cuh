@@ -477,7 +477,7 @@ struct PolyShared {
     double* loc;         // max_good
     double* scl;         // max_good
     double* red;         // 40 doubles: block reduction scratch
-    double* samples;     // per warp 100 (device) / 100 (host)
+    double* samples;     // per warp 100 values + the +inf the padding indices point at (4 doubles of room)
     uint16_t* rows;      // max_good
 };
 
@@ -541,14 +541,26 @@ MOTES_HD void sky_poly_fit_column(const Scope& sc, const PolyShared& sh, int n, 
             sc.sync();
         }
     }
-    // ---- one projection + back-substitution per bootstrap sample
-    for (int smp = sc.tid; smp < kBootstrap; smp += sc.size()) {
-        double z[kMaxPoly], cf[kMaxPoly];
+    // ---- one projection + back-substitution per bootstrap sample; the rows are split between as many groups of 100
+    // threads as the scope has (partial sums of the second group go through sh.samples)
+    const int groups = sc.size() >= 2 * kBootstrap ? 2 : 1;
+    for (int item = sc.tid; item < groups * kBootstrap; item += sc.size()) {
+        const int grp = item / kBootstrap, smp = item % kBootstrap;
+        const int g0 = (int)(((long long)n * grp) / groups), g1 = (int)(((long long)n * (grp + 1)) / groups);
+        double z[kMaxPoly];
         for (int k = 0; k < p; ++k) z[k] = 0.0;
-        for (int g = 0; g < n; ++g) {
+#pragma unroll 4
+        for (int g = g0; g < g1; ++g) {
             const double yv = y[(size_t)g * kBootstrap + smp];
             for (int k = 0; k < p; ++k) z[k] = fma(sh.q[(size_t)g * kMaxPoly + k], yv, z[k]);
         }
+        double* part = (grp == 0 ? sh.coef : sh.samples) + smp * kMaxPoly;
+        for (int k = 0; k < p; ++k) part[k] = z[k];
+    }
+    sc.sync();
+    for (int smp = sc.tid; smp < kBootstrap; smp += sc.size()) {
+        double z[kMaxPoly], cf[kMaxPoly];
+        for (int k = 0; k < p; ++k) z[k] = sh.coef[smp * kMaxPoly + k] + (groups > 1 ? sh.samples[smp * kMaxPoly + k] : 0.0);
         for (int k = p - 1; k >= 0; --k) {
             double acc2 = z[k];
             for (int j2 = k + 1; j2 < p; ++j2) acc2 -= sh.rmat[k * kMaxPoly + j2] * cf[j2];
@@ -560,88 +572,133 @@ MOTES_HD void sky_poly_fit_column(const Scope& sc, const PolyShared& sh, int n, 
     sc.sync();
     // ---- per spatial pixel: median and std over the 100 polynomial values (sky.py:231-239)
 #if defined(__CUDA_ARCH__)
-    const int nwarp = (sc.size() + 31) >> 5;
-    const int wid = sc.size() > 1 ? warp : 0, ln = sc.size() > 1 ? lane : 0, lanes = sc.size() > 1 ? 32 : 1;
-#else
-    const int nwarp = 1, wid = 0, ln = 0, lanes = 1;
+    if (sc.size() > 1) {
+        // One warp per run of neighbouring pixels.  The 100 polynomials are smooth, so their order at one pixel is
+        // almost their order at the next: the warp keeps the sample indices in sorted order (four per lane, padded to
+        // 128 with +inf) and repairs the order with odd-even transposition passes - a full bitonic sort only for the
+        // first pixel of the run or when the repair takes long.  The selection is exact either way.
+        const int nwarp = (sc.size() + 31) >> 5;
+        const int per = (nspat + nwarp - 1) / nwarp;
+        const int px0 = warp * per, px1 = min(nspat, px0 + per);
+        double* vals = sh.samples + (size_t)warp * (kBootstrap + 4);
+        int id[4];
+        double sv[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) id[k] = (4 * lane + k < kBootstrap) ? 4 * lane + k : kBootstrap;
+        if (lane == 0) vals[kBootstrap] = INFINITY;          // where the padding indices point
+        bool have_order = false;
+        for (int px = px0; px < px1; ++px) {
+            const double x = (double)(px + spatial_floor);
+            for (int smp = lane; smp < kBootstrap; smp += 32) {
+                double acc2 = 0.0, pw = 1.0;
+                for (int k = 0; k < p; ++k) { acc2 += pw * sh.coef[smp * kMaxPoly + k]; pw *= x; }
+                vals[smp] = acc2;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < 4; ++k) sv[k] = vals[id[k]];
+            // (value, index) order; the index breaks ties so that both sides of an exchange agree
+            auto before = [](double va, int ia, double vb, int ib) { return va < vb || (va == vb && ia < ib); };
+            auto exchange = [&](int ka, int kb) {           // ascending inside the lane
+                if (before(sv[kb], id[kb], sv[ka], id[ka])) {
+                    const double tv = sv[ka]; sv[ka] = sv[kb]; sv[kb] = tv;
+                    const int ti = id[ka]; id[ka] = id[kb]; id[kb] = ti;
+                }
+            };
+            bool sorted_now = false;
+            if (have_order) {
+                for (int pass = 0; pass < 12; ++pass) {
+                    const double nv = __shfl_down_sync(0xffffffffu, sv[0], 1);
+                    const int ni = __shfl_down_sync(0xffffffffu, id[0], 1);
+                    const bool ok = !before(sv[1], id[1], sv[0], id[0]) && !before(sv[2], id[2], sv[1], id[1]) &&
+                                    !before(sv[3], id[3], sv[2], id[2]) && (lane == 31 || !before(nv, ni, sv[3], id[3]));
+                    if (__all_sync(0xffffffffu, ok)) { sorted_now = true; break; }
+                    exchange(0, 1);
+                    exchange(2, 3);
+                    exchange(1, 2);
+                    // slot 3 of this lane against slot 0 of the next one, both from the values before the exchange
+                    const double dv = __shfl_down_sync(0xffffffffu, sv[0], 1), uv = __shfl_up_sync(0xffffffffu, sv[3], 1);
+                    const int di = __shfl_down_sync(0xffffffffu, id[0], 1), ui = __shfl_up_sync(0xffffffffu, id[3], 1);
+                    if (lane < 31 && before(dv, di, sv[3], id[3])) { sv[3] = dv; id[3] = di; }
+                    if (lane > 0 && before(sv[0], id[0], uv, ui)) { sv[0] = uv; id[0] = ui; }
+                }
+            }
+            if (!sorted_now) {
+                // warp bitonic sort of the 128 (value, index) pairs
+#pragma unroll
+                for (int size = 2; size <= 128; size <<= 1) {
+#pragma unroll
+                    for (int d = size >> 1; d > 0; d >>= 1) {
+                        if (d < 4) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                if ((k & d) == 0) {
+                                    const bool up = (size < 4) ? ((k & size) == 0) : ((lane & (size / 4)) == 0);
+                                    const bool wrong = up ? before(sv[k | d], id[k | d], sv[k], id[k]) : before(sv[k], id[k], sv[k | d], id[k | d]);
+                                    if (wrong) {
+                                        const double tv = sv[k]; sv[k] = sv[k | d]; sv[k | d] = tv;
+                                        const int ti = id[k]; id[k] = id[k | d]; id[k | d] = ti;
+                                    }
+                                }
+                            }
+                        } else {
+                            const int dl = d / 4;
+                            const bool up = (lane & (size / 4)) == 0 || size == 128;
+                            const bool keep_min = (((lane & dl) == 0) == up);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const double ov = __shfl_xor_sync(0xffffffffu, sv[k], dl);
+                                const int oi = __shfl_xor_sync(0xffffffffu, id[k], dl);
+                                const bool other_first = before(ov, oi, sv[k], id[k]);
+                                if (other_first == keep_min) { sv[k] = ov; id[k] = oi; }
+                            }
+                        }
+                    }
+                }
+                have_order = true;
+            }
+            // np.median of 100: mean of the order statistics 49 and 50 (lane 12, slots 1 and 2)
+            const double m1 = __shfl_sync(0xffffffffu, sv[1], 12), m2 = __shfl_sync(0xffffffffu, sv[2], 12);
+            double psum = 0.0;
+            for (int e = lane; e < kBootstrap; e += 32) psum += vals[e];
+            for (int o = 16; o > 0; o >>= 1) psum += __shfl_xor_sync(0xffffffffu, psum, o);
+            const double mean = psum / (double)kBootstrap;
+            double sq = 0.0;
+            for (int e = lane; e < kBootstrap; e += 32) { const double d = vals[e] - mean; sq += d * d; }
+            for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+            if (lane == 0) {
+                model[(size_t)px * ndisp + c] = (m1 + m2) * 0.5;
+                model_err[(size_t)px * ndisp + c] = sqrt(sq / (double)kBootstrap);
+            }
+            __syncwarp();
+        }
+        sc.sync();
+        return;
+    }
 #endif
-    double* vals = sh.samples + (size_t)wid * kBootstrap;
-    for (int px = wid; px < nspat; px += nwarp) {
+    // one lane (host build, one-thread scopes): rank counting
+    double* vals = sh.samples;
+    for (int px = 0; px < nspat; ++px) {
         const double x = (double)(px + spatial_floor);
-        for (int smp = ln; smp < kBootstrap; smp += lanes) {
+        for (int smp = 0; smp < kBootstrap; ++smp) {
             double acc2 = 0.0, pw = 1.0;
             for (int k = 0; k < p; ++k) { acc2 += pw * sh.coef[smp * kMaxPoly + k]; pw *= x; }
             vals[smp] = acc2;
         }
-#if defined(__CUDA_ARCH__)
-        __syncwarp();
-#endif
-        // np.median of 100: mean of the order statistics 49 and 50
         double m1 = 0.0, m2 = 0.0, psum = 0.0;
-        double mean;
-#if defined(__CUDA_ARCH__)
-        if (sc.size() > 1) {
-            // warp bitonic sort of the 100 values (padded to 128 with +inf), four per lane
-            double sv[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) sv[k] = (4 * ln + k < kBootstrap) ? vals[4 * ln + k] : INFINITY;
-#pragma unroll
-            for (int size = 2; size <= 128; size <<= 1) {
-#pragma unroll
-                for (int d = size >> 1; d > 0; d >>= 1) {
-                    if (d < 4) {
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            if ((k & d) == 0) {
-                                const bool up = (size < 4) ? ((k & size) == 0) : ((ln & (size / 4)) == 0);
-                                const double va = sv[k], vb = sv[k | d];
-                                const bool sw = (va > vb) == up;
-                                sv[k] = sw ? vb : va;
-                                sv[k | d] = sw ? va : vb;
-                            }
-                        }
-                    } else {
-                        const int dl = d / 4;
-                        const bool up = (ln & (size / 4)) == 0 || size == 128;
-                        const bool keep_min = (((ln & dl) == 0) == up);
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const double o = __shfl_xor_sync(0xffffffffu, sv[k], dl);
-                            sv[k] = keep_min ? fmin(sv[k], o) : fmax(sv[k], o);
-                        }
-                    }
-                }
-            }
-            m1 = __shfl_sync(0xffffffffu, sv[1], 12);            // sorted position 49 = lane 12, slot 1
-            m2 = __shfl_sync(0xffffffffu, sv[2], 12);            // sorted position 50
-            for (int e = ln; e < kBootstrap; e += lanes) psum += vals[e];
-            for (int o = 16; o > 0; o >>= 1) psum += __shfl_xor_sync(0xffffffffu, psum, o);
-        } else
-#endif
-        {
-            for (int e = ln; e < kBootstrap; e += lanes) {
-                const double v = vals[e];
-                int rank = 0;
-                for (int j2 = 0; j2 < kBootstrap; ++j2) { const double o = vals[j2]; rank += (o < v) || (o == v && j2 < e); }
-                if (rank == 49) m1 = v;
-                if (rank == 50) m2 = v;
-                psum += v;
-            }
+        for (int e = 0; e < kBootstrap; ++e) {
+            const double v = vals[e];
+            int rank = 0;
+            for (int j2 = 0; j2 < kBootstrap; ++j2) { const double o = vals[j2]; rank += (o < v) || (o == v && j2 < e); }
+            if (rank == 49) m1 = v;
+            if (rank == 50) m2 = v;
+            psum += v;
         }
-        mean = psum / (double)kBootstrap;
+        const double mean = psum / (double)kBootstrap;
         double sq = 0.0;
-        for (int e = ln; e < kBootstrap; e += lanes) { const double d = vals[e] - mean; sq += d * d; }
-#if defined(__CUDA_ARCH__)
-        if (sc.size() > 1)
-            for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-#endif
-        if (ln == 0) {
-            model[(size_t)px * ndisp + c] = (m1 + m2) * 0.5;
-            model_err[(size_t)px * ndisp + c] = sqrt(sq / (double)kBootstrap);
-        }
-#if defined(__CUDA_ARCH__)
-        __syncwarp();
-#endif
+        for (int e = 0; e < kBootstrap; ++e) { const double d = vals[e] - mean; sq += d * d; }
+        model[(size_t)px * ndisp + c] = (m1 + m2) * 0.5;
+        model_err[(size_t)px * ndisp + c] = sqrt(sq / (double)kBootstrap);
     }
     sc.sync();
 }

@@ -1094,7 +1094,7 @@ sky_poly_column_kernel(const uint32_t* __restrict__ stream, SegLayout lay, const
     sh.scl = sh.loc + nspat;
     sh.red = sh.scl + nspat;
     sh.samples = sh.red + 40;
-    sh.ring = reinterpret_cast<uint32_t*>(sh.samples + (size_t)(kBootThreads / 32) * kBootstrap);     // unused here
+    sh.ring = reinterpret_cast<uint32_t*>(sh.samples + (size_t)(kBootThreads / 32) * (kBootstrap + 4));     // unused here
     sh.counts = sh.ring;                                                                                // 16 words
     sh.ctl = reinterpret_cast<int*>(sh.counts + 16);
     sh.rows = reinterpret_cast<uint16_t*>(sh.ctl + 4);
