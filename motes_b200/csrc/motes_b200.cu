@@ -733,6 +733,9 @@ static int run_frames_core(motes_handle* h, Batch& b, double* data, double* errs
                                  cudaMemcpyDeviceToDevice, h->stream));
     MOTES_CUDA(cudaMemcpy2DAsync(&b.st->pixres, sizeof(FrameState), pixres_dev, sizeof(double), sizeof(double), b.F,
                                  cudaMemcpyDeviceToDevice, h->stream));
+    // a hoisted generator belongs to this call only, whichever way the call ends
+    struct HoistScope { motes_handle* h; ~HoistScope() { h->boot.hoisted = false; } } hoist_scope{h};
+    h->boot.hoisted = false;
     if (p.subtract_sky && p.sky_order == 0) MOTES_TRY(boot_hoist(h, b, rng));
     MOTES_TRY(stage_median_fit(h, b, data, frame_stride));
     if (p.subtract_sky) {

@@ -1,9 +1,10 @@
 """Full-size runs of BASELINE.json's configurations (no oracle run: the CPU path needs 8-50 s per frame there).
 
 What is checked instead are properties that do not depend on the size:
-  * the segmented generator replay (jump-ahead / stream / walk / histogram kernels) and the literal one-CTA
-    replay of ``np.random.choice`` (validated bit for bit against numpy on the golden cases) give the same sky
-    model, the same spectra and leave numpy's RandomState in the same state;
+  * the segmented generator replay (jump-ahead / stream / walk / histogram kernels; generator started early on the
+    second stream, or where it is consumed) and the literal one-CTA replay of ``np.random.choice`` (validated bit
+    for bit against numpy on the golden cases) give the same sky model, the same spectra and leave numpy's
+    RandomState in the same state;
   * a frame gives the same result alone and inside a batch;
   * the aperture flux is the plain sum of the sky-subtracted pixels between the integer limits
     (extraction.py:87-88), the optimal flux equals it within the noise where the profile is well sampled,
@@ -47,7 +48,8 @@ def test_segmented_replay_equals_literal_replay_at_full_size(name):
     args = synth.default_args()
     runs = {}
     for label, env in (("segmented", {"MOTES_B200_BOOTSTRAP": "segmented"}), ("literal", {"MOTES_B200_BOOTSTRAP": "classic"}),
-                       ("slots", {"MOTES_B200_BOOTSTRAP": "segmented", "MOTES_B200_COLUMN": "0"})):
+                       ("slots", {"MOTES_B200_BOOTSTRAP": "segmented", "MOTES_B200_COLUMN": "0"}),
+                       ("unhoisted", {"MOTES_B200_BOOTSTRAP": "segmented", "MOTES_B200_HOIST": "0"})):
         h = _fresh_handle(env)
         data, errs = frame["data"][None].copy(), frame["errs"][None].copy()
         runs[label] = pipeline.run_frames(data, errs, frame["qual"][None], args, header["seeing"], header["pixel_resolution"],
@@ -59,7 +61,7 @@ def test_segmented_replay_equals_literal_replay_at_full_size(name):
         assert all(r["frame_status"][0] == a["frame_status"][0] for r in runs.values())
         pytest.skip(f"frame status {a['frame_status'][0]} (what the reference raises) in every variant")
     assert int((a["sky_flag"][0] == 0).sum()) > 0.9 * a["sky_flag"].shape[1]          # the sky was modelled
-    for other in ("literal", "slots"):
+    for other in ("literal", "slots", "unhoisted"):
         b = runs[other]
         assert np.array_equal(a["rng_states"], b["rng_states"]), other
         for key in ("sky_model", "sky_uncertainty", "spectra", "ext_limits", "sky_limits", "data", "errs"):
