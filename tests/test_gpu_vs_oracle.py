@@ -25,6 +25,12 @@ CASES = {
                         {"minimum_column_limit": 0, "extraction_snr_limit": 0, "sky_snr_limit": 0}, 107),
     "no_sky_subtraction": ("T2", {"nan_fraction": 0.01}, {"subtract_sky": False}, 108),
     "tight_sky_window": ("T1", {}, {"sky_fwhm_multiplier": 1.5}, 109),
+    # shapes that are not multiples of any tile, vector or warp width
+    "odd_shape": ("T1", {"nspat": 97, "ndisp": 1003, "chip_gaps": ((333, 21),)}, {}, 110),
+    "small_odd_shape": ("T2", {"nspat": 41, "ndisp": 263, "alpha": 1.8, "cosmic_fraction": 0.0}, {}, 111),
+    # wider than 512 rows: the general sky preparation, packed histograms, 10-bit rejection mask
+    "wide_slit": ("T1", {"nspat": 601, "ndisp": 512, "alpha": 4.0, "curvature": 6.0, "chip_gaps": ()}, {}, 112),
+    "wide_slit_poly": ("T1", {"nspat": 601, "ndisp": 256, "alpha": 4.0, "chip_gaps": ()}, {"sky_order": 2}, 113),
 }
 
 
