@@ -502,29 +502,45 @@ sky_walk_kernel(const uint16_t* __restrict__ stream, SegLayout lay, const uint32
                             const uint32_t r2 = ((d.z & mask2) + kk2) & 0x80008000u, r3 = ((d.w & mask2) + kk2) & 0x80008000u;
                             rej[k] = r0 | (r1 >> 1) | (r2 >> 2) | (r3 >> 3);
                         }
-                        const uint32_t below = (1u << lane) - 1u;
-                        bool found = false;
+                        // lane-inclusive prefix of the eight row counts at once: 10-bit fields (a row holds <= 256 draws),
+                        // three rows to a register, five shuffle steps; lane 31 then holds the row totals
+                        static_assert(kPieceRows == 8, "the packed prefix below is laid out for eight rows");
+                        uint32_t mine[kPieceRows];
+#pragma unroll
+                        for (int k = 0; k < kPieceRows; ++k) mine[k] = 8u - (uint32_t)__popc(rej[k]);
+                        uint32_t pre[3] = {mine[0] | (mine[1] << 10) | (mine[2] << 20), mine[3] | (mine[4] << 10) | (mine[5] << 20),
+                                           mine[6] | (mine[7] << 10)};
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+#pragma unroll
+                            for (int q = 0; q < 3; ++q) {
+                                const uint32_t t = __shfl_up_sync(0xffffffffu, pre[q], o);
+                                if (lane >= o) pre[q] += t;
+                            }
+                        }
+                        uint32_t tot[3];
+#pragma unroll
+                        for (int q = 0; q < 3; ++q) tot[q] = __shfl_sync(0xffffffffu, pre[q], 31);
+                        uint32_t acc = 0, want = 0, incl = 0, own = 0, flags = 0;
+                        int row = -1;
 #pragma unroll
                         for (int k = 0; k < kPieceRows; ++k) {
-                            if (found) continue;
-                            const uint32_t mine = 8u - (uint32_t)__popc(rej[k]);
-                            const uint32_t b0 = __ballot_sync(0xffffffffu, mine & 1u), b1 = __ballot_sync(0xffffffffu, mine & 2u);
-                            const uint32_t b2 = __ballot_sync(0xffffffffu, mine & 4u), b3 = __ballot_sync(0xffffffffu, mine & 8u);
-                            const uint32_t row_total = (uint32_t)(__popc(b0) + 2 * __popc(b1) + 4 * __popc(b2) + 8 * __popc(b3));
-                            if (target <= row_total) {
-                                const uint32_t excl = (uint32_t)(__popc(b0 & below) + 2 * __popc(b1 & below) + 4 * __popc(b2 & below) +
-                                                                 8 * __popc(b3 & below));
-                                if (excl < target && target <= excl + mine) {
-                                    uint32_t seen = excl;
+                            const uint32_t row_total = (tot[k / 3] >> (10 * (k % 3))) & 0x3ffu;
+                            if (row < 0 && target <= acc + row_total) {
+                                row = k;
+                                want = target - acc;
+                                incl = (pre[k / 3] >> (10 * (k % 3))) & 0x3ffu;
+                                own = mine[k];
+                                flags = rej[k];
+                            }
+                            acc += row_total;
+                        }
+                        if (row >= 0 && incl - own < want && want <= incl) {      // this lane holds the last draw
+                            uint32_t seen = incl - own;
 #pragma unroll
-                                    for (int e = 0; e < 8; ++e) {
-                                        const uint32_t bit = 1u << ((e & 1) * 16 + 15 - (e >> 1));
-                                        if (!(rej[k] & bit) && ++seen == target) cross = sb + (uint32_t)(k * 256 + lane * 8 + e) + 1u;
-                                    }
-                                }
-                                found = true;
-                            } else {
-                                target -= row_total;
+                            for (int e = 0; e < 8; ++e) {
+                                const uint32_t bit = 1u << ((e & 1) * 16 + 15 - (e >> 1));
+                                if (!(flags & bit) && ++seen == want) cross = sb + (uint32_t)(row * 256 + lane * 8 + e) + 1u;
                             }
                         }
                     } else
