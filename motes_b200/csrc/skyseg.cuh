@@ -435,7 +435,7 @@ sky_walk_kernel(const uint16_t* __restrict__ stream, SegLayout lay, const uint32
             if (producer) top_up(head_chunk);
             // this warp's pieces: piece w in the first round, piece 31 - w in the second, so that warp 0 - whose first
             // piece starts inside the previous column and takes the slower count - is the last to get a second one
-            for (int round = 0; round < kWalkPieces / kWalkWarps; ++round) {
+            for (int round = 0; round < (kWalkPieces + kWalkWarps - 1) / kWalkWarps; ++round) {
             const int pc = (round & 1) ? (round + 1) * kWalkWarps - 1 - warp : round * kWalkWarps + warp;
             if (pc >= span) continue;
             int cnt = 0;
@@ -459,8 +459,7 @@ sky_walk_kernel(const uint16_t* __restrict__ stream, SegLayout lay, const uint32
                     for (int k = 0; k < kPieceRows; ++k)
                         cnt += walk_count8(src[k * 32 + lane], sb + (uint32_t)(k * 256 + lane * 8), P, limit, mask, top);
                 }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+                cnt = __reduce_add_sync(0xffffffffu, cnt);       // one REDUX instead of five dependent shuffles
             }
             if (lane == 0) piece_cnt[parity][pc] = (uint32_t)cnt;
             }
