@@ -42,6 +42,14 @@ extern "C" {
 typedef struct motes_handle motes_handle;
 
 /* Library / device management ------------------------------------------------------ */
+/* motes_create reads these environment switches (A/B timing and cross-checks in tests/; none changes results):
+ *   MOTES_B200_BOOTSTRAP=classic  one CTA replays a frame's whole generator stream (the literal form of sky.py:34-38)
+ *   MOTES_B200_COLUMN=0|<window>  exact rank-slot kernel only / histogram window of the bootstrap column kernel
+ *   MOTES_B200_HOIST=0            generate the bootstrap stream where it is consumed instead of at the start of the call
+ *   MOTES_B200_HOIST_CTAS=<n>     generator CTAs per SM while it runs beside the localisation stages (default 8)
+ *   MOTES_B200_STREAM_GB=<x>      device memory the generator streams may take (default: half of what is free)
+ *   MOTES_B200_FIT=warp           round-1 one-warp-per-fit kernel
+ *   MOTES_B200_CHUNKS=<n>         sub-batches per call on two streams (default 1) */
 int motes_create(int device, motes_handle** out);
 int motes_destroy(motes_handle* h);
 const char* motes_last_error(void);
