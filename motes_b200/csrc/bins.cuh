@@ -71,30 +71,107 @@ MOTES_HD ColumnStats column_stats(const double* data, const double* errs, int ns
 //   bins_snr  out, [maxbins]
 //   tmp_i / tmp_snr  scratch of the same sizes (blue-ward bins are produced in reverse order)
 // Returns the number of bins.
+struct BinWindow {        // staging area for a run of columns: S, V and the all-rows-good flag
+    double* S;
+    double* V;
+    uint8_t* good;
+    double* xfer;         // 10 doubles: scan state handed from the warp that runs ahead to the rest of the scope
+    int cap;
+};
+
 template <class Scope>
 MOTES_HD int snr_bins_scan(const Scope& sc, const uint8_t* qual, const double* S, const double* V, int nspat,
                            int ndisp, double snr_limit, double min_cols, int* counts, int32_t* bins_i,
                            double* bins_snr, int32_t* tmp_i, double* tmp_snr, const uint8_t* allgood = nullptr,
-                           unsigned long long* cell = nullptr) {
+                           unsigned long long* cell = nullptr, const BinWindow* win = nullptr) {
     const int centre = ndisp / 2;
     int n_blue = 0, n_red = 0;
+    // Per-column inputs through a staged window (shared memory on the device): the scan is one serial chain per
+    // frame, and a global load per column would sit on it.  Every thread sees the same `col`, so the refill
+    // (two scope barriers around a cooperative copy) is taken by all of them together.
+    int win_lo = 0, win_n = 0;
+    const double limit2 = (snr_limit * snr_limit) * (1.0 - 1e-12);      // see the S/N test below
+    auto stage = [&](int col, int dir) {
+        if (!win || (col >= win_lo && col < win_lo + win_n)) return;
+        sc.sync();
+        win_lo = (dir == 0) ? (col - win->cap + 1 > 0 ? col - win->cap + 1 : 0) : col;
+        win_n = (ndisp - win_lo < win->cap) ? ndisp - win_lo : win->cap;
+        for (int i = sc.tid; i < win_n; i += sc.size()) {
+            win->S[i] = S[win_lo + i];
+            win->V[i] = V[win_lo + i];
+            win->good[i] = allgood ? allgood[win_lo + i] : (uint8_t)0;
+        }
+        sc.sync();
+    };
     for (int dir = 0; dir < 2; ++dir) {
         int edge = centre, width = 0;
         while (dir == 0 ? (edge - width > 0) : (edge + width < ndisp)) {
             double snr = 0.0;
+            bool pending = false;               // the last window's S/N was passed over (see below)
+            double s_pending = 0.0, v_pending = 0.0;
             Accum sum_s, sum_v;
             for (int r = sc.tid; r < nspat; r += sc.size()) counts[r] = 0;
             int common = 0, least = 0;          // counter of row r = common + counts[r]; least = min over r of counts[r]
             sc.sync();
             while (snr <= snr_limit) {
+                // Runs of all-good columns inside the staged window need no other thread: one warp takes them alone
+                // (the arithmetic is a serial chain; a dozen warps repeating it only compete for issue slots) and hands
+                // the state back through win->xfer.  It stops in front of the frame edge, the window's end and any
+                // column with a bad pixel, which the code below handles.
+                if (win) {
+                    const int w1 = width + 1;
+                    const int next = (dir == 0) ? edge - w1 : edge + w1 - 1;
+                    const bool inside = (dir == 0) ? (edge - w1 >= 0) : (edge + w1 <= ndisp);
+                    if (inside && next >= win_lo && next < win_lo + win_n && win->good[next - win_lo]) {
+                        if (sc.tid < 32) {
+                            while (true) {
+                                const int w2 = width + 1;
+                                if (dir == 0 ? (edge - w2 < 0) : (edge + w2 > ndisp)) break;
+                                const int col = (dir == 0) ? edge - w2 : edge + w2 - 1;
+                                if (col < win_lo || col >= win_lo + win_n || !win->good[col - win_lo]) break;
+                                width = w2;
+                                common += 1;
+                                sum_s.add(win->S[col - win_lo]);
+                                sum_v.add(win->V[col - win_lo]);
+                                if ((double)(common + least) <= min_cols) continue;
+                                const double s_now = sum_s.value(), v_now = sum_v.value();
+                                if (snr_limit >= 0.0 && v_now > 0.0 && (s_now <= 0.0 || s_now * s_now < limit2 * v_now)) {
+                                    pending = true;
+                                    s_pending = s_now;
+                                    v_pending = v_now;
+                                    continue;
+                                }
+                                pending = false;
+                                snr = s_now / sqrt(v_now);
+                                if (!(snr <= snr_limit)) break;
+                            }
+                            if (sc.tid == 0) {
+                                double* x = win->xfer;
+                                x[0] = (double)width; x[1] = (double)common; x[2] = snr; x[3] = pending ? 1.0 : 0.0;
+                                x[4] = s_pending; x[5] = v_pending; x[6] = sum_s.s; x[7] = sum_s.c; x[8] = sum_v.s; x[9] = sum_v.c;
+                            }
+                        }
+                        sc.sync();
+                        {
+                            const double* x = win->xfer;
+                            width = (int)x[0]; common = (int)x[1]; snr = x[2]; pending = x[3] != 0.0;
+                            s_pending = x[4]; v_pending = x[5]; sum_s.s = x[6]; sum_s.c = x[7]; sum_v.s = x[8]; sum_v.c = x[9];
+                        }
+                        sc.sync();
+                        continue;
+                    }
+                }
                 width += 1;
                 if (dir == 0 ? (edge - width < 0) : (edge + width > ndisp)) {
                     width = (dir == 0) ? edge : ndisp - edge;
                     break;
                 }
                 int col = (dir == 0) ? edge - width : edge + width - 1;
+                stage(col, dir);
+                const bool col_good = win ? (win->good[col - win_lo] != 0) : (allgood && allgood[col]);
+                const double s_col = win ? win->S[col - win_lo] : S[col], v_col = win ? win->V[col - win_lo] : V[col];
                 bool any_short;
-                if (allgood && allgood[col]) {
+                if (col_good) {
                     common += 1;
                     any_short = ((double)(common + least) <= min_cols);
                 } else {
@@ -108,11 +185,25 @@ MOTES_HD int snr_bins_scan(const Scope& sc, const uint8_t* qual, const double* S
                     if (allgood) least = (int)sc.umin((unsigned long long)(unsigned)mine, cell);
                     any_short = sc.any(is_short) != 0;
                 }
-                sum_s.add(S[col]);
-                sum_v.add(V[col]);
+                sum_s.add(s_col);
+                sum_v.add(v_col);
                 if (any_short) continue;
-                snr = sum_s.value() / sqrt(sum_v.value());
+                // tracing.py:272-278: snr = sum / sqrt(sum of variances), tested against the limit.  The division and
+                // the square root sit on the serial chain, so a window that is below the limit by a clear margin
+                // (1e-12 relative, ten thousand times the rounding of either side) is passed over without them; the
+                // decision, and the S/N stored with the bin, still come from the exact expression.
+                const double s_now = sum_s.value(), v_now = sum_v.value();
+                if (snr_limit >= 0.0 && v_now > 0.0 &&
+                    (s_now <= 0.0 || s_now * s_now < limit2 * v_now)) {
+                    pending = true;             // below the limit: the value itself is only needed if the frame ends here
+                    s_pending = s_now;
+                    v_pending = v_now;
+                    continue;
+                }
+                pending = false;
+                snr = s_now / sqrt(v_now);
             }
+            if (pending) snr = s_pending / sqrt(v_pending);      // the bin ended at the frame edge
             if (sc.tid == 0) {
                 if (dir == 0) {
                     tmp_i[2 * n_blue] = edge - width;

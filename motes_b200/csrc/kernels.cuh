@@ -134,19 +134,26 @@ qual_columns_kernel(const uint8_t* __restrict__ qual, size_t qual_stride, int ns
 }
 
 // a5: greedy S/N binning, one CTA per frame (tracing.py:114-254).
+constexpr int kBinWindow = 1024;       // columns staged in shared memory at a time (bins.cuh: BinWindow)
 __global__ void __launch_bounds__(1024)
 bins_kernel(const uint8_t* __restrict__ qual, size_t qual_stride, const uint8_t* __restrict__ allgood, const double* __restrict__ S,
             const double* __restrict__ V, int nspat, int ndisp, double snr_limit, double min_cols, int cap,
             int32_t* __restrict__ bins_i /* [F][2*cap] */, double* __restrict__ bins_snr /* [F][cap] */,
             int32_t* __restrict__ tmp_i, double* __restrict__ tmp_snr, int32_t* __restrict__ nbins) {
-    extern __shared__ __align__(16) int bins_counts[];
+    extern __shared__ __align__(16) int bins_counts[];      // nspat counters (padded to 16 bytes), then the column window
     __shared__ unsigned long long cell;
     BlockScope sc{(int)threadIdx.x};
     const int f = blockIdx.x;
+    BinWindow win;
+    win.S = reinterpret_cast<double*>(bins_counts + ((nspat + 3) & ~3));
+    win.V = win.S + kBinWindow;
+    win.xfer = win.V + kBinWindow;
+    win.good = reinterpret_cast<uint8_t*>(win.xfer + 10);
+    win.cap = kBinWindow;
     int nb = snr_bins_scan(sc, qual + (size_t)f * qual_stride, S + (size_t)f * ndisp, V + (size_t)f * ndisp, nspat,
                            ndisp, snr_limit, min_cols, bins_counts, bins_i + (size_t)f * 2 * cap,
                            bins_snr + (size_t)f * cap, tmp_i + (size_t)f * 2 * cap, tmp_snr + (size_t)f * cap,
-                           allgood + (size_t)f * ndisp, &cell);
+                           allgood + (size_t)f * ndisp, &cell, &win);
     if (threadIdx.x == 0) nbins[f] = nb;
 }
 

@@ -230,7 +230,7 @@ static int stage_bins(motes_handle* h, Batch& b, const uint8_t* qual, size_t qua
     StageTimer timer(h, ST_BINS);
     int threads = ((b.nspat + 31) / 32) * 32;
     if (threads > 1024) threads = 1024;
-    size_t smem = (size_t)b.nspat * sizeof(int);
+    size_t smem = (size_t)((b.nspat + 3) & ~3) * sizeof(int) + (size_t)kBinWindow * (2 * sizeof(double) + 1) + 10 * sizeof(double);
     qual_columns_kernel<<<dim3((b.ndisp + 127) / 128, b.F), 128, 0, h->stream>>>(qual, qual_stride, b.nspat, b.ndisp, b.allgood);
     MOTES_LAUNCHED(h);
     bins_kernel<<<b.F, threads, smem, h->stream>>>(qual, qual_stride, b.allgood, b.S, b.V, b.nspat, b.ndisp, snr_limit, min_cols,

@@ -64,8 +64,14 @@ extern "C" int hostsim_snr_bins(const double* data, const double* errs, const ui
     }
     unsigned long long cell = 0;
     motes::SeqScope sc;
+    // the staged column window and the run-ahead over all-good columns, as bins_kernel sets them up (a short
+    // window, so that refills in both scan directions are exercised)
+    const int cap = 37;
+    std::vector<double> wS(cap), wV(cap), xfer(10);
+    std::vector<uint8_t> wG(cap);
+    motes::BinWindow win{wS.data(), wV.data(), wG.data(), xfer.data(), cap};
     return motes::snr_bins_scan(sc, qual, S.data(), V.data(), nspat, ndisp, snr_limit, min_cols, counts.data(),
-                                bins_i, bins_snr, tmp_i.data(), tmp_snr.data(), allgood.data(), &cell);
+                                bins_i, bins_snr, tmp_i.data(), tmp_snr.data(), allgood.data(), &cell, &win);
 }
 
 extern "C" int hostsim_interp_limits(const double* table, int nb, int ndisp, double* out_lo, double* out_hi) {
