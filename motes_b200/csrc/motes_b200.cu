@@ -422,12 +422,10 @@ static int boot_hoist(motes_handle* h, const Batch& b, uint32_t* rng) {
     BootPlan plan;
     MOTES_TRY(boot_plan(h, b, &plan, h->hoist_ctas));
     if (!plan.ok || plan.wave != b.F) return MOTES_OK;
-    if (!h->ev_hoist[0]) {
-        MOTES_CUDA(cudaEventCreateWithFlags(&h->ev_hoist[0], cudaEventDisableTiming));
-        MOTES_CUDA(cudaEventCreateWithFlags(&h->ev_hoist[1], cudaEventDisableTiming));
-    }
-    MOTES_CUDA(cudaEventRecord(h->ev_hoist[0], h->stream));                // the generator states are on the device
-    MOTES_CUDA(cudaStreamWaitEvent(h->lane1_stream, h->ev_hoist[0], 0));
+    if (!h->ev_hoist[1]) MOTES_CUDA(cudaEventCreateWithFlags(&h->ev_hoist[1], cudaEventDisableTiming));
+    // The second stream already waits for the start-of-call event of run_frames_chunked, which follows the previous
+    // call's work and the upload of the generator states - but not the upload of the frames: from host buffers the
+    // generator runs while the frames are still on their way.
     MOTES_TRY(boot_generate(h, h->lane1_stream, nullptr, b.ndisp, plan, rng, 0, b.F, false));
     MOTES_CUDA(cudaEventRecord(h->ev_hoist[1], h->lane1_stream));
     plan.hoisted = true;
