@@ -168,6 +168,8 @@ def run_reference_arm(a):
     rate = cal_cols / cal_secs                       # columns/s of one core
     budget = 120.0 / max(1, total_steps)
     crop = int(min(a.ndisp, max(256, (budget * rate * 0.7) // 256 * 256)))
+    if a.cpu_sample_columns:
+        crop = int(min(crop, max(64, a.cpu_sample_columns)))
     ctx = mp.get_context("fork")
     with ctx.Pool(procs) as pool:
         def step(k):
