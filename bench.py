@@ -438,10 +438,25 @@ def run_b200_arm(a):
                     ncu_util = tj.get("ncu_utilisation", {}).get(dominant)
             except Exception:
                 pass
+            # the kernel closest to the memory roofline: measured DRAM bytes per launch (same ncu capture) over its
+            # CUDA-event time in this run
+            nearest = None
+            try:
+                if (w["frames_per_gpu"], w["nspat"], w["ndisp"]) == (F, ns, nd):
+                    for name, nbytes in tj["dram_bytes_per_launch"].items():
+                        if name in stage_ms and stage_ms[name]["ms_per_step"] > 0 and stage_ms[name]["launches_per_step"] > 0:
+                            per_launch_s = stage_ms[name]["ms_per_step"] * 1e-3 / stage_ms[name]["launches_per_step"]
+                            gbs = nbytes / per_launch_s / 1e9
+                            if nearest is None or gbs > nearest["achieved"]:
+                                nearest = {"kernel": name, "achieved": gbs, "unit": "GB/s", "frac": gbs / hbm_peak,
+                                           "dram_bytes_per_launch": nbytes, "kernel_ms_per_launch": per_launch_s * 1e3}
+            except Exception:
+                nearest = None
             roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                         "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                         "algorithmic_bytes_per_column": alg_bytes_per_col,
                         "kernel_ms_per_launch": 1e3 * dur / launches_dom, "ncu_utilisation": ncu_util,
+                        "nearest_to_hbm_roofline": nearest,
                         "note": "whole-path algorithmic bytes (17*nspat+80 per column) over the dominant stage's "
                                 "CUDA-event time (stage times are taken in separate profiling steps, each kernel alone: the "
                                 "timed steps overlap the generator with the localisation stages); the path is "
