@@ -131,6 +131,7 @@ struct motes_handle {
     int hoist_ctas = 8;          // MOTES_B200_HOIST_CTAS: generator CTAs per SM when it runs beside the localisation stages
     motes::BootPlan boot;
     cudaEvent_t ev_hoist[2] = {nullptr, nullptr};
+    bool upload_pending = false; // the frames of the running call are still being uploaded (host entry points)
     std::vector<motes::StageSpan> spans;
     double stage_ms[motes::ST_COUNT] = {0};
     long long stage_launches[motes::ST_COUNT] = {0};

@@ -422,10 +422,19 @@ static int boot_hoist(motes_handle* h, const Batch& b, uint32_t* rng) {
     BootPlan plan;
     MOTES_TRY(boot_plan(h, b, &plan, h->hoist_ctas));
     if (!plan.ok || plan.wave != b.F) return MOTES_OK;
-    if (!h->ev_hoist[1]) MOTES_CUDA(cudaEventCreateWithFlags(&h->ev_hoist[1], cudaEventDisableTiming));
+    if (!h->ev_hoist[0]) {
+        MOTES_CUDA(cudaEventCreateWithFlags(&h->ev_hoist[0], cudaEventDisableTiming));
+        MOTES_CUDA(cudaEventCreateWithFlags(&h->ev_hoist[1], cudaEventDisableTiming));
+    }
     // The second stream already waits for the start-of-call event of run_frames_chunked, which follows the previous
     // call's work and the upload of the generator states - but not the upload of the frames: from host buffers the
-    // generator runs while the frames are still on their way.
+    // generator runs while the frames are still on their way.  With the frames already on the device it is released
+    // together with the first kernels of the main stream instead, so that the two share the SMs from the start
+    // (released earlier it takes every SM first and the call gets slower, 185 against 175 ms per 128 frames).
+    if (!h->upload_pending) {
+        MOTES_CUDA(cudaEventRecord(h->ev_hoist[0], h->stream));
+        MOTES_CUDA(cudaStreamWaitEvent(h->lane1_stream, h->ev_hoist[0], 0));
+    }
     MOTES_TRY(boot_generate(h, h->lane1_stream, nullptr, b.ndisp, plan, rng, 0, b.F, false));
     MOTES_CUDA(cudaEventRecord(h->ev_hoist[1], h->lane1_stream));
     plan.hoisted = true;
@@ -1073,8 +1082,11 @@ static int run_frames_host_enqueue(motes_handle* h, double* data, double* errs, 
         }
         return MOTES_OK;
     };
-    return run_frames_chunked(h, d_data, d_errs, d_qual, nframes, nspat, ndisp, cap, p, d_seeing, d_pixres, d_rng,
-                              upload_chunk, emit);
+    h->upload_pending = true;
+    const int rc = run_frames_chunked(h, d_data, d_errs, d_qual, nframes, nspat, ndisp, cap, p, d_seeing, d_pixres, d_rng,
+                                      upload_chunk, emit);
+    h->upload_pending = false;
+    return rc;
 }
 
 int motes_run_frames_host(motes_handle* h, double* data, double* errs, const uint8_t* qual, int nframes, int nspat,
