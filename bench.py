@@ -2,14 +2,16 @@
 """Benchmark of the MOTES extraction hot path on B200: spectral columns extracted per second.
 
     python bench.py --gpus N --steps K --warmup W          # this repo's CUDA path
-    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference algorithm on host cores
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference itself on the host cores
 
 Workload (BASELINE.json configs[1] / configs[3]): FORS2-like 4096 x 400 float64 spectrograms, default
 MOTES flags (-k -ko 0 -m 15 -xs 10 -ks 100 -kf 3.0).  A step is one pass of the whole path
 (median fit -> S/N bins -> per-bin Moffat fits -> sky bootstrap + subtraction -> bins -> fits -> limits
--> optimal + aperture extraction) over `frames_per_gpu` frames on every GPU, followed, for N > 1, by the
-all-gather of the extracted spectra and limits.  frames_per_gpu defaults to 128 = 1024 / 8, so N = 8
-is exactly the 1024-frame batch of configs[3] (weak scaling: per-GPU work is fixed).
+-> optimal + aperture extraction) over `frames_per_gpu` frames on every GPU, followed, for N > 1, by ONE
+all-gather of the extracted spectra, limits and bin parameters.  frames_per_gpu defaults to 128 = 1024 / 8,
+so N = 8 is exactly the 1024-frame batch of configs[3] (weak scaling: per-GPU work is fixed);
+--total-frames 1024 splits that batch over the GPUs instead (strong scaling).  The other BASELINE.json shapes
+are reached with --nspat / --ndisp / --cosmic-fraction / --binning off (tools/config_sweep.sh).
 
 One JSON line is printed by rank 0; see the README / DESIGN.md for the meaning of every key.
 """
@@ -20,7 +22,6 @@ import argparse
 import ctypes
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -32,6 +33,9 @@ if ROOT not in sys.path:
 NSPAT, NDISP = 400, 4096            # configs[1]: FORS2-like 4096x400 spectrogram
 METRIC = "spectral columns extracted/sec (fit+sky+optimal)"
 UNIT = "columns/s"
+SHAPES = {(400, 4096): "C2 FORS2-like", (200, 3000): "C1 GMOS-like", (80, 24000): "C3 X-shooter-like NIR order",
+          (256, 2048): "C5a faint-source sweep", (512, 16384): "C5b faint-source sweep"}
+SEEING, PIXRES = 0.8, 0.16
 
 
 def parse():
@@ -41,19 +45,61 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames-per-gpu", type=int, default=128)
+    ap.add_argument("--total-frames", type=int, default=0,
+                    help="strong scaling: this many frames in all, split evenly over the GPUs (default: --frames-per-gpu each, weak)")
     ap.add_argument("--nspat", type=int, default=NSPAT)
     ap.add_argument("--ndisp", type=int, default=NDISP)
     ap.add_argument("--sky-order", type=int, default=0, help="MOTES -ko: 0 = bootstrap median sky (the headline workload), 1..5 = polynomial sky")
+    ap.add_argument("--cosmic-fraction", type=float, default=0.0, help="fraction of pixels hit by a cosmic ray (configs[2]: 0.01)")
+    ap.add_argument("--binning", default="on", choices=["on", "off"], help="off = -m 0 -xs 0 -ks 0 (configs[4]: every column its own bin)")
+    ap.add_argument("--input-dtype", default="f64", choices=["f64", "f32"],
+                    help="end-to-end leg: dtype of the host frames (f32 = what the GMOS harvester hands over, 4 B per pixel over PCIe)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-sample-columns", type=int, default=0, help="columns of one frame the CPU baseline runs (0 = auto)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the reference run on frame 0 of the timed batch")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end (host buffer) legs")
+    ap.add_argument("--cpu-sample-columns", type=int, default=0, help="columns of one frame the CPU legs run (0 = the whole frame)")
+    ap.add_argument("--cpu-procs", type=int, default=0, help="--impl reference: worker processes (0 = one per host core)")
     ap.add_argument("--profile-steps", type=int, default=1, help="extra untimed steps with per-stage CUDA events")
     return ap.parse_args()
 
 
+def workload_name(a):
+    """config.workload: named from the shape and flags actually run (BASELINE.json configs)."""
+    name = SHAPES.get((a.nspat, a.ndisp), "custom shape")
+    flags = "default MOTES flags (-m 15 -xs 10 -ks 100 -kf 3.0)" if a.binning == "on" else \
+        "binning off (-m 0 -xs 0 -ks 0: every column its own bin)"
+    cr = f", {100 * a.cosmic_fraction:g} % of the pixels hit by cosmic rays" if a.cosmic_fraction > 0 else ""
+    sky = "bit-exact numpy-MT19937 sky bootstrap" if a.sky_order == 0 else "bootstrap polynomial sky"
+    return f"{name} {a.ndisp}x{a.nspat} float64 frames{cr}, {flags}, sky order {a.sky_order}, {sky}"
+
+
+def run_config(a, world):
+    """The `config` object both arms print: it names the workload, not the arm."""
+    F = a.total_frames // world if a.total_frames else a.frames_per_gpu
+    return {"workload": workload_name(a), "nspat": a.nspat, "ndisp": a.ndisp, "frames_per_gpu": F, "frames_per_step": world * F,
+            "columns_per_step": world * F * a.ndisp,
+            "l2": f"inputs {2 * F * a.nspat * a.ndisp * 8 / 1e9:.2f} GB per GPU per step, larger than the 126 MB L2",
+            "parallelism": f"frames sharded over {world} GPU(s), one all-gather of spectra/limits/params" if world > 1 else "1 GPU"}
+
+
+def motes_args(a):
+    from motes_b200 import synth
+    over = {"sky_order": a.sky_order}
+    if a.binning == "off":
+        over.update(minimum_column_limit=0, extraction_snr_limit=0, sky_snr_limit=0)
+    return synth.default_args(**over)
+
+
 # ------------------------------------------------------------------------------------------ synthetic frames
-def make_frames_torch(nframes, nspat, ndisp, seed0, device):
+def frame_constants(seed):
+    k = seed % 17
+    return k, 3.2 + 0.05 * k, 0.37 + 0.11 * k, 900.0 + 20.0 * k, 120.0 + k
+
+
+def make_frames_torch(nframes, nspat, ndisp, seed0, device, cosmic_fraction=0.0):
     """FORS2-like frames on the device: Moffat trace (beta 3, curving centre, amplitude x2 along dispersion),
-    sky with ripple and sparse sky lines, Gaussian noise sqrt(signal + RN^2); errs = sigma, qual = 1."""
+    sky with ripple and sparse sky lines, Gaussian noise sqrt(signal + RN^2), optionally cosmic-ray hits of
+    +500..5000 counts; errs = sigma, qual = 1."""
     import torch
     data = torch.empty((nframes, nspat, ndisp), dtype=torch.float64, device=device)
     errs = torch.empty_like(data)
@@ -66,19 +112,47 @@ def make_frames_torch(nframes, nspat, ndisp, seed0, device):
     gen = torch.Generator(device=device)
     for i in range(nframes):
         gen.manual_seed(seed0 + i)
-        k = (seed0 + i) % 17
-        alpha = 3.2 + 0.05 * k
-        centre = nspat * 0.5 + 0.37 + 0.11 * k + 9.0 * (4.0 * tc * tc - 0.5)
+        k, alpha, offset, amp, level = frame_constants(seed0 + i)
+        centre = nspat * 0.5 + offset + 9.0 * (4.0 * tc * tc - 0.5)
         b = 1.0 + ((r - centre) ** 2) / (alpha * alpha)
-        trace = (900.0 + 20.0 * k) * (1.0 + t) / (b * b * b)
-        sky = (120.0 + k) * (1.0 + 0.3 * saw) + 400.0 * line
+        trace = amp * (1.0 + t) / (b * b * b)
+        sky = level * (1.0 + 0.3 * saw) + 400.0 * line
         signal = trace + sky[None, :]
         sigma = torch.sqrt(signal + 25.0)
         noise = torch.randn((nspat, ndisp), dtype=torch.float64, device=device, generator=gen)
-        data[i] = signal + sigma * noise
+        frame = signal + sigma * noise
+        if cosmic_fraction > 0.0:
+            hit = torch.rand((nspat, ndisp), dtype=torch.float64, device=device, generator=gen) < cosmic_fraction
+            boost = 500.0 + 4500.0 * torch.rand((nspat, ndisp), dtype=torch.float64, device=device, generator=gen)
+            frame = torch.where(hit, frame + boost, frame)
+        data[i] = frame
         errs[i] = sigma
     qual = torch.ones((nframes, nspat, ndisp), dtype=torch.uint8, device=device)
     return data, errs, qual
+
+
+def make_frame_numpy(nspat, ndisp, seed, cosmic_fraction=0.0):
+    """The same frame model as make_frames_torch on the host (numpy generator: other noise bits, same workload)."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    r = np.arange(nspat, dtype=np.float64)[:, None]
+    x = np.arange(ndisp, dtype=np.float64)[None, :]
+    t = x / ndisp
+    tc = t - 0.5
+    saw = (np.arange(ndisp) % 257).astype(np.float64) / 257.0
+    line = (((np.arange(ndisp) * 7919) % 97) < 3).astype(np.float64)
+    k, alpha, offset, amp, level = frame_constants(seed)
+    centre = nspat * 0.5 + offset + 9.0 * (4.0 * tc * tc - 0.5)
+    b = 1.0 + ((r - centre) ** 2) / (alpha * alpha)
+    trace = amp * (1.0 + t) / (b * b * b)
+    sky = level * (1.0 + 0.3 * saw) + 400.0 * line
+    signal = trace + sky[None, :]
+    sigma = np.sqrt(signal + 25.0)
+    frame = signal + sigma * rng.standard_normal((nspat, ndisp))
+    if cosmic_fraction > 0.0:
+        hit = rng.random((nspat, ndisp)) < cosmic_fraction
+        frame = np.where(hit, frame + 500.0 + 4500.0 * rng.random((nspat, ndisp)), frame)
+    return frame, sigma
 
 
 # ------------------------------------------------------------------------------------------ clocks
@@ -127,55 +201,97 @@ class ClockSampler(threading.Thread):
                 "samples": len(s)}
 
 
-# ------------------------------------------------------------------------------------------ CPU arm (oracle port)
-def _cpu_worker(job):
-    """One process: the reference algorithm (oracle port) on one cropped frame; returns (columns, seconds)."""
-    seed, nspat, ndisp, crop = job
-    import numpy as np
-    from motes_b200 import synth
+def bind_to_gpu_numa_node(local):
+    """Pin this rank's threads to the CPUs NVML reports as local to its GPU (pinned buffers allocated afterwards land on
+    that NUMA node by first touch).  Returns a description for the JSON line."""
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(visible.split(",")[local]) if visible and visible.split(",")[local].isdigit() else local
+        dev = nv.nvmlDeviceGetHandleByIndex(idx)
+        words = ((os.cpu_count() or 64) + 63) // 64
+        mask = nv.nvmlDeviceGetCpuAffinity(dev, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        want = cpus & allowed
+        if want:
+            os.sched_setaffinity(0, want)
+        return {"gpu_local_cpus": len(cpus), "bound_to": f"{min(want)}-{max(want)}" if want else "unchanged",
+                "allowed": len(allowed)}
+    except Exception as exc:
+        return {"bound_to": "unchanged", "why": f"{type(exc).__name__}: {exc}"[:120]}
+
+
+# ------------------------------------------------------------------------------------------ CPU legs
+def reference_runner():
+    """(run_frame, kind, description): the UNMODIFIED reference staged under oracle/_ref when present
+    (cpu_baseline.kind = "reference"), else the oracle port (kind = "port")."""
+    try:
+        from oracle import ref_runner
+        if ref_runner.available():
+            ref = ref_runner.load()
+            return ref_runner.run_frame, "reference", f"unmodified reference modules from {ref.origin}, stages in core.motes order"
+    except Exception:
+        pass
     from oracle import motes_oracle as mo
+    return mo.run_frame, "port", "oracle/motes_oracle.py (numpy + scipy least_squares as the reference calls them)"
+
+
+def _cpu_worker(job):
+    """One process, one thread: the reference on one synthetic frame of the workload; returns (columns, seconds)."""
+    seed, nspat, ndisp, crop, cosmic, binning, sky_order = job
     import warnings
-    spec = synth.config_spec("C2", seed=seed, nspat=nspat, ndisp=crop)
-    frame, axes, header = synth.make_frame(spec)
-    args = synth.default_args()
+    from types import SimpleNamespace
+    import numpy as np
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(1)
+    except Exception:
+        pass
+    from motes_b200 import synth            # numpy only: does not load libmotes_b200.so
+    run_frame, _, _ = reference_runner()
+    cols = crop if crop else ndisp
+    data, errs = make_frame_numpy(nspat, cols, seed, cosmic)
+    frame = {"data": data, "errs": errs, "qual": np.ones_like(data)}
+    axes = synth.make_axes(nspat, cols)
+    header = {"seeing": SEEING, "pixel_resolution": PIXRES}
+    args = motes_args(SimpleNamespace(sky_order=sky_order, binning=binning))
     t0 = time.perf_counter()
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        mo.run_frame(frame, axes, header, args, seed=seed)
-    return crop, time.perf_counter() - t0
+        run_frame(frame, axes, header, args, seed=seed)
+    return cols, time.perf_counter() - t0
 
 
-def cpu_baseline_single(nspat, ndisp, crop):
-    """Oracle port, 1 Python thread (the reference as shipped has no parallelism), one cropped frame."""
-    cols, secs = _cpu_worker((4242, nspat, ndisp, crop))
-    return {"value": cols / secs, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": f"1 frame {nspat}x{crop} (dispersion crop of the {ndisp}-column workload), whole path, "
-                      f"oracle/motes_oracle.py (numpy + scipy least_squares as the reference calls it), {secs:.1f} s"}
+def cpu_baseline_single(a):
+    """The reference as shipped: 1 Python thread, one frame of the workload (the >= 100x denominator of north_star)."""
+    _, kind, what = reference_runner()
+    cols, secs = _cpu_worker((4242, a.nspat, a.ndisp, min(a.cpu_sample_columns, a.ndisp), a.cosmic_fraction, a.binning, a.sky_order))
+    shape = f"{a.nspat}x{cols}" + ("" if cols == a.ndisp else f" (dispersion crop of the {a.ndisp}-column frame)")
+    return {"value": cols / secs, "unit": UNIT, "cores": 1, "kind": kind,
+            "sample": f"1 whole frame {shape} of the workload through the whole path, {what}, {secs:.1f} s"}
 
 
 def run_reference_arm(a):
-    """--impl reference: the reference algorithm on all host cores (one process per core over independent
-    frames; the reference itself is single-threaded).  Rank 0 only."""
+    """--impl reference: the reference's own CPU implementation of the path on all host cores (one single-threaded
+    process per core over independent frames - the reference itself has no parallelism).  Each step = one WHOLE frame
+    of the workload per process.  Rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
     import multiprocessing as mp
-    cores = os.cpu_count() or 1
-    procs = max(1, min(cores, 64))
-    total_steps = a.steps + a.warmup
-    # size the per-step sample so the run takes about two minutes: calibrate on a 256-column crop
-    cal_cols, cal_secs = _cpu_worker((1, a.nspat, a.ndisp, 256))
-    rate = cal_cols / cal_secs                       # columns/s of one core
-    budget = 120.0 / max(1, total_steps)
-    crop = int(min(a.ndisp, max(256, (budget * rate * 0.7) // 256 * 256)))
-    if a.cpu_sample_columns:
-        crop = int(min(crop, max(64, a.cpu_sample_columns)))
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    procs = a.cpu_procs or max(1, min(cores, 64))
+    crop = min(a.cpu_sample_columns, a.ndisp)
+    _, kind, what = reference_runner()
     ctx = mp.get_context("fork")
     with ctx.Pool(procs) as pool:
         def step(k):
-            jobs = [(1000 * k + p, a.nspat, a.ndisp, crop) for p in range(procs)]
+            jobs = [(1000 * k + p, a.nspat, a.ndisp, crop, a.cosmic_fraction, a.binning, a.sky_order) for p in range(procs)]
             t0 = time.perf_counter()
-            done = pool.map(_cpu_worker, jobs)
+            done = pool.map(_cpu_worker, jobs, chunksize=1)
             return sum(c for c, _ in done), time.perf_counter() - t0
         for k in range(a.warmup):
             step(k)
@@ -185,15 +301,16 @@ def run_reference_arm(a):
             cols += c
             secs += s
     value = cols / secs
+    cfg = run_config(a, world)
+    shape = f"{a.nspat}x{crop or a.ndisp}" + (f" (dispersion crop of the {a.ndisp}-column frame)" if crop and crop != a.ndisp else "")
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
-        "ms_per_step": 1e3 * secs / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic", "impl": "reference",
-        "config": {"workload": f"C2 FORS2-like {a.ndisp}x{a.nspat} float64 frames, default MOTES flags, sky order 0",
-                   "frames_per_step": procs, "columns_per_frame_sample": crop},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port",
-                         "sample": f"{procs} processes x 1 frame {a.nspat}x{crop} per step (dispersion crop), "
-                                   f"oracle/motes_oracle.py"},
+        "ms_per_step": 1e3 * secs / a.steps, "higher_is_better": True, "scaling": "strong" if a.total_frames else "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
+        "config": cfg,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": kind,
+                         "sample": f"each step = {procs} single-threaded processes x 1 whole frame {shape} of the workload "
+                                   f"(a bounded sample of the {cfg['frames_per_step']}-frame step), {what}"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -205,65 +322,72 @@ def run_b200_arm(a):
     import numpy as np
     import torch
     import torch.distributed as dist
-    from motes_b200 import _lib, pipeline, synth
+    from motes_b200 import _lib, distributed, pipeline, synth
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl b200 needs a CUDA device (there is no CPU fallback)")
+    numa = bind_to_gpu_numa_node(local)
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
 
-    F, ns, nd = a.frames_per_gpu, a.nspat, a.ndisp
-    args = synth.default_args(sky_order=a.sky_order)
+    if a.total_frames and a.total_frames % world:
+        raise SystemExit("--total-frames must be a multiple of the number of GPUs")
+    F = a.total_frames // world if a.total_frames else a.frames_per_gpu
+    ns, nd = a.nspat, a.ndisp
+    args = motes_args(a)
     h = _lib.Handle(local)
     stream = torch.cuda.current_stream(device)
     _lib.check(_lib.lib.motes_set_stream(h.raw, ctypes.c_void_p(stream.cuda_stream)))
     p = pipeline.make_params(args)
     cap = pipeline.bin_capacity(nd, p.minimum_column_limit)
+    seed0 = 100000 + rank * F
 
     # pristine inputs (device) + pinned host copies for the end-to-end leg
-    data0, errs0, qual = make_frames_torch(F, ns, nd, 100000 + rank * F, device)
+    data0, errs0, qual = make_frames_torch(F, ns, nd, seed0, device, a.cosmic_fraction)
     data = torch.empty_like(data0)
     errs = torch.empty_like(errs0)
-    seeing = torch.full((F,), 0.8, dtype=torch.float64, device=device)
-    pixres = torch.full((F,), 0.16, dtype=torch.float64, device=device)
+    seeing = torch.full((F,), SEEING, dtype=torch.float64, device=device)
+    pixres = torch.full((F,), PIXRES, dtype=torch.float64, device=device)
     seeds = (np.arange(F) + 7 + rank * F).astype(np.uint32)
     states0 = torch.from_numpy(pipeline.seed_states(seeds).view(np.int32)).to(device)
     states = torch.empty_like(states0)
 
-    out = {
-        "spectra": torch.zeros((F, 4, nd), dtype=torch.float64, device=device),
-        "ext_limits": torch.zeros((F, 2, nd), dtype=torch.float64, device=device),
-        "ext_params": torch.zeros((F, cap, 8), dtype=torch.float64, device=device),
-        "n_ext_bins": torch.zeros((F,), dtype=torch.int32, device=device),
-        "n_sky_bins": torch.zeros((F,), dtype=torch.int32, device=device),
-        "sky_model": torch.zeros((F, nd), dtype=torch.float64, device=device),
-        "frame_status": torch.zeros((F,), dtype=torch.int32, device=device),
-    }
-    if a.sky_order > 0:
-        out.pop("sky_model")            # (F, nspat, ndisp) for a polynomial sky: not part of the timed outputs
+    # the outputs every rank shares live in one flat buffer (motes_b200.distributed.GatherPlan): the C ABI writes
+    # straight into it and the step's only collective is one all-gather of that buffer
+    shared = ("spectra", "ext_limits", "ext_params", "n_ext_bins", "frame_status")
+    plan = distributed.GatherPlan({"spectra": ((4, nd), torch.float64), "ext_limits": ((2, nd), torch.float64),
+                                   "ext_params": ((cap, 8), torch.float64), "n_ext_bins": ((), torch.int32),
+                                   "frame_status": ((), torch.int32)}, F, device=device)
+    out = {k: plan.local(k) for k in shared}
+    extra_shapes = {"sky_limits": ((F, 2, nd), torch.float64), "sky_params": ((F, cap, 8), torch.float64),
+                    "ext_bins": ((F, cap, 2), torch.int32), "sky_bins": ((F, cap, 2), torch.int32),
+                    "ext_bin_snr": ((F, cap), torch.float64), "sky_bin_snr": ((F, cap), torch.float64),
+                    "n_sky_bins": ((F,), torch.int32), "median_params": ((F, 6), torch.float64), "scale": ((F,), torch.float64),
+                    "seeing_px": ((F,), torch.float64), "sky_flag": ((F, nd), torch.int32)}
+    if a.sky_order == 0:
+        extra_shapes.update({"sky_model": ((F, nd), torch.float64), "sky_uncertainty": ((F, nd), torch.float64)})
+    for k, (shape, dtype) in extra_shapes.items():
+        out[k] = torch.zeros(shape, dtype=dtype, device=device)
     ostruct = _lib.MotesOutputs()
     for k, v in out.items():
         setattr(ostruct, k, v.data_ptr())
-    gathered = None
-    if world > 1:
-        gathered = {k: torch.empty((world * F,) + tuple(out[k].shape[1:]), dtype=out[k].dtype, device=device)
-                    for k in ("spectra", "ext_limits", "ext_params")}
+
+    def run_dev(nframes):
+        _lib.check(_lib.lib.motes_run_frames_dev(h.raw, data.data_ptr(), errs.data_ptr(), qual.data_ptr(), nframes, ns, nd, cap,
+                                                 ctypes.byref(p), seeing.data_ptr(), pixres.data_ptr(),
+                                                 states.data_ptr(), ctypes.byref(ostruct)))
 
     def device_step():
         data.copy_(data0)
         errs.copy_(errs0)
         states.copy_(states0)
-        _lib.check(_lib.lib.motes_run_frames_dev(h.raw, data.data_ptr(), errs.data_ptr(), qual.data_ptr(), F, ns, nd, cap,
-                                                 ctypes.byref(p), seeing.data_ptr(), pixres.data_ptr(),
-                                                 states.data_ptr(), ctypes.byref(ostruct)))
-        if world > 1:
-            for k in gathered:
-                dist.all_gather_into_tensor(gathered[k], out[k])
+        run_dev(F)
+        plan.gather()
 
     def fence():
         if world > 1:
@@ -296,6 +420,65 @@ def run_b200_arm(a):
     columns_per_step = world * F * nd
     value = columns_per_step * a.steps / (ms * 1e-3)
 
+    # ---- parity of the timed batch.  (i) every rank: its block of the gathered buffer is what it produced;
+    # (ii) rank 0 recomputes the first frame of the LAST rank alone on its own GPU and compares bit for bit with the
+    # gathered block; (iii) rank 0 runs the reference on frame 0 of its timed batch (oracle/parity_report.py)
+    parity = None
+    frame0 = {k: v[0].cpu().numpy() for k, v in out.items()}
+    gathered_last = {}
+    if world > 1:
+        mine = all(torch.equal(plan.gathered(k)[rank], plan.local(k)) for k in ("spectra", "ext_limits", "ext_params"))
+        flag = torch.tensor([0 if mine else 1], dtype=torch.int32, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.SUM)
+        if int(flag.item()):
+            raise SystemExit("gathered outputs differ from what the ranks produced")
+        gathered_last = {k: plan.gathered(k)[world - 1, 0].clone() for k in ("spectra", "ext_limits")}
+    if not a.no_parity and rank == 0:
+        parity = {}
+        if world > 1:
+            other = world - 1
+            d1, e1, _ = make_frames_torch(1, ns, nd, 100000 + other * F, device, a.cosmic_fraction)
+            data[:1].copy_(d1)
+            errs[:1].copy_(e1)
+            st1 = pipeline.seed_states(np.array([7 + other * F], dtype=np.uint32))
+            states[:1].copy_(torch.from_numpy(st1.view(np.int32)).to(device))
+            run_dev(1)
+            torch.cuda.synchronize(device)
+            parity["gathered_equals_single_gpu_run"] = bool(all(torch.equal(out[k][0], gathered_last[k]) for k in gathered_last))
+            parity["gathered_frame_checked"] = f"rank {other} frame 0, recomputed alone on rank 0"
+        import warnings
+        from oracle import parity_report
+        run_frame, kind, what = reference_runner()
+        frame = {"data": data0[0].cpu().numpy(), "errs": errs0[0].cpu().numpy(), "qual": np.ones((ns, nd))}
+        header = {"seeing": SEEING, "pixel_resolution": PIXRES}
+        t0 = time.perf_counter()
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            want = run_frame(frame, synth.make_axes(ns, nd), header, args, seed=int(seeds[0]))
+        ne, nsb = int(frame0["n_ext_bins"]), int(frame0["n_sky_bins"])
+        got = {"median_params": frame0["median_params"], "scale": float(frame0["scale"]),
+               "ext_bins": np.column_stack([frame0["ext_bins"][:ne].astype(np.float64), frame0["ext_bin_snr"][:ne]]),
+               "ext_params": frame0["ext_params"][:ne], "ext_limits": frame0["ext_limits"],
+               "optimal": frame0["spectra"][0], "optimal_err": frame0["spectra"][1],
+               "aperture": frame0["spectra"][2], "aperture_err": frame0["spectra"][3]}
+        if args.subtract_sky:
+            got.update({"sky_bins": np.column_stack([frame0["sky_bins"][:nsb].astype(np.float64), frame0["sky_bin_snr"][:nsb]]),
+                        "sky_params": frame0["sky_params"][:nsb], "sky_limits": frame0["sky_limits"]})
+            if a.sky_order == 0:
+                modelled = frame0["sky_flag"] == 0
+                got.update({"sky_model": frame0["sky_model"][modelled], "sky_uncertainty": frame0["sky_uncertainty"][modelled]})
+            else:
+                want.pop("sky_model", None)
+        rep = parity_report.compare(got, want, ns)
+        parity.update({k: rep[k] for k in ("bins_exact", "sky_exact", "limit_flips", "sky_limit_flips", "flux_max_rel", "param_p99",
+                                           "param_max", "fits", "fits_beyond_1e-6", "columns") if k in rep})
+        parity["checker"] = f"{kind}: {what}; frame 0 of the timed batch ({time.perf_counter() - t0:.1f} s on one host thread)"
+        parity["tolerances"] = ("integers and sky model bit-exact; Moffat parameters rel 1e-6 in the bulk (tail: "
+                                "profiles/r02_parity.json); flux rel 1e-5")
+        parity["ok"] = bool(rep["bins_exact"] and rep.get("sky_exact", True) and rep["flux_max_rel"] < 1e-5
+                            and rep["limit_flips"] <= max(2, nd // 500) and parity.get("gathered_equals_single_gpu_run", True))
+    fence()
+
     # ---- per-stage CUDA-event timing (separate, untimed steps) for the roofline of the dominant kernel
     stage_ms = {}
     if a.profile_steps > 0:
@@ -310,20 +493,20 @@ def run_b200_arm(a):
         for i in range(n_st):
             name = _lib.lib.motes_profile_stage_name(i).decode()
             stage_ms[name] = {"ms_per_step": buf[i] / a.profile_steps, "launches_per_step": cnt[i] / a.profile_steps}
+    fp64_peak = ctypes.c_double(0.0)
+    _lib.check(_lib.lib.motes_fp64_peak(h.raw, ctypes.byref(fp64_peak)))
     fence()
 
-    # ---- BASELINE.json configs[1] as stated: ONE 4096 x 400 frame on one B200 (latency of a single-frame call)
+    # ---- BASELINE.json configs[1] as stated: ONE frame on one B200 (latency of a single-frame call)
     def single_step():
         data[:1].copy_(data0[:1])
         errs[:1].copy_(errs0[:1])
         states[:1].copy_(states0[:1])
-        _lib.check(_lib.lib.motes_run_frames_dev(h.raw, data.data_ptr(), errs.data_ptr(), qual.data_ptr(), 1, ns, nd, cap,
-                                                 ctypes.byref(p), seeing.data_ptr(), pixres.data_ptr(),
-                                                 states.data_ptr(), ctypes.byref(ostruct)))
+        run_dev(1)
     for _ in range(3):
         single_step()
     torch.cuda.synchronize(device)
-    # a one-frame call is ~90 short launches: its time is sensitive to whatever else the host is doing, so it is
+    # a one-frame call is a chain of short launches: its time is sensitive to whatever else the host is doing, so it is
     # taken as the best of four groups of five calls (the median group is reported beside it)
     groups = []
     for _ in range(4):
@@ -339,27 +522,155 @@ def run_b200_arm(a):
     fence()
 
     # ---- end-to-end leg: pinned host buffers -> H2D -> path -> D2H of the spectra, through the host C ABI
-    hd = torch.empty((F, ns, nd), dtype=torch.float64).pin_memory()
-    he = torch.empty((F, ns, nd), dtype=torch.float64).pin_memory()
+    e2e = None
+    if not a.no_e2e:
+        del data, errs, states
+        torch.cuda.empty_cache()
+        e2e = run_e2e_legs(a, _lib, pipeline, h, p, cap, F, ns, nd, data0, errs0, seeds, local, device, world, fence,
+                           columns_per_step)
+        e2e["numa"] = numa
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+        alg_bytes_per_col = 17 * ns + 80              # SURVEY.md §8d
+        dominant = max(stage_ms, key=lambda k: stage_ms[k]["ms_per_step"]) if stage_ms else None
+        roofline = None
+        if dominant:
+            roofline = make_roofline(stage_ms, dominant, alg_bytes_per_col, F, ns, nd, hbm_peak, peak_src, fp64_peak.value)
+        total_stage = sum(v["ms_per_step"] for v in stage_ms.values()) or 1.0
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong" if a.total_frames else "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": run_config(a, world),
+            "clocks": clocks,
+            "e2e": e2e,
+            "gpu_launches": int(launches),
+            "parity": parity,
+            "single_frame": {"ms": single_ms, "ms_median_group": single_ms_median, "columns_per_s": nd / (single_ms * 1e-3),
+                             "note": f"one {nd}x{ns} frame per call on one GPU, device-resident"
+                                     + (" (BASELINE.json configs[1] as stated)" if (ns, nd) == (NSPAT, NDISP) else "")},
+            "roofline": roofline,
+            "stage_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in stage_ms.items()},
+            "stage_share": {k: round(v["ms_per_step"] / total_stage, 4) for k, v in stage_ms.items()},
+            "gather": {"collectives_per_step": 1 if world > 1 else 0, "bytes_per_rank": plan.bytes_per_rank(),
+                       "api": "motes_b200.distributed.GatherPlan (outputs written in place, one all_gather_into_tensor)"},
+        }
+        if e2e is None:
+            line.pop("e2e")
+        if not a.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline_single(a)
+        emit(line)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def make_roofline(stage_ms, dominant, alg_bytes_per_col, F, ns, nd, hbm_peak, peak_src, fp64_peak_tflops):
+    dur = stage_ms[dominant]["ms_per_step"] * 1e-3
+    launches_dom = max(1.0, stage_ms[dominant]["launches_per_step"])
+    achieved = alg_bytes_per_col * F * nd / dur / 1e9
+    traffic = ncu_util = nearest = None
+    fp64 = {"peak_measured_tflops": fp64_peak_tflops,
+            "peak_source": "motes_fp64_peak: DFMA micro-benchmark on this GPU in this run (8 chains per thread, every SM full)"}
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        w = tj["workload"]
+        if (w["frames_per_gpu"], w["nspat"], w["ndisp"]) != (F, ns, nd):
+            tj = None
+    except Exception:
+        tj = None
+    if tj:
+        traffic = tj["dram_bytes_per_launch"].get(dominant)
+        ncu_util = tj.get("ncu_utilisation", {}).get(dominant)
+        # the kernel closest to the memory roofline: measured DRAM bytes per launch (ncu capture) over its CUDA-event time here
+        for name, nbytes in tj["dram_bytes_per_launch"].items():
+            if name in stage_ms and stage_ms[name]["ms_per_step"] > 0 and stage_ms[name]["launches_per_step"] > 0:
+                per_launch_s = stage_ms[name]["ms_per_step"] * 1e-3 / stage_ms[name]["launches_per_step"]
+                gbs = nbytes / per_launch_s / 1e9
+                if nearest is None or gbs > nearest["achieved"]:
+                    nearest = {"kernel": name, "achieved": gbs, "unit": "GB/s", "frac": gbs / hbm_peak,
+                               "dram_bytes_per_launch": nbytes, "kernel_ms_per_launch": per_launch_s * 1e3}
+        # FP64 roof of the fit stage: ncu-counted (2 x DFMA + DADD + DMUL, thread-level, predicated-on) per launch
+        # over the stage's CUDA-event time in this run, against the DFMA peak measured in this run
+        flop = tj.get("fp64_flop_per_launch", {}).get("bin_fits")
+        if flop and "bin_fits" in stage_ms and stage_ms["bin_fits"]["launches_per_step"] > 0:
+            per_launch_s = stage_ms["bin_fits"]["ms_per_step"] * 1e-3 / stage_ms["bin_fits"]["launches_per_step"]
+            tf = flop / per_launch_s / 1e12
+            fp64.update({"kernel": "bin_fits", "flop_per_launch": flop, "achieved_tflops": tf,
+                         "frac": tf / fp64_peak_tflops if fp64_peak_tflops > 0 else None,
+                         "pipe_fp64_pct": tj.get("ncu_utilisation", {}).get("bin_fits", {}).get("fp64_pipe_pct"),
+                         "flop_source": tj.get("fp64_flop_source")})
+    return {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+            "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+            "algorithmic_bytes_per_column": alg_bytes_per_col,
+            "kernel_ms_per_launch": 1e3 * dur / launches_dom, "ncu_utilisation": ncu_util,
+            "nearest_to_hbm_roofline": nearest, "fp64": fp64,
+            "note": "whole-path algorithmic bytes (17*nspat+80 per column) over the dominant stage's CUDA-event time "
+                    "(stage times are taken in separate profiling steps, each kernel alone: the timed steps overlap the "
+                    "generator with the localisation stages); the path is FP64 / integer-issue bound, not HBM bound "
+                    "(DESIGN.md), hence the fp64 object: the fit stage against the measured DFMA peak"}
+
+
+def run_e2e_legs(a, _lib, pipeline, h, p, cap, F, ns, nd, data0, errs0, seeds, local, device, world, fence, columns_per_step):
+    """End to end through the reference-facing C ABI with HOST buffers: every step uploads its frames from pinned
+    memory, runs the path and downloads its spectra."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    f32 = a.input_dtype == "f32"
+    hdt = torch.float32 if f32 else torch.float64
+    px_bytes = 4 if f32 else 8
+    hd = torch.empty((F, ns, nd), dtype=hdt).pin_memory()
+    he = torch.empty((F, ns, nd), dtype=hdt).pin_memory()
     hq = torch.ones((F, ns, nd), dtype=torch.uint8).pin_memory()
     hd.copy_(data0)
     he.copy_(errs0)
-    hsee = np.full(F, 0.8)
-    hpix = np.full(F, 0.16)
+    hsee = np.full(F, SEEING)
+    hpix = np.full(F, PIXRES)
     hstates0 = pipeline.seed_states(seeds)
-    hout = {"spectra": torch.zeros((F, 4, nd), dtype=torch.float64).pin_memory(),
-            "frame_status": torch.zeros((F,), dtype=torch.int32).pin_memory()}
-    hstruct = _lib.MotesOutputs()
-    for k, v in hout.items():
-        setattr(hstruct, k, v.data_ptr())
-    h2d = F * ns * nd * (8 + 8 + 1) + F * (625 * 4 + 16)
+    h2d = F * ns * nd * (2 * px_bytes + 1) + F * (625 * 4 + 16)
+
+    def make_out():
+        o = {"spectra": torch.zeros((F, 4, nd), dtype=torch.float64).pin_memory(),
+             "frame_status": torch.zeros((F,), dtype=torch.int32).pin_memory()}
+        st = _lib.MotesOutputs()
+        for k, v in o.items():
+            setattr(st, k, v.data_ptr())
+        return o, st
+    hout, hstruct = make_out()
     d2h = hout["spectra"].numel() * 8 + F * 4 + F * 625 * 4
+
+    # host -> device bandwidth of this rank's pinned buffers with every rank copying at once (the e2e leg's ceiling)
+    stage = torch.empty((F, ns, nd), dtype=hdt, device=device)
+    stage.copy_(hd, non_blocking=True)
+    fence()
+    t0 = time.perf_counter()
+    for _ in range(2):
+        stage.copy_(hd, non_blocking=True)
+    fence()
+    h2d_gbs = 2 * hd.numel() * px_bytes / (time.perf_counter() - t0) / 1e9
+    del stage
+    torch.cuda.empty_cache()
+
+    def call(hh, st_ptr, ostr, wait):
+        if f32:
+            return _lib.lib.motes_run_frames_host_f32(hh.raw, hd.data_ptr(), he.data_ptr(), hq.data_ptr(), F, ns, nd, cap,
+                                                      ctypes.byref(p), hsee.ctypes.data, hpix.ctypes.data, st_ptr, 0,
+                                                      1 if wait else 0, ctypes.byref(ostr))
+        fn = _lib.lib.motes_run_frames_host if wait else _lib.lib.motes_run_frames_host_async
+        return fn(hh.raw, hd.data_ptr(), he.data_ptr(), hq.data_ptr(), F, ns, nd, cap, ctypes.byref(p), hsee.ctypes.data,
+                  hpix.ctypes.data, st_ptr, 0, ctypes.byref(ostr))
 
     def e2e_step():
         hst = hstates0.copy()
-        _lib.check(_lib.lib.motes_run_frames_host(h.raw, hd.data_ptr(), he.data_ptr(), hq.data_ptr(), F, ns, nd, cap,
-                                                  ctypes.byref(p), hsee.ctypes.data, hpix.ctypes.data, hst.ctypes.data, 0,
-                                                  ctypes.byref(hstruct)))
+        _lib.check(call(h, hst.ctypes.data, hstruct, True))
     e2e_steps = max(1, min(a.steps, 3))
     e2e_step()
     fence()
@@ -367,24 +678,18 @@ def run_b200_arm(a):
     for _ in range(e2e_steps):
         e2e_step()
     fence()
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=device)
+    te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_sync_value = columns_per_step * e2e_steps / float(te.item())
 
-    # the same with two batches in flight: motes_run_frames_host_async on two handles, so that the upload of
-    # step k+1 runs under the kernels of step k (what a caller with a stream of batches does); every step still
-    # uploads its own inputs and downloads its own spectra inside the timed region
-    del data, errs, states
-    torch.cuda.empty_cache()
+    # the same with two batches in flight: the async entry point on two handles, so that the upload of step k+1 runs
+    # under the kernels of step k (what a caller with a stream of batches does); every step still uploads its own
+    # inputs and downloads its own spectra inside the timed region
     h2 = _lib.Handle(local)
     handles = [h, h2]
-    houts = [hout, {"spectra": torch.zeros((F, 4, nd), dtype=torch.float64).pin_memory(),
-                    "frame_status": torch.zeros((F,), dtype=torch.int32).pin_memory()}]
-    hstructs = [hstruct, _lib.MotesOutputs()]
-    for k, v in houts[1].items():
-        setattr(hstructs[1], k, v.data_ptr())
+    hout2, hstruct2 = make_out()
+    houts, hstructs = [hout, hout2], [hstruct, hstruct2]
     hsts = [torch.from_numpy(hstates0.view(np.int32).copy()).pin_memory() for _ in range(2)]
     hstates0_t = torch.from_numpy(hstates0.view(np.int32))
 
@@ -394,9 +699,7 @@ def run_b200_arm(a):
             if k >= 2:
                 _lib.check(_lib.lib.motes_synchronize(handles[i].raw))
             hsts[i].copy_(hstates0_t)
-            _lib.check(_lib.lib.motes_run_frames_host_async(handles[i].raw, hd.data_ptr(), he.data_ptr(), hq.data_ptr(), F, ns,
-                                                            nd, cap, ctypes.byref(p), hsee.ctypes.data, hpix.ctypes.data,
-                                                            hsts[i].data_ptr(), 0, ctypes.byref(hstructs[i])))
+            _lib.check(call(handles[i], hsts[i].data_ptr(), hstructs[i], False))
         for hh in handles:
             _lib.check(_lib.lib.motes_synchronize(hh.raw))
 
@@ -412,88 +715,17 @@ def run_b200_arm(a):
     e2e_value = columns_per_step * pipe_steps / float(te.item())
     if not np.array_equal(houts[0]["spectra"].numpy(), houts[1]["spectra"].numpy()):
         raise SystemExit("end-to-end leg: the two in-flight batches (same inputs) returned different spectra")
-
-    if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-        alg_bytes_per_col = 17 * ns + 80              # SURVEY.md §8d
-        dominant = max(stage_ms, key=lambda k: stage_ms[k]["ms_per_step"]) if stage_ms else None
-        roofline = None
-        if dominant:
-            dur = stage_ms[dominant]["ms_per_step"] * 1e-3
-            launches_dom = max(1.0, stage_ms[dominant]["launches_per_step"])
-            achieved = alg_bytes_per_col * F * nd / dur / 1e9
-            traffic = None                  # DRAM bytes per launch of that kernel from the committed ncu capture
-            ncu_util = None                 # issue-slot / FP64-pipe utilisation of that kernel, same capture
-            try:
-                tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-                w = tj["workload"]
-                if (w["frames_per_gpu"], w["nspat"], w["ndisp"]) == (F, ns, nd):
-                    traffic = tj["dram_bytes_per_launch"].get(dominant)
-                    ncu_util = tj.get("ncu_utilisation", {}).get(dominant)
-            except Exception:
-                pass
-            # the kernel closest to the memory roofline: measured DRAM bytes per launch (same ncu capture) over its
-            # CUDA-event time in this run
-            nearest = None
-            try:
-                if (w["frames_per_gpu"], w["nspat"], w["ndisp"]) == (F, ns, nd):
-                    for name, nbytes in tj["dram_bytes_per_launch"].items():
-                        if name in stage_ms and stage_ms[name]["ms_per_step"] > 0 and stage_ms[name]["launches_per_step"] > 0:
-                            per_launch_s = stage_ms[name]["ms_per_step"] * 1e-3 / stage_ms[name]["launches_per_step"]
-                            gbs = nbytes / per_launch_s / 1e9
-                            if nearest is None or gbs > nearest["achieved"]:
-                                nearest = {"kernel": name, "achieved": gbs, "unit": "GB/s", "frac": gbs / hbm_peak,
-                                           "dram_bytes_per_launch": nbytes, "kernel_ms_per_launch": per_launch_s * 1e3}
-            except Exception:
-                nearest = None
-            roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                        "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
-                        "algorithmic_bytes_per_column": alg_bytes_per_col,
-                        "kernel_ms_per_launch": 1e3 * dur / launches_dom, "ncu_utilisation": ncu_util,
-                        "nearest_to_hbm_roofline": nearest,
-                        "note": "whole-path algorithmic bytes (17*nspat+80 per column) over the dominant stage's "
-                                "CUDA-event time (stage times are taken in separate profiling steps, each kernel alone: the "
-                                "timed steps overlap the generator with the localisation stages); the path is "
-                                "FP64/integer-latency bound, not HBM bound (DESIGN.md)"}
-        total_stage = sum(v["ms_per_step"] for v in stage_ms.values()) or 1.0
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-            "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"C2 FORS2-like {nd}x{ns} float64 frames (C4 batch slice), default MOTES flags, sky order {a.sky_order}, "
-                                   f"bit-exact numpy-MT19937 sky bootstrap",
-                       "frames_per_gpu": F, "frames_per_step": world * F, "columns_per_step": columns_per_step,
-                       "l2": f"inputs {2 * F * ns * nd * 8 / 1e9:.2f} GB per GPU per step, larger than the 126 MB L2",
-                       "parallelism": f"frames sharded over {world} GPU(s), all-gather of spectra/limits/params" if world > 1
-                                      else "1 GPU"},
-            "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": pipe_steps,
-                    "api": "motes_run_frames_host_async on two handles (pinned host buffers; every step uploads its inputs, "
-                           "runs the path and downloads its spectra; two steps in flight so the next upload overlaps the "
-                           "kernels)",
-                    "one_call_at_a_time": {"value": e2e_sync_value, "steps": e2e_steps,
-                                           "api": "motes_run_frames_host (H2D + path + D2H, then return)"}},
-            "gpu_launches": int(launches),
-            "single_frame": {"ms": single_ms, "ms_median_group": single_ms_median, "columns_per_s": nd / (single_ms * 1e-3),
-                             "note": "BASELINE.json configs[1] as stated: one 4096x400 frame per call on one GPU, device-resident"},
-            "roofline": roofline,
-            "stage_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in stage_ms.items()},
-            "stage_share": {k: round(v["ms_per_step"] / total_stage, 4) for k, v in stage_ms.items()},
-        }
-        if not a.no_cpu_baseline and world == 1:
-            crop = a.cpu_sample_columns or 2048
-            line["cpu_baseline"] = cpu_baseline_single(ns, nd, min(crop, nd))
-        emit(line)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    if np.any(houts[0]["frame_status"].numpy() != 0):
+        raise SystemExit("end-to-end leg: frames failed on the device")
+    api = "motes_run_frames_host_f32 (wait = 0)" if f32 else "motes_run_frames_host_async"
+    return {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": pipe_steps,
+            "input_dtype": a.input_dtype,
+            "api": f"{api} on two handles (pinned host buffers; every step uploads its inputs, runs the path and downloads "
+                   "its spectra; two steps in flight so the next upload overlaps the kernels)",
+            "h2d_gbs_measured": h2d_gbs,
+            "h2d_bound_columns_per_s": F * nd * world / (h2d / (h2d_gbs * 1e9)) if h2d_gbs > 0 else None,
+            "one_call_at_a_time": {"value": e2e_sync_value, "steps": e2e_steps,
+                                   "api": "the synchronous entry point (H2D + path + D2H, then return)"}}
 
 
 RESULT_FD = None

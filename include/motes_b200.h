@@ -61,6 +61,11 @@ int motes_synchronize(motes_handle* h);
 /* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */
 long long motes_launch_count(motes_handle* h);
 
+/* FP64 roof of the handle's device: a DFMA micro-benchmark (8 independent chains per thread, every SM full),
+ * best of four timed launches, in TFLOP/s counting an FMA as two.  The denominator of bench.py's roofline.fp64
+ * (the reference has no counterpart). */
+int motes_fp64_peak(motes_handle* h, double* tflops);
+
 /* Optional per-stage timing with CUDA events on the handle's stream.  Stages: see
  * motes_profile_stage_name().  ms / launches: motes_profile_stage_count() entries, accumulated since
  * the last reset; motes_profile_read synchronises the stream. */

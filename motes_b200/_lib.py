@@ -66,6 +66,7 @@ SIGNATURES = {
     "motes_profile_stage_count": (ctypes.c_int, []),
     "motes_profile_stage_name": (ctypes.c_char_p, [c_int]),
     "motes_profile_read": (ctypes.c_int, [c_handle, c_dp, ctypes.POINTER(ctypes.c_longlong), c_int]),
+    "motes_fp64_peak": (ctypes.c_int, [c_handle, c_dp]),
     "motes_bin_capacity": (ctypes.c_int, [c_int, ctypes.c_double]),
     "motes_seed_states": (ctypes.c_int, [c_u32p, c_int, c_u32p]),
     "motes_run_frames_host": (ctypes.c_int, [c_handle, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int,

@@ -3,6 +3,7 @@
 #include "kernels.cuh"
 #include "skyseg.cuh"
 #include "mtjump.hpp"
+#include "peak.cuh"
 #include <utility>
 
 namespace motes {
@@ -990,6 +991,32 @@ int motes_profile_read(motes_handle* h, double* ms, long long* launches, int res
         if (launches) launches[i] = h->stage_launches[i];
         if (reset) { h->stage_ms[i] = 0; h->stage_launches[i] = 0; }
     }
+    return MOTES_OK;
+}
+
+int motes_fp64_peak(motes_handle* h, double* tflops) {
+    if (!h || !tflops) return fail_arg("motes_fp64_peak: null argument");
+    MOTES_CUDA(cudaSetDevice(h->device));
+    MOTES_TRY(h->counters.ensure(256));
+    const int iters = 4096, ctas = h->sm_count * 8;
+    const double flop = 2.0 * 4.0 * kPeakChains * (double)iters * (double)kPeakThreads * (double)ctas;
+    cudaEvent_t a, b;
+    MOTES_CUDA(cudaEventCreate(&a));
+    MOTES_CUDA(cudaEventCreate(&b));
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        MOTES_CUDA(cudaEventRecord(a, h->stream));
+        fp64_peak_kernel<<<ctas, kPeakThreads, 0, h->stream>>>(h->counters.as<double>(), iters, 0.999999, 1e-9);
+        MOTES_LAUNCHED(h);
+        MOTES_CUDA(cudaEventRecord(b, h->stream));
+        MOTES_CUDA(cudaEventSynchronize(b));
+        float ms = 0.f;
+        MOTES_CUDA(cudaEventElapsedTime(&ms, a, b));
+        if (rep > 0 && ms > 0.f && flop / (ms * 1e9) > best) best = flop / (ms * 1e9);    // first launch is warm-up
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    *tflops = best;
     return MOTES_OK;
 }
 

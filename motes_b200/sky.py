@@ -92,7 +92,7 @@ def sky_locator(frame_dict, axes_dict, data_scaling_factor, header_parameters, b
     """sky.sky_locator (sky.py:46-174): ``(frame_dict, ndarray(nbins, 8), [lower, upper])``."""
     logger.info("Fitting Moffat Functions to each bin to localise sky.")
     params, table, _ = tracing.moffat_fitting_all(bin_parameters, frame_dict["data"], axes_dict, data_scaling_factor,
-                                                  header_parameters, motes_parameters.sky_fwhm_multiplier)
+                                                  header_parameters, motes_parameters.sky_fwhm_multiplier, handle=handle)
     logger.info("Fitting complete. Drawing target/sky boundaries.")
     limits = tracing.interpolate_extraction_lims(table, axes_dict["dispersion_axis_length"], handle=handle)
     logger.info("Subtracting sky.")

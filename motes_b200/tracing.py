@@ -48,7 +48,7 @@ def moffat_fit_batch(profiles, alpha0, handle=None, full_output=False):
     return params
 
 
-def moffat_least_squares(r, col, seeing, pixel_resolution):
+def moffat_least_squares(r, col, seeing, pixel_resolution, handle=None):
     """tracing.moffat_least_squares (tracing.py:550-607): list of the six best-fit parameters.
 
     ``r`` must be the pixel axis 0..n-1 that ``data_harvest`` builds (io/motesio.py:94); the
@@ -57,7 +57,7 @@ def moffat_least_squares(r, col, seeing, pixel_resolution):
     r = np.asarray(r, dtype=np.float64)
     if r.shape != np.shape(col) or not np.array_equal(r, np.arange(len(r), dtype=np.float64)):
         raise ValueError("motes_b200 fits on the pixel axis 0..n-1 produced by motesio.data_harvest")
-    params = moffat_fit_batch(np.asarray(col, dtype=np.float64)[None, :], seeing / pixel_resolution)
+    params = moffat_fit_batch(np.asarray(col, dtype=np.float64)[None, :], seeing / pixel_resolution, handle=handle)
     return [params[0, k] for k in range(6)]
 
 
@@ -69,12 +69,12 @@ def set_extraction_limits(moffat_parameters, width_multiplier=3.0):
     return [lower, upper, moffat_parameters[1]]
 
 
-def median_moffat_fitting(median_profile, header_parameters, spatial_axis):
+def median_moffat_fitting(median_profile, header_parameters, spatial_axis, handle=None):
     """tracing.median_moffat_fitting (tracing.py:403-456); overwrites header_parameters['seeing'] (tracing.py:449)."""
     centre_value = np.nanmedian(median_profile)
     data_scaling_factor = 10 ** np.abs(np.floor(np.log10(np.abs(centre_value))))
     params = moffat_least_squares(spatial_axis, median_profile * data_scaling_factor,
-                                  header_parameters["seeing"], header_parameters["pixel_resolution"])
+                                  header_parameters["seeing"], header_parameters["pixel_resolution"], handle=handle)
     header_parameters["seeing"] = common.moffat_fwhm(params[2], params[3])
     for k in (0, 4, 5):
         params[k] /= data_scaling_factor
@@ -129,11 +129,11 @@ def bin_profiles(data, bins, handle=None):
 
 
 def moffat_fitting(each_bin, data, axes_dict, data_scaling_factor, header_parameters, fwhm_multiplier,
-                   extraction_limits):
+                   extraction_limits, handle=None):
     """tracing.moffat_fitting (tracing.py:459-547) for one bin: ``(list[8], extraction_limits, bin_data)``."""
-    bin_data = bin_profiles(data, [each_bin])[0]
+    bin_data = bin_profiles(data, [each_bin], handle=handle)[0]
     params = moffat_least_squares(axes_dict["spatial_axis"], bin_data * data_scaling_factor,
-                                  header_parameters["seeing"], header_parameters["pixel_resolution"])
+                                  header_parameters["seeing"], header_parameters["pixel_resolution"], handle=handle)
     for k in (0, 4, 5):
         params[k] /= data_scaling_factor
     lower, upper, centre = set_extraction_limits(params, width_multiplier=fwhm_multiplier)
@@ -143,12 +143,12 @@ def moffat_fitting(each_bin, data, axes_dict, data_scaling_factor, header_parame
     return params, extraction_limits, bin_data
 
 
-def moffat_fitting_all(bins, data, axes_dict, data_scaling_factor, header_parameters, fwhm_multiplier):
+def moffat_fitting_all(bins, data, axes_dict, data_scaling_factor, header_parameters, fwhm_multiplier, handle=None):
     """All bins of a frame in two launches (profiles, fits): what the per-bin loops at core.py:200-212
     and sky.py:96-109 compute.  Returns ``(ndarray(nbins, 8), limit table (4, nbins), profiles)``."""
-    profiles = bin_profiles(data, bins)
+    profiles = bin_profiles(data, bins, handle=handle)
     alpha0 = header_parameters["seeing"] / header_parameters["pixel_resolution"]
-    fitted = moffat_fit_batch(profiles * data_scaling_factor, alpha0)
+    fitted = moffat_fit_batch(profiles * data_scaling_factor, alpha0, handle=handle)
     rows, table = [], []
     for b, p in zip(bins, fitted):
         p = [p[k] for k in range(6)]

@@ -1,0 +1,82 @@
+"""GPU path against the UNMODIFIED reference at the full sizes of BASELINE.json's configurations.
+
+The golden files (tests/golden/make_golden_fullsize.py) hold what the reference itself produced for the seeded
+synthetic frames of configs[1] (FORS2-like 4096x400 - the shape the headline metric is quoted on), configs[2]
+(X-shooter-like 24000x80 with 1 % cosmic rays) and configs[4] (2048x256 with binning on and off, 16384x512), so the
+comparison costs no CPU time on the GPU box.  Bar: bin edges bit-exact, integer extraction limits bit-exact up to a
+counted flip, bootstrap sky model bit-exact (device replay of numpy's MT19937), Moffat parameters inside the
+north_star tolerance in the bulk and inside the reference's own +-1-ulp self-noise in the tail, spectra rel 1e-5.
+Every report is also written to gpurun_out/parity_<case>.json (tools/parity_table.py collects them into
+profiles/r02_parity.json).
+"""
+import copy
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_golden, golden_inputs
+from parity import assert_within_reference_noise, param_errors
+
+pytestmark = pytest.mark.gpu
+
+CASES = ["c2_fors2_4096x400", "c3_xshooter_24000x80_cr", "c5a_2048x256_binned", "c5a_2048x256_unbinned",
+         "c5b_16384x512_binned"]
+
+
+def check_against_golden(name, out, g, nspat, max_flip_fraction=1 / 500):
+    from oracle import parity_report
+    rep = parity_report.compare(out, g, nspat, control=parity_report.control_of(g))
+    try:
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", f"parity_{name}.json"), "w") as fh:
+            json.dump(rep, fh, indent=1)
+    except OSError:
+        pass
+    assert rep["bins_exact"], "bin edges differ from the reference"
+    assert rep["scale_exact"]
+    assert rep["median_params_max"] < 1e-6
+    assert rep["limit_flips"] <= max(2, int(rep["columns"] * max_flip_fraction)), rep["limit_flips"]
+    if "sky_model" in g:
+        if rep.get("sky_limit_flips", 0) == 0:
+            assert rep["sky_exact"], "bootstrap sky model is not bit-exact although every column has the same sky pixels"
+        else:
+            assert rep["sky_max_rel"] < 1e-5
+    for key in ("sky_params", "ext_params"):
+        if key in g and len(g[key]):
+            err = param_errors(out[key], g[key], nspat)
+            assert_within_reference_noise(err, g, g[key][:, :6], 1.0, nspat, key="ctl_" + key)
+    assert rep["flux_max_rel"] < 1e-5, rep
+    for key in ("optimal", "optimal_err", "aperture", "aperture_err"):
+        assert rep[key + "_nan_pattern_equal"], key
+    return rep
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_full_size_configuration_matches_reference(name):
+    from motes_b200 import pipeline
+    meta, g = load_golden(name)
+    frame, axes, header, args = golden_inputs(meta)
+    out = pipeline.run_frame(copy.deepcopy(frame), axes, dict(header), args, seed=meta["rng_seed"])
+    rep = check_against_golden(name, out, g, frame["data"].shape[0])
+    print(name, {k: rep[k] for k in ("bins_exact", "sky_exact", "limit_flips", "flux_max_rel", "param_p99", "param_max",
+                                     "fits_beyond_1e-6", "fits") if k in rep})
+
+
+def test_fit_trajectories_match_scipy_at_full_size():
+    """configs[1]: every one of the 256 extraction-bin fits stops with the reference's status after the reference's
+    number of evaluations, at the reference's cost."""
+    from motes_b200 import pipeline, tracing
+    meta, g = load_golden("c2_fors2_4096x400")
+    frame, axes, header, args = golden_inputs(meta)
+    out = pipeline.run_frame(copy.deepcopy(frame), axes, dict(header), args, seed=meta["rng_seed"])
+    bins = [[int(a), int(b)] for a, b in g["ext_bins"][:, :2]]
+    profiles = tracing.bin_profiles(out["data_after"], bins)
+    params, info = tracing.moffat_fit_batch(profiles * g["scale"], float(g["seeing_px"]) / meta["spec"]["pixel_resolution"],
+                                            full_output=True)
+    ref = g["ext_fitinfo"]
+    assert np.all((info["status"] >= 1) & (info["status"] <= 4))
+    assert (info["status"] != ref[:, 2].astype(np.int32)).sum() <= len(ref) // 20, "stop reasons differ from scipy's in more than 5 % of the fits"
+    assert (info["nfev"] != ref[:, 0]).sum() <= len(ref) // 20, "evaluation counts drift from scipy's in more than 5 % of the fits"
+    assert np.allclose(info["cost"], ref[:, 3], rtol=1e-9)
