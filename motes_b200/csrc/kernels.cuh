@@ -460,6 +460,117 @@ moffat_fit_group_kernel(FitBatch fb, int group, unsigned int* __restrict__ queue
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// a3, lock-step rounds (large batches).  The group kernel above keeps a CTA's warps idle while one thread per fit
+// chooses the next step (ncu, round 1: 17 % of all stall samples on that barrier) and holds its group's states in
+// shared memory, which caps the fits in flight per SM at four.  Here the two phases are separate kernels over ALL
+// running fits of the batch, with the states in global memory (L2 resident: 648 B per fit):
+//
+//   fit_init_kernel    start point and bounds, one warp per fit; running fits enter list 0
+//   fit_sweep_kernel   one small CTA per running fit: fit_evaluate (residual sweep, accept / reject / stop,
+//                      Jacobian, QR) - no step-phase bubble, only the 7 m slab in shared memory
+//   fit_step_kernel    one THREAD per running fit, full warps: fit_propose; finished fits are written out,
+//                      the others enter the next round's list
+//   fit_finish_kernel  after kFitRounds rounds: the few fits still running, one CTA each, to the end
+//
+// Every fit sees exactly the arithmetic of the group kernel; the order of the lists does not enter any result.
+// ---------------------------------------------------------------------------------------------
+constexpr int kFitRoundsMax = 64;
+struct FitRounds {                                   // zeroed before every stage_fit call
+    unsigned int queue[kFitRoundsMax + 2];           // work counter of the sweep (finish) kernel of round r
+    unsigned int count[kFitRoundsMax + 2];           // fits running at the start of round r
+};
+
+__global__ void __launch_bounds__(256)
+fit_init_kernel(FitBatch fb, FitState* __restrict__ states, unsigned int* __restrict__ list, FitRounds* __restrict__ rounds) {
+    const int lane = threadIdx.x & 31;
+    const unsigned int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const unsigned int total = (unsigned int)fb.nframes * (unsigned int)fb.bound;
+    if (item >= total) return;
+    const int f = item / fb.bound, slot = item % fb.bound;
+    if (fb.nbins && slot >= fb.nbins[f]) return;
+    const size_t idx = (size_t)f * fb.cap + slot;
+    const double alpha0 = fit_frame_scalar(fb.alpha0, fb.alpha0_frame_stride, f, idx);
+    const double scale = fb.scale ? fit_frame_scalar(fb.scale, fb.scale_frame_stride, f, 0) : 1.0;
+    FitState* st = &states[item];
+    fit_start_warp(lane, fb.m, fb.profiles + idx * fb.m, scale, alpha0, st);
+    __syncwarp();
+    if (lane == 0) {
+        if (st->status == kStatusRunning) list[atomicAdd(&rounds->count[0], 1u)] = item;
+        else fit_finalize(fb, idx, *st);
+    }
+}
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 512 / THREADS)
+fit_sweep_kernel(FitBatch fb, FitState* __restrict__ states, const unsigned int* __restrict__ list,
+                 FitRounds* __restrict__ rounds, int round) {
+    extern __shared__ __align__(16) double fits_smem[];
+    __shared__ unsigned int s_item;
+    using Ctx = BlockCtx<THREADS>;
+    const int tid = threadIdx.x, m = fb.m;
+    Ctx ctx{tid, fits_smem + fit_sweep_doubles(m), 0};
+    const unsigned int n = rounds->count[round];
+    while (true) {
+        if (tid == 0) s_item = atomicAdd(&rounds->queue[round], 1u);
+        __syncthreads();
+        const unsigned int k = s_item;
+        __syncthreads();
+        if (k >= n) break;
+        const unsigned int item = list[k];
+        const int f = item / fb.bound, slot = item % fb.bound;
+        const size_t idx = (size_t)f * fb.cap + slot;
+        const double scale = fb.scale ? fit_frame_scalar(fb.scale, fb.scale_frame_stride, f, 0) : 1.0;
+        fit_evaluate(ctx, m, fb.profiles + idx * m, scale, fits_smem, &states[item]);
+    }
+}
+
+__global__ void __launch_bounds__(128)
+fit_step_kernel(FitBatch fb, FitState* __restrict__ states, const unsigned int* __restrict__ list,
+                unsigned int* __restrict__ list_next, FitRounds* __restrict__ rounds, int round) {
+    const unsigned int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= rounds->count[round]) return;
+    const unsigned int item = list[t];
+    FitState* st = &states[item];
+    if (fit_propose_call(fb.m, st)) {
+        list_next[atomicAdd(&rounds->count[round + 1], 1u)] = item;
+    } else {
+        const int f = item / fb.bound, slot = item % fb.bound;
+        fit_finalize(fb, (size_t)f * fb.cap + slot, *st);
+    }
+}
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 512 / THREADS)
+fit_finish_kernel(FitBatch fb, FitState* __restrict__ states, const unsigned int* __restrict__ list,
+                  FitRounds* __restrict__ rounds, int round) {
+    extern __shared__ __align__(16) double fitf_smem[];
+    __shared__ unsigned int s_item;
+    using Ctx = BlockCtx<THREADS>;
+    const int tid = threadIdx.x, m = fb.m;
+    Ctx ctx{tid, fitf_smem + fit_sweep_doubles(m), 0};
+    const unsigned int n = rounds->count[round];
+    while (true) {
+        if (tid == 0) s_item = atomicAdd(&rounds->queue[round], 1u);
+        __syncthreads();
+        const unsigned int k = s_item;
+        __syncthreads();
+        if (k >= n) break;
+        const unsigned int item = list[k];
+        const int f = item / fb.bound, slot = item % fb.bound;
+        const size_t idx = (size_t)f * fb.cap + slot;
+        const double scale = fb.scale ? fit_frame_scalar(fb.scale, fb.scale_frame_stride, f, 0) : 1.0;
+        FitState* st = &states[item];
+        while (true) {
+            fit_evaluate(ctx, m, fb.profiles + idx * m, scale, fitf_smem, st);
+            int running = 0;
+            if (tid == 0) running = fit_propose_call(m, st) ? 1 : 0;
+            if (!__syncthreads_or(running)) break;
+        }
+        if (tid == 0) fit_finalize(fb, idx, *st);
+    }
+}
+
 // a6 (second half): un-scale, extraction limits, limit table row and the 8-vector of a bin
 // (tracing.py:517-545).  One thread per (frame, slot).
 __global__ void bin_post_kernel(int nframes, int bound, int cap, const int32_t* __restrict__ nbins,

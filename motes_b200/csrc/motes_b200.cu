@@ -10,7 +10,7 @@ namespace motes {
 
 // Work-area slots inside motes_handle::work
 enum WorkSlot { W_STATE = 0, W_F64, W_I32, W_U8, W_SORTED, W_RANKS, W_PROFILES, W_GOODROW, W_YSCRATCH, W_MODEL, W_MODELERR,
-                W_STREAM, W_WINDOWS, W_SNAPS, W_SEGI, W_SUBS, W_YPOOL };
+                W_STREAM, W_WINDOWS, W_SNAPS, W_SEGI, W_SUBS, W_YPOOL, W_FITSTATE, W_FITLIST };
 
 // Device-side working set of one batch.  All pointers are carved out of handle scratch.
 struct Batch {
@@ -173,10 +173,50 @@ static int stage_fit_warp(motes_handle* h, const FitBatch& fb) {
 // four warps: 75-76 ms; one warp per group of 8 / 16 / 32 fits with warp-wide sweeps and no CTA barriers: 96-106 ms;
 // a single Householder body instead of six specialisations: 81 ms.  ncu: instruction-cache hit rate 62 %, FP64 pipe
 // 19 %, issue 25 % - the kernel streams ~110 KB of mostly straight-line FP64 code per fit and round.
+// Lock-step rounds (kernels.cuh: fit_init / fit_sweep / fit_step / fit_finish): the default for large batches.
+template <int THREADS>
+static int stage_fit_rounds_t(motes_handle* h, const FitBatch& fb) {
+    const long long items = (long long)fb.nframes * fb.bound;
+    const size_t smem = (fit_sweep_doubles(fb.m) + BlockCtx<THREADS>::kRedDoubles) * sizeof(double);
+    if (smem > h->smem_optin) return fail_arg("nspat too large for the shared-memory fit slab");
+    MOTES_TRY(h->work[W_FITSTATE].ensure((size_t)items * sizeof(FitState) + sizeof(FitRounds) + 256));
+    MOTES_TRY(h->work[W_FITLIST].ensure((size_t)items * 2 * sizeof(unsigned int) + 256));
+    FitRounds* rounds = h->work[W_FITSTATE].as<FitRounds>();
+    FitState* states = reinterpret_cast<FitState*>(reinterpret_cast<char*>(rounds) + ((sizeof(FitRounds) + 255) & ~(size_t)255));
+    unsigned int* list[2] = {h->work[W_FITLIST].as<unsigned int>(), h->work[W_FITLIST].as<unsigned int>() + items};
+    MOTES_CUDA(cudaMemsetAsync(rounds, 0, sizeof(FitRounds), h->stream));
+    auto sweep = fit_sweep_kernel<THREADS>;
+    auto finish = fit_finish_kernel<THREADS>;
+    MOTES_CUDA(cudaFuncSetAttribute(sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MOTES_CUDA(cudaFuncSetAttribute(finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    MOTES_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sweep, THREADS, smem));
+    if (per_sm < 1) per_sm = 1;
+    long long grid = (long long)h->sm_count * per_sm;
+    if (grid > items) grid = items;
+    fit_init_kernel<<<(unsigned)((items + 7) / 8), 256, 0, h->stream>>>(fb, states, list[0], rounds);
+    MOTES_LAUNCHED(h);
+    const int nrounds = h->fit_rounds < kFitRoundsMax ? h->fit_rounds : kFitRoundsMax;
+    for (int r = 0; r < nrounds; ++r) {
+        sweep<<<(unsigned)grid, THREADS, smem, h->stream>>>(fb, states, list[r & 1], rounds, r);
+        MOTES_LAUNCHED(h);
+        fit_step_kernel<<<(unsigned)((items + 127) / 128), 128, 0, h->stream>>>(fb, states, list[r & 1], list[(r + 1) & 1], rounds, r);
+        MOTES_LAUNCHED(h);
+    }
+    finish<<<(unsigned)grid, THREADS, smem, h->stream>>>(fb, states, list[nrounds & 1], rounds, nrounds);
+    MOTES_LAUNCHED(h);
+    return MOTES_OK;
+}
+
 static int stage_fit(motes_handle* h, const FitBatch& fb) {
     if (fb.nframes <= 0 || fb.bound <= 0) return MOTES_OK;
     if (h->fit_mode == 1) return stage_fit_warp(h, fb);
     const long long items = (long long)fb.nframes * fb.bound;
+    if (h->fit_mode == 0 && items >= h->fit_rounds_min) {
+        if (h->fit_threads == 128) return stage_fit_rounds_t<128>(h, fb);
+        if (h->fit_threads == 32) return stage_fit_rounds_t<32>(h, fb);
+        return stage_fit_rounds_t<64>(h, fb);
+    }
     // enough groups to give every SM several CTAs; at most 32 fits (one per lane of the step phase) per group
     long long group = items / (8ll * h->sm_count);
     if (group < 1) group = 1;
@@ -900,7 +940,13 @@ int motes_create(int device, motes_handle** out) {
     const char* colw = getenv("MOTES_B200_COLUMN");
     if (colw) h->column_window = atoi(colw);
     const char* fitm = getenv("MOTES_B200_FIT");              // "warp": round-1 one-warp-per-fit kernel
-    h->fit_mode = (fitm && strcmp(fitm, "warp") == 0) ? 1 : 0;
+    h->fit_mode = (fitm && strcmp(fitm, "warp") == 0) ? 1 : (fitm && strcmp(fitm, "group") == 0) ? 2 : 0;
+    const char* fit_threads = getenv("MOTES_B200_FIT_THREADS");   // threads per fit of the lock-step sweep kernel: 32, 64, 128
+    if (fit_threads && atoi(fit_threads) > 0) h->fit_threads = atoi(fit_threads);
+    const char* fit_rounds = getenv("MOTES_B200_FIT_ROUNDS");     // lock-step rounds before the finishing kernel
+    if (fit_rounds && atoi(fit_rounds) > 0) h->fit_rounds = atoi(fit_rounds);
+    const char* fit_min = getenv("MOTES_B200_FIT_MIN");           // fits per call from which the lock-step rounds are used
+    if (fit_min && atoll(fit_min) >= 0) h->fit_rounds_min = atoll(fit_min);
     const char* budget = getenv("MOTES_B200_STREAM_GB");
     if (budget && atof(budget) > 0.0) h->stream_budget = (size_t)(atof(budget) * 1073741824.0);
     const char* hoist = getenv("MOTES_B200_HOIST");            // "0": generate the bootstrap stream where it is consumed

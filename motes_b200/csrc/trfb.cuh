@@ -29,8 +29,10 @@ struct FitState {
     int nfev, njev, status, first;
 };
 
-// Scratch of the sweep phases: unit [m] pow cache, a [7 m] Jacobian columns + residual column.
-MOTES_HD size_t fit_sweep_doubles(int m) { return (size_t)8 * m; }
+// Scratch of the sweep phases: a [7 m] = six Jacobian columns + the residual column.  The pow cache of the residual
+// sweep (unit [m]) shares the storage of column 0: the thread that owns point i reads unit[i] before it writes the
+// point's six column entries, and after the QR the columns are dead (R and Q^T f live in FitState).
+MOTES_HD size_t fit_sweep_doubles(int m) { return (size_t)7 * m; }
 
 // ---- start point and bounds -------------------------------------------------------------------
 // Replicated serial scan of the profile (every lane of the calling scope computes the same values).
@@ -349,7 +351,7 @@ MOTES_HD void fit_evaluate(const Ctx& ctx, int m, const double* profile, double 
     constexpr int n = kParams;
     const bool leader = ctx.lane == 0;
     double* unit = slab;
-    double* a = slab + m;
+    double* a = slab;
     double* fcol = a + 6 * (size_t)m;
     double x[n], lb[n], ub[n];
     const bool first = st->first != 0;

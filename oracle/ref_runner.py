@@ -1,8 +1,8 @@
 """Loader and stage driver for the UNMODIFIED reference.  TEST INFRASTRUCTURE ONLY.
 
-``load()`` imports the reference's hot-path modules either from the byte-compiled staging area ``oracle/_ref``
-(made by ``oracle/build_ref.py``; it travels to the GPU box) or, in the build container, straight from
-``/root/reference/src``.  ``matplotlib`` is absent from the image and ``motes/sky.py:10`` imports the plotting
+``load()`` imports the reference's hot-path modules either from the compiled staging area ``oracle/_ref``
+(marshalled module code objects made by ``oracle/build_ref.py``; it travels to the GPU box) or, in the build
+container, straight from ``/root/reference/src``.  ``matplotlib`` is absent from the image and ``motes/sky.py:10`` imports the plotting
 module, so empty stand-in modules are registered first; no plot function is reached while every ``diag_plot_*``
 flag is False.  ``motes.core`` needs astropy (absent), so ``run_frame`` drives the stage functions in the order of
 ``core.motes`` (``core.py:80-275``) on in-memory dictionaries - the same driver the golden files were made with.
@@ -13,6 +13,7 @@ Used by ``tests/`` (checker), ``__graft_entry__.smoke()`` and ``bench.py``'s CPU
 
 from __future__ import annotations
 
+import marshal
 import os
 import sys
 import types
@@ -26,8 +27,33 @@ REFERENCE_SRC = "/root/reference/src"
 _loaded = None
 
 
+STAGED_MARK = os.path.join(STAGED, "motes", "tracing.code")
+# import order of the staged modules (each only imports the ones before it, numpy and scipy)
+STAGED_ORDER = ("common", "logs", "diagnostics", "tracing", "extraction", "sky")
+
+
 def available() -> bool:
-    return os.path.exists(os.path.join(STAGED, "motes", "tracing.pyc")) or os.path.isdir(os.path.join(REFERENCE_SRC, "motes"))
+    return os.path.exists(STAGED_MARK) or os.path.isdir(os.path.join(REFERENCE_SRC, "motes"))
+
+
+def _import_staged():
+    """Execute the staged code objects into a ``motes`` package (sys.modules), dependencies first."""
+    pkg_dir = os.path.join(STAGED, "motes")
+    pkg = types.ModuleType("motes")
+    pkg.__path__ = [pkg_dir]
+    pkg.__file__ = os.path.join(pkg_dir, "__init__.code")
+    pkg.__package__ = "motes"
+    sys.modules["motes"] = pkg
+    with open(pkg.__file__, "rb") as fh:
+        exec(marshal.load(fh), pkg.__dict__)
+    for name in STAGED_ORDER:
+        mod = types.ModuleType(f"motes.{name}")
+        mod.__file__ = os.path.join(pkg_dir, name + ".code")
+        mod.__package__ = "motes"
+        sys.modules[mod.__name__] = mod
+        setattr(pkg, name, mod)
+        with open(mod.__file__, "rb") as fh:
+            exec(marshal.load(fh), mod.__dict__)
 
 
 def _stub_matplotlib():
@@ -47,7 +73,7 @@ def load(prefer_staged: bool = True):
     global _loaded
     if _loaded is not None:
         return _loaded
-    staged_ok = os.path.exists(os.path.join(STAGED, "motes", "tracing.pyc"))
+    staged_ok = os.path.exists(STAGED_MARK)
     source_ok = os.path.isdir(os.path.join(REFERENCE_SRC, "motes"))
     if not (staged_ok or source_ok):
         raise ImportError("the reference is neither staged under oracle/_ref (python oracle/build_ref.py in the build "
@@ -58,6 +84,8 @@ def load(prefer_staged: bool = True):
     if already:
         # the process has the reference imported already (a test that drives /root/reference directly): use that copy
         root = STAGED if already.startswith(STAGED) else os.path.dirname(os.path.dirname(already))
+    if root == STAGED and not already:
+        _import_staged()
     sys.path.insert(0, root)
     try:
         import motes.common as common
@@ -67,7 +95,7 @@ def load(prefer_staged: bool = True):
     finally:
         sys.path.remove(root)
     _loaded = types.SimpleNamespace(tracing=tracing, sky=sky, extraction=extraction, common=common,
-                                    origin="oracle/_ref (byte-compiled reference)" if root == STAGED else REFERENCE_SRC)
+                                    origin="oracle/_ref (compiled code objects of the reference modules)" if root == STAGED else REFERENCE_SRC)
     return _loaded
 
 

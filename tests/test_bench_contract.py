@@ -29,7 +29,7 @@ def test_reference_arm_prints_one_json_line():
     assert line["impl"] == "reference" and line["unit"] == "columns/s" and line["higher_is_better"] is True
     assert line["gpu_launches"] == 0 and line["value"] > 0 and line["steps"] == 1
     assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
-    staged = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "motes", "tracing.pyc")) or os.path.isdir("/root/reference/src/motes")
+    staged = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "motes", "tracing.code")) or os.path.isdir("/root/reference/src/motes")
     assert line["cpu_baseline"]["kind"] == ("reference" if staged else "port")
     assert line["e2e"] == {"value": line["value"], "unit": "columns/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in line["config"] and line["dtype"] == "f64" and line["data"] == "synthetic"

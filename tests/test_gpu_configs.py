@@ -36,7 +36,9 @@ def check_against_golden(name, out, g, nspat, max_flip_fraction=1 / 500):
         pass
     assert rep["bins_exact"], "bin edges differ from the reference"
     assert rep["scale_exact"]
-    assert rep["median_params_max"] < 1e-6
+    # the full-frame median fit against the reference's own +-1-ulp self-noise for the same fit
+    own = parity_report.param_errors(g["ctl_median_params"], g["median_params"], nspat).max() if "ctl_median_params" in g else 0.0
+    assert rep["median_params_max"] < max(1e-6, 5 * own), (rep["median_params_max"], own)
     assert rep["limit_flips"] <= max(2, int(rep["columns"] * max_flip_fraction)), rep["limit_flips"]
     if "sky_model" in g:
         if rep.get("sky_limit_flips", 0) == 0:

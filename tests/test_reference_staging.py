@@ -33,7 +33,7 @@ def test_build_recipe_stages_only_bytecode():
     """oracle/_ref holds compiled modules, never reference source text (and is git-ignored)."""
     staged = os.path.join(ROOT, "oracle", "_ref", "motes")
     if os.path.isdir(staged):
-        assert not [f for f in os.listdir(staged) if f.endswith(".py")]
+        assert not [f for f in os.listdir(staged) if f.endswith((".py", ".pyc"))]
     assert "oracle/_ref/" in open(os.path.join(ROOT, ".gitignore")).read()
 
 
