@@ -15,7 +15,7 @@ import threading
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmotes_b200.so")
+LIB_PATH = os.environ.get("MOTES_B200_LIB") or os.path.join(_HERE, "libmotes_b200.so")   # override: A/B builds (tools/)
 
 MOTES_OK, E_CUDA, E_ARG, E_NOMEM, E_NOSKY, E_FIT, E_INTERNAL = 0, -1, -2, -3, -4, -5, -6
 

@@ -122,8 +122,8 @@ struct motes_handle {
     int chunks = 0;              // MOTES_B200_CHUNKS: sub-batches per call (0 = auto)
     bool profiling = false;
     int fit_mode = 0;            // MOTES_B200_FIT: 0 auto (lock-step rounds for large batches, else the group kernel), 1 "warp", 2 "group"
-    int fit_threads = 64;        // MOTES_B200_FIT_THREADS: threads per fit of the lock-step sweep kernel
-    int fit_rounds = 24;         // MOTES_B200_FIT_ROUNDS: lock-step rounds before the finishing kernel takes the stragglers
+    int fit_threads = 0;         // MOTES_B200_FIT_THREADS: threads per fit of the lock-step sweep kernel (0 = by nspat)
+    int fit_rounds = 40;         // MOTES_B200_FIT_ROUNDS: lock-step rounds before the finishing kernel takes the stragglers
     long long fit_rounds_min = 2048;   // MOTES_B200_FIT_MIN: fits per call from which the lock-step rounds are used
     int column_window = -1;      // MOTES_B200_COLUMN: histogram window of the bootstrap column kernel (-1 = auto, 0 = exact slot kernel only)
     int boot_mode = 0;           // MOTES_B200_BOOTSTRAP: 0 segmented (default), 1 classic (one CTA per frame)

@@ -345,10 +345,8 @@ moffat_fit_kernel(FitBatch fb, unsigned int* work_counter) {
 // six-parameter logic runs once per fit instead of once per lane.  The states of the group live in
 // shared memory; nothing but the profiles is read from and the results written to HBM.
 // ---------------------------------------------------------------------------------------------
-constexpr int kFitThreads = 128;
 constexpr int kFitGroupMax = 32;
 constexpr int kStatusRetired = -200;          // finished (results written) or empty slot
-using FitBlockCtx = BlockCtx<kFitThreads>;
 
 __device__ __forceinline__ void fit_finalize(const FitBatch& fb, size_t idx, const FitState& st) {
     for (int k = 0; k < kParams; ++k) fb.params[idx * kParams + k] = st.x[k];
@@ -362,21 +360,34 @@ __device__ __forceinline__ double fit_frame_scalar(const double* base, size_t st
     return stride ? *reinterpret_cast<const double*>(reinterpret_cast<const char*>(base) + f * stride) : base[idx];
 }
 
-constexpr int kFitTeams = kFitThreads / 8;        // 8-lane teams of the step phase
-constexpr int kFitStepScratch = kFitTeams * 36 + 48;   // V per team, an identity R and a zero z for idle teams
+// Threads that cooperate on one fit, by profile length - the SAME choice in the group kernel (small batches) and in the
+// lock-step rounds (large batches), so that a fit's arithmetic (the order of its reductions) does not depend on the
+// size of the batch it arrives in.  Measured on B200 (32.9 k fits, lock-step rounds): one warp wins up to ~224 points
+// (80 points: 5.1 ms against 7.4 / 10.5 ms with two / four warps), two warps up to ~576 (400 points: 11.6 against 15.1
+// ms with four warps and 15.9 with one), four warps beyond.
+constexpr int kFitWarpMax = 224, kFitPairMax = 576;
+MOTES_HD int fit_threads_for(int m) { return m <= kFitWarpMax ? 32 : m <= kFitPairMax ? 64 : 128; }
 
-MOTES_HD size_t fit_group_smem(int m, int group) {
-    return (fit_sweep_doubles(m) + FitBlockCtx::kRedDoubles + kFitStepScratch) * sizeof(double) +
-           (size_t)group * sizeof(FitState);
-}
+template <int THREADS>
+struct FitGroupShape {
+    static constexpr int kTeams = THREADS / 8;                 // 8-lane teams of the step phase
+    static constexpr int kStepScratch = kTeams * 36 + 48;      // V per team, an identity R and a zero z for idle teams
+    static size_t smem(int m, int group) {
+        return (fit_sweep_doubles(m) + BlockCtx<THREADS>::kRedDoubles + kStepScratch) * sizeof(double) +
+               (size_t)group * sizeof(FitState);
+    }
+};
 // out of line: the step logic is long, runs once per round and must not bloat the sweep loop's registers
 __device__ __noinline__ bool fit_propose_call(int m, FitState* st) { return fit_propose(m, *st); }
 
-template <bool TEAM_STEP>
-__global__ void __launch_bounds__(kFitThreads, 4)
+template <bool TEAM_STEP, int THREADS>
+__global__ void __launch_bounds__(THREADS, 512 / THREADS)
 moffat_fit_group_kernel(FitBatch fb, int group, unsigned int* __restrict__ queue) {
     extern __shared__ __align__(16) double fitb_smem[];
     __shared__ unsigned int s_item;
+    using FitBlockCtx = BlockCtx<THREADS>;
+    constexpr int kFitTeams = FitGroupShape<THREADS>::kTeams, kFitStepScratch = FitGroupShape<THREADS>::kStepScratch;
+    constexpr int kFitThreads = THREADS;
     const int tid = threadIdx.x, warp = tid >> 5;
     const int m = fb.m;
     double* slab = fitb_smem;
@@ -384,7 +395,7 @@ moffat_fit_group_kernel(FitBatch fb, int group, unsigned int* __restrict__ queue
     double* vscratch = fitb_smem + fit_sweep_doubles(m) + FitBlockCtx::kRedDoubles;
     double* idle_R = vscratch + kFitTeams * 36;          // identity; idle_z = idle_R + 36 (zeros)
     FitState* states = reinterpret_cast<FitState*>(vscratch + kFitStepScratch);
-    if (tid < 48) idle_R[tid] = (tid < 36 && tid % 7 == 0) ? 1.0 : 0.0;
+    for (int i = tid; i < 48; i += THREADS) idle_R[i] = (i < 36 && i % 7 == 0) ? 1.0 : 0.0;
     const int lane = tid & 31, team = tid >> 3, sub = tid & 7;
     const unsigned int total = (unsigned int)fb.nframes * (unsigned int)fb.bound;
     while (true) {

@@ -208,15 +208,9 @@ static int stage_fit_rounds_t(motes_handle* h, const FitBatch& fb) {
     return MOTES_OK;
 }
 
-static int stage_fit(motes_handle* h, const FitBatch& fb) {
-    if (fb.nframes <= 0 || fb.bound <= 0) return MOTES_OK;
-    if (h->fit_mode == 1) return stage_fit_warp(h, fb);
+template <int THREADS>
+static int stage_fit_group_t(motes_handle* h, const FitBatch& fb) {
     const long long items = (long long)fb.nframes * fb.bound;
-    if (h->fit_mode == 0 && items >= h->fit_rounds_min) {
-        if (h->fit_threads == 128) return stage_fit_rounds_t<128>(h, fb);
-        if (h->fit_threads == 32) return stage_fit_rounds_t<32>(h, fb);
-        return stage_fit_rounds_t<64>(h, fb);
-    }
     // enough groups to give every SM several CTAs; at most 32 fits (one per lane of the step phase) per group
     long long group = items / (8ll * h->sm_count);
     if (group < 1) group = 1;
@@ -224,21 +218,34 @@ static int stage_fit(motes_handle* h, const FitBatch& fb) {
     // small groups are latency-bound (few fits in flight): spread each step over an 8-lane team; large groups are
     // throughput-bound: one thread per step costs an eighth of the instructions (B200, 128 frames: 76 vs 102 ms)
     const bool team_step = group < 16;
-    const size_t smem = fit_group_smem(fb.m, (int)group);
+    const size_t smem = FitGroupShape<THREADS>::smem(fb.m, (int)group);
     if (smem > h->smem_optin) return fail_arg("nspat too large for the shared-memory fit slab");
-    auto kernel = team_step ? moffat_fit_group_kernel<true> : moffat_fit_group_kernel<false>;
+    auto kernel = team_step ? moffat_fit_group_kernel<true, THREADS> : moffat_fit_group_kernel<false, THREADS>;
     MOTES_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    MOTES_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kFitThreads, smem));
+    MOTES_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, THREADS, smem));
     if (per_sm < 1) per_sm = 1;
     const long long groups = (items + group - 1) / group;
     long long grid = (long long)h->sm_count * per_sm;
     if (grid > groups) grid = groups;
     MOTES_TRY(h->counters.ensure(256));
     MOTES_CUDA(cudaMemsetAsync(h->counters.ptr, 0, 256, h->stream));
-    kernel<<<(unsigned)grid, kFitThreads, smem, h->stream>>>(fb, (int)group, h->counters.as<unsigned int>());
+    kernel<<<(unsigned)grid, THREADS, smem, h->stream>>>(fb, (int)group, h->counters.as<unsigned int>());
     MOTES_LAUNCHED(h);
     return MOTES_OK;
+}
+
+// Large batches: lock-step rounds; small ones (a single frame: latency matters, few fits in flight): the group kernel.
+// Both with fit_threads_for(nspat) threads per fit, so a fit's result does not depend on the batch it is part of.
+static int stage_fit(motes_handle* h, const FitBatch& fb) {
+    if (fb.nframes <= 0 || fb.bound <= 0) return MOTES_OK;
+    if (h->fit_mode == 1) return stage_fit_warp(h, fb);
+    const long long items = (long long)fb.nframes * fb.bound;
+    const int threads = h->fit_threads ? h->fit_threads : fit_threads_for(fb.m);
+    const bool rounds = h->fit_mode == 0 && items >= h->fit_rounds_min;
+    if (threads >= 128) return rounds ? stage_fit_rounds_t<128>(h, fb) : stage_fit_group_t<128>(h, fb);
+    if (threads <= 32) return rounds ? stage_fit_rounds_t<32>(h, fb) : stage_fit_group_t<32>(h, fb);
+    return rounds ? stage_fit_rounds_t<64>(h, fb) : stage_fit_group_t<64>(h, fb);
 }
 
 // median profile -> scale -> fit -> FWHM / binning rows  (core.py:80-100)

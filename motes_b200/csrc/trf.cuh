@@ -401,6 +401,78 @@ MOTES_HD void jacobi_svd6(const Ctx& ctx, const double* R, const double* z, doub
     ctx.sync();
 }
 
+// One-thread form of the warp variant below, operation for operation: the same round-robin pair ordering, the same
+// rotation formulas and the same association of the six-term sums (sum8's xor tree with two zero rows:
+// ((x0 + x1) + (x2 + x3)) + (x4 + x5)), so that a fit takes the same steps whether its step is chosen by one thread
+// (large batches: lock-step rounds) or by an 8-lane team (small batches: the group kernel).  wc / vc: column-major
+// 6 x 6 scratch.
+MOTES_HD double jacobi_rsqrt(double x) {
+#if defined(__CUDA_ARCH__)
+    return rsqrt(x);
+#else
+    return 1.0 / sqrt(x);
+#endif
+}
+MOTES_HD double jacobi_tree6(double x0, double x1, double x2, double x3, double x4, double x5) {
+    return ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + 0.0);
+}
+MOTES_HD double jacobi_dot6(const double* p, const double* q) {
+    return jacobi_tree6(p[0] * q[0], p[1] * q[1], p[2] * q[2], p[3] * q[3], p[4] * q[4], p[5] * q[5]);
+}
+MOTES_HD int jacobi_rotate_cols(double* wp, double* wq, double* vp, double* vq, double a, double b, double c) {
+    if (c == 0.0 || !(fabs(c) > kEps * trf_detail::ool_sqrt(a * b))) return 0;
+    const double d = b - a;
+    const double t = trf_detail::ool_div((2.0 * c) * (d >= 0.0 ? 1.0 : -1.0), fabs(d) + trf_detail::ool_sqrt(d * d + 4.0 * (c * c)));
+    const double cs = jacobi_rsqrt(1.0 + t * t);
+    const double sn = cs * t;
+    for (int r = 0; r < kParams; ++r) {
+        const double a_p = wp[r], a_q = wq[r], b_p = vp[r], b_q = vq[r];
+        wp[r] = cs * a_p - sn * a_q;
+        wq[r] = sn * a_p + cs * a_q;
+        vp[r] = cs * b_p - sn * b_q;
+        vq[r] = sn * b_p + cs * b_q;
+    }
+    return 1;
+}
+MOTES_HD void jacobi_svd6_serial(const double* R, const double* z, double* s, double* suf, double* V) {
+    constexpr int n = kParams;
+    // the five rounds of three disjoint pairs of jacobi_svd6_warp
+    const unsigned char pairs[5][6] = {{0, 5, 1, 4, 2, 3}, {0, 4, 3, 5, 1, 2}, {0, 3, 2, 4, 1, 5}, {0, 2, 1, 3, 4, 5}, {0, 1, 2, 5, 3, 4}};
+    double wc[n * n], vc[n * n];
+    for (int j = 0; j < n; ++j)
+        for (int r = 0; r < n; ++r) { wc[j * n + r] = R[r * n + j]; vc[j * n + r] = (r == j) ? 1.0 : 0.0; }
+    for (int sweep = 0; sweep < 40; ++sweep) {
+        int rot = 0;
+        for (int round = 0; round < 5; ++round) {
+            double a[3], b[3], c[3];
+            for (int k = 0; k < 3; ++k) {
+                const double* wp = wc + pairs[round][2 * k] * n;
+                const double* wq = wc + pairs[round][2 * k + 1] * n;
+                a[k] = jacobi_dot6(wp, wp);
+                b[k] = jacobi_dot6(wq, wq);
+                c[k] = jacobi_dot6(wp, wq);
+            }
+            for (int k = 0; k < 3; ++k) {
+                const int P = pairs[round][2 * k], Q = pairs[round][2 * k + 1];
+                rot |= jacobi_rotate_cols(wc + P * n, wc + Q * n, vc + P * n, vc + Q * n, a[k], b[k], c[k]);
+            }
+        }
+        if (!rot) break;
+    }
+    double sv[n], sz[n];
+    for (int j = 0; j < n; ++j) {
+        sv[j] = trf_detail::ool_sqrt(jacobi_dot6(wc + j * n, wc + j * n));
+        sz[j] = jacobi_dot6(wc + j * n, z);
+    }
+    for (int j = 0; j < n; ++j) {
+        int rank = 0;
+        for (int k = 0; k < n; ++k) rank += (sv[k] > sv[j]) || (sv[k] == sv[j] && k < j);
+        s[rank] = sv[j];
+        suf[rank] = sz[j];
+        for (int r = 0; r < n; ++r) V[r * n + rank] = vc[j * n + r];
+    }
+}
+
 #if defined(__CUDACC__)
 // Warp variant of the same decomposition.  Lane L (mod 8) < 6 owns row L of W (= R V) and of V;
 // the 15 column pairs of a sweep are visited in 5 rounds of 3 disjoint pairs (round-robin

@@ -15,8 +15,20 @@
 
 #include "trf.cuh"
 
+// Unroll factors of the sweeps' point loops (1 = not unrolled: smallest code; see qr_step).
+#ifndef MOTES_FIT_UNROLL_RES
+#define MOTES_FIT_UNROLL_RES 1
+#endif
+#ifndef MOTES_FIT_UNROLL_LIN
+#define MOTES_FIT_UNROLL_LIN 1
+#endif
+#ifndef MOTES_FIT_UNROLL_QR
+#define MOTES_FIT_UNROLL_QR 1
+#endif
+
 namespace motes {
 
+constexpr int kFitUnrollRes = MOTES_FIT_UNROLL_RES, kFitUnrollLin = MOTES_FIT_UNROLL_LIN, kFitUnrollQr = MOTES_FIT_UNROLL_QR;
 constexpr int kStatusRunning = -100;      // scipy's termination_status None
 
 struct FitState {
@@ -176,6 +188,7 @@ MOTES_HD bool residual_sweep_b(const Ctx& ctx, int m, const double* profile, dou
                                double* unit_out, double* out, double* cost) {
     double acc = 0.0;
     int finite = 1;
+#pragma unroll kFitUnrollRes
     for (int i = ctx.lane; i < m; i += Ctx::kLanes) {
         double r = (double)i;
         double u = moffat_unit(r, xe[1], xe[2], xe[3]);
@@ -234,18 +247,21 @@ MOTES_HD void qr_step(const Ctx& ctx, int m, double* a, double diag_hk, FitState
     double part[W], c[W];
 #pragma unroll
     for (int j = 0; j < W; ++j) part[j] = 0.0;
+    // (the point loops of the sweeps are not unrolled: six specialisations of this step, unrolled four times each,
+    // made the kernel 104 KB of code and instruction fetch its first stall reason - ncu, round 2)
+#pragma unroll kFitUnrollQr
     for (int i = ctx.lane; i < m; i += Ctx::kLanes) {
         double aki = colk[i];
 #pragma unroll
         for (int j = 0; j < W; ++j) part[j] = fma(aki, a[(size_t)(K + j) * m + i], part[j]);
     }
     ctx.template sum_vec<W>(part, c);
-    double ek = sqrt(diag_hk);
+    double ek = trf_detail::ool_sqrt(diag_hk);
     double norm2 = c[0] + ek * ek;
     if (norm2 > 0.0) {
-        double nrm = sqrt(norm2);
+        double nrm = trf_detail::ool_sqrt(norm2);
         double v_piv = ek + nrm;
-        double tau = 1.0 / (norm2 + nrm * ek);
+        double tau = trf_detail::ool_div(1.0, norm2 + nrm * ek);
         double wj[W];
 #pragma unroll
         for (int j = 1; j < W; ++j) wj[j] = c[j] * tau;
@@ -257,6 +273,7 @@ MOTES_HD void qr_step(const Ctx& ctx, int m, double* a, double diag_hk, FitState
                 if (K + j < n) st->R[K * n + K + j] = rkj; else st->z[K] = rkj;
             }
         }
+#pragma unroll kFitUnrollQr
         for (int i = ctx.lane; i < m; i += Ctx::kLanes) {
             double aki = colk[i];
 #pragma unroll
@@ -287,11 +304,12 @@ MOTES_HD void linearize(const Ctx& ctx, int m, const double* profile, double sca
     for (int k = 0; k < n; ++k) dx[k] = (x[k] + h[k]) - x[k];
     double inv_dx[n];
 #pragma unroll
-    for (int k = 0; k < n; ++k) inv_dx[k] = 1.0 / dx[k];
+    for (int k = 0; k < n; ++k) inv_dx[k] = ool_div(1.0, dx[k]);
     const double c1 = x[1] + h[1], a1 = x[2] + h[2];
     const double aa = x[2] * x[2], aa1 = a1 * a1;
-    const double inv_aa = 1.0 / aa, inv_aa1 = 1.0 / aa1;
+    const double inv_aa = ool_div(1.0, aa), inv_aa1 = ool_div(1.0, aa1);
     double gp[n] = {0, 0, 0, 0, 0, 0};
+#pragma unroll kFitUnrollLin
     for (int i = ctx.lane; i < m; i += Ctx::kLanes) {
         const double r = (double)i;
         const double yi = profile[i] * scale, fi = f0[i], u0 = unit[i];
@@ -323,12 +341,13 @@ MOTES_HD void linearize(const Ctx& ctx, int m, const double* profile, double sca
     double v[n], dv[n], d[n], diag_h[n];
     coleman_li(x, g, lb, ub, v, dv);
 #pragma unroll
-    for (int i = 0; i < n; ++i) { d[i] = sqrt(v[i]); diag_h[i] = g[i] * dv[i]; }
+    for (int i = 0; i < n; ++i) { d[i] = ool_sqrt(v[i]); diag_h[i] = g[i] * dv[i]; }
     if (leader) {
 #pragma unroll
         for (int k = 0; k < n; ++k) st->g[k] = g[k];
         for (int i = 0; i < n * n; ++i) st->R[i] = 0.0;
     }
+#pragma unroll 1
     for (int i = ctx.lane; i < m; i += Ctx::kLanes) {
 #pragma unroll
         for (int k = 0; k < n; ++k) a[(size_t)k * m + i] *= d[k];
@@ -490,8 +509,8 @@ MOTES_HD bool fit_propose(int m, FitState& st) {
     constexpr int n = kParams;
     ProposeVars pv;
     if (!propose_begin(&st, pv, true, &st)) return false;
-    double s[n], suf[n], V[n * n], w[n * n], vv[n * n];
-    jacobi_svd6(SeqCtx{}, st.R, st.z, w, vv, s, suf, V);
+    double s[n], suf[n], V[n * n];
+    jacobi_svd6_serial(st.R, st.z, s, suf, V);
     propose_finish(m, &st, pv, s, suf, V, true, &st);
     return true;
 }
