@@ -57,6 +57,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the reference run on frame 0 of the timed batch")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end (host buffer) legs")
+    ap.add_argument("--no-single-frame", action="store_true", help="skip the one-frame-per-call latency leg")
     ap.add_argument("--cpu-sample-columns", type=int, default=0, help="columns of one frame the CPU legs run (0 = the whole frame)")
     ap.add_argument("--cpu-procs", type=int, default=0, help="--impl reference: worker processes (0 = one per host core)")
     ap.add_argument("--profile-steps", type=int, default=1, help="extra untimed steps with per-stage CUDA events")
@@ -503,13 +504,13 @@ def run_b200_arm(a):
         errs[:1].copy_(errs0[:1])
         states[:1].copy_(states0[:1])
         run_dev(1)
-    for _ in range(3):
+    for _ in range(0 if a.no_single_frame else 3):
         single_step()
     torch.cuda.synchronize(device)
     # a one-frame call is a chain of short launches: its time is sensitive to whatever else the host is doing, so it is
     # taken as the best of four groups of five calls (the median group is reported beside it)
     groups = []
-    for _ in range(4):
+    for _ in range(0 if a.no_single_frame else 4):
         sv0, sv1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         sv0.record(stream)
         for _ in range(5):
@@ -517,8 +518,8 @@ def run_b200_arm(a):
         sv1.record(stream)
         torch.cuda.synchronize(device)
         groups.append(sv0.elapsed_time(sv1) / 5.0)
-    single_ms = min(groups)
-    single_ms_median = sorted(groups)[len(groups) // 2]
+    single_ms = min(groups) if groups else float("nan")
+    single_ms_median = sorted(groups)[len(groups) // 2] if groups else float("nan")
     fence()
 
     # ---- end-to-end leg: pinned host buffers -> H2D -> path -> D2H of the spectra, through the host C ABI
@@ -564,6 +565,8 @@ def run_b200_arm(a):
         }
         if e2e is None:
             line.pop("e2e")
+        if a.no_single_frame:
+            line.pop("single_frame")
         if not a.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline_single(a)
         emit(line)

@@ -136,6 +136,14 @@ int motes_run_frames_dev(motes_handle* h, double* data, double* errs, const uint
 int motes_run_frames_host_async(motes_handle* h, double* data, double* errs, const uint8_t* qual, int nframes,
                                 int nspat, int ndisp, int cap, const motes_params* params, const double* seeing,
                                 const double* pixres, uint32_t* rng_states, int copy_back, const motes_outputs* out);
+/* The same path for frames held as float32 planes - what the GMOS harvester hands over: big-endian float32 straight
+ * from the FITS file (io/gmosio.py:40-52; big_endian != 0) or native float32.  The planes cross PCIe at 4 bytes per
+ * pixel and are widened to float64 on the device (exact), so the results are those of motes_run_frames_host on the
+ * same values converted on the host; nothing is written back into the caller's frames.  wait != 0: return when the
+ * results are in the output block (motes_run_frames_host semantics); wait == 0: motes_run_frames_host_async semantics. */
+int motes_run_frames_host_f32(motes_handle* h, const float* data, const float* errs, const uint8_t* qual, int nframes,
+                              int nspat, int ndisp, int cap, const motes_params* params, const double* seeing,
+                              const double* pixres, uint32_t* rng_states, int big_endian, int wait, const motes_outputs* out);
 /* float64 {0,1} quality frame -> uint8 on the device (harvesters produce float64, io/gmosio.py:50-52) */
 int motes_qual_pack_dev(motes_handle* h, const double* qual, size_t count, uint8_t* out);
 

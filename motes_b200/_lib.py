@@ -75,6 +75,9 @@ SIGNATURES = {
     "motes_run_frames_host_async": (ctypes.c_int, [c_handle, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int,
                                                    ctypes.POINTER(MotesParams), c_vp, c_vp, c_vp, c_int,
                                                    ctypes.POINTER(MotesOutputs)]),
+    "motes_run_frames_host_f32": (ctypes.c_int, [c_handle, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int,
+                                                 ctypes.POINTER(MotesParams), c_vp, c_vp, c_vp, c_int, c_int,
+                                                 ctypes.POINTER(MotesOutputs)]),
     "motes_run_frames_dev": (ctypes.c_int, [c_handle, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int,
                                             ctypes.POINTER(MotesParams), c_vp, c_vp, c_vp,
                                             ctypes.POINTER(MotesOutputs)]),

@@ -1027,4 +1027,26 @@ __global__ void qual_pack_kernel(const double* __restrict__ q, size_t n, uint8_t
     if (i < n) out[i] = (q[i] != 0.0) ? 1 : 0;
 }
 
+// float32 planes as the GMOS harvester hands them over (big-endian float32 straight from the FITS file,
+// io/gmosio.py:40-52) -> float64 frames: byte swap (optional) and exact widening, four pixels per thread.
+__global__ void __launch_bounds__(256)
+widen_f32_kernel(const uint32_t* __restrict__ src, size_t n, int swap, double* __restrict__ dst) {
+    const size_t i4 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15u) == 0;   // odd frame sizes
+    if (i4 + 3 < n && aligned) {
+        const uint4 w = *reinterpret_cast<const uint4*>(src + i4);
+        uint32_t v[4] = {w.x, w.y, w.z, w.w};
+        double o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) o[k] = (double)__uint_as_float(swap ? __byte_perm(v[k], 0u, 0x0123) : v[k]);
+        *reinterpret_cast<double2*>(dst + i4) = make_double2(o[0], o[1]);
+        *reinterpret_cast<double2*>(dst + i4 + 2) = make_double2(o[2], o[3]);
+    } else {
+        for (size_t i = i4; i < n && i < i4 + 4; ++i) {
+            const uint32_t v = src[i];
+            dst[i] = (double)__uint_as_float(swap ? __byte_perm(v, 0u, 0x0123) : v);
+        }
+    }
+}
+
 }  // namespace motes

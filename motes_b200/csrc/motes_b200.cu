@@ -1123,18 +1123,25 @@ int motes_run_frames_dev(motes_handle* h, double* data, double* errs, const uint
     return run_frames_chunked(h, data, errs, qual, nframes, nspat, ndisp, cap, p, seeing, pixres, rng_states, upload, emit);
 }
 
-static int run_frames_host_enqueue(motes_handle* h, double* data, double* errs, const uint8_t* qual, int nframes, int nspat,
+// `f32`: data / errs are float32 planes (`swap`: big-endian) that are widened on the device after a 4-byte-per-pixel
+// upload; otherwise float64.
+static int run_frames_host_enqueue(motes_handle* h, void* data_v, void* errs_v, const uint8_t* qual, int nframes, int nspat,
                                    int ndisp, int cap, const motes_params* params, const double* seeing, const double* pixres,
-                                   uint32_t* rng_states, int copy_back, const motes_outputs* out) {
-    MOTES_TRY(check_run_args(h, data, errs, qual, nframes, nspat, ndisp, cap, params, seeing, pixres, rng_states, out));
+                                   uint32_t* rng_states, int copy_back, const motes_outputs* out, bool f32 = false,
+                                   bool swap = false) {
+    MOTES_TRY(check_run_args(h, data_v, errs_v, qual, nframes, nspat, ndisp, cap, params, seeing, pixres, rng_states, out));
+    if (f32 && copy_back) return fail_arg("motes_run_frames_host_f32: copy_back is not available for float32 frames");
     MOTES_CUDA(cudaSetDevice(h->device));
     const motes_params p = *params;
     const motes_outputs o = *out;
     const size_t frame_px = (size_t)nspat * ndisp;
     const size_t npix = (size_t)nframes * frame_px;
+    double* data = static_cast<double*>(data_v);
+    double* errs = static_cast<double*>(errs_v);
     double *d_data, *d_errs, *d_seeing, *d_pixres;
     uint8_t* d_qual;
     uint32_t* d_rng = nullptr;
+    uint32_t *d_data32 = nullptr, *d_errs32 = nullptr;
     // frames go up sub-batch by sub-batch on the copy stream (below); the small per-frame arrays go now
     MOTES_TRY(upload<double>(h, h->stage[0], nullptr, npix, &d_data));
     MOTES_TRY(upload<double>(h, h->stage[1], nullptr, npix, &d_errs));
@@ -1142,10 +1149,25 @@ static int run_frames_host_enqueue(motes_handle* h, double* data, double* errs, 
     MOTES_TRY(upload(h, h->stage[3], seeing, (size_t)nframes, &d_seeing));
     MOTES_TRY(upload(h, h->stage[4], pixres, (size_t)nframes, &d_pixres));
     if (rng_states) MOTES_TRY(upload(h, h->stage[5], rng_states, (size_t)nframes * 625, &d_rng));
+    if (f32) {
+        MOTES_TRY(upload<uint32_t>(h, h->stage[8], nullptr, npix, &d_data32));
+        MOTES_TRY(upload<uint32_t>(h, h->stage[9], nullptr, npix, &d_errs32));
+    }
     auto upload_chunk = [&](int f0, int nf, cudaEvent_t ev) -> int {
         const size_t off = (size_t)f0 * frame_px, cnt = (size_t)nf * frame_px;
-        MOTES_CUDA(cudaMemcpyAsync(d_data + off, data + off, cnt * sizeof(double), cudaMemcpyHostToDevice, h->copy_stream));
-        MOTES_CUDA(cudaMemcpyAsync(d_errs + off, errs + off, cnt * sizeof(double), cudaMemcpyHostToDevice, h->copy_stream));
+        if (f32) {
+            const uint32_t* h_data = static_cast<const uint32_t*>(data_v);
+            const uint32_t* h_errs = static_cast<const uint32_t*>(errs_v);
+            MOTES_CUDA(cudaMemcpyAsync(d_data32 + off, h_data + off, cnt * 4, cudaMemcpyHostToDevice, h->copy_stream));
+            widen_f32_kernel<<<(unsigned)((cnt / 4 + 256) / 256), 256, 0, h->copy_stream>>>(d_data32 + off, cnt, swap ? 1 : 0, d_data + off);
+            MOTES_LAUNCHED(h);
+            MOTES_CUDA(cudaMemcpyAsync(d_errs32 + off, h_errs + off, cnt * 4, cudaMemcpyHostToDevice, h->copy_stream));
+            widen_f32_kernel<<<(unsigned)((cnt / 4 + 256) / 256), 256, 0, h->copy_stream>>>(d_errs32 + off, cnt, swap ? 1 : 0, d_errs + off);
+            MOTES_LAUNCHED(h);
+        } else {
+            MOTES_CUDA(cudaMemcpyAsync(d_data + off, data + off, cnt * sizeof(double), cudaMemcpyHostToDevice, h->copy_stream));
+            MOTES_CUDA(cudaMemcpyAsync(d_errs + off, errs + off, cnt * sizeof(double), cudaMemcpyHostToDevice, h->copy_stream));
+        }
         MOTES_CUDA(cudaMemcpyAsync(d_qual + off, qual + off, cnt, cudaMemcpyHostToDevice, h->copy_stream));
         MOTES_CUDA(cudaEventRecord(ev, h->copy_stream));
         return MOTES_OK;
@@ -1169,11 +1191,7 @@ static int run_frames_host_enqueue(motes_handle* h, double* data, double* errs, 
     return rc;
 }
 
-int motes_run_frames_host(motes_handle* h, double* data, double* errs, const uint8_t* qual, int nframes, int nspat,
-                          int ndisp, int cap, const motes_params* params, const double* seeing, const double* pixres,
-                          uint32_t* rng_states, int copy_back, const motes_outputs* out) {
-    int rc = run_frames_host_enqueue(h, data, errs, qual, nframes, nspat, ndisp, cap, params, seeing, pixres, rng_states,
-                                     copy_back, out);
+static int finish_host_call(motes_handle* h, int rc) {
     // the caller's buffers must not be touched after return, whatever happened
     if (h) {
         cudaStreamSynchronize(h->copy_stream);
@@ -1182,6 +1200,21 @@ int motes_run_frames_host(motes_handle* h, double* data, double* errs, const uin
         if (rc == MOTES_OK && e != cudaSuccess) return fail_cuda(e, "cudaStreamSynchronize", __FILE__, __LINE__);
     }
     return rc;
+}
+
+int motes_run_frames_host_f32(motes_handle* h, const float* data, const float* errs, const uint8_t* qual, int nframes,
+                              int nspat, int ndisp, int cap, const motes_params* params, const double* seeing,
+                              const double* pixres, uint32_t* rng_states, int big_endian, int wait, const motes_outputs* out) {
+    const int rc = run_frames_host_enqueue(h, const_cast<float*>(data), const_cast<float*>(errs), qual, nframes, nspat, ndisp, cap,
+                                           params, seeing, pixres, rng_states, 0, out, true, big_endian != 0);
+    return wait ? finish_host_call(h, rc) : rc;
+}
+
+int motes_run_frames_host(motes_handle* h, double* data, double* errs, const uint8_t* qual, int nframes, int nspat,
+                          int ndisp, int cap, const motes_params* params, const double* seeing, const double* pixres,
+                          uint32_t* rng_states, int copy_back, const motes_outputs* out) {
+    return finish_host_call(h, run_frames_host_enqueue(h, data, errs, qual, nframes, nspat, ndisp, cap, params, seeing, pixres,
+                                                       rng_states, copy_back, out));
 }
 
 int motes_run_frames_host_async(motes_handle* h, double* data, double* errs, const uint8_t* qual, int nframes, int nspat,

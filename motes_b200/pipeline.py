@@ -82,8 +82,14 @@ def run_frames(data, errs, qual, args, seeing, pixel_resolution, seeds=None, rng
     the other frames.
     """
     h = handle or _lib.default_handle()
-    d = _lib.f64(data)
-    e = _lib.f64(errs)
+    # float32 planes (what harvest_gmos hands over, big-endian, io/gmosio.py:40-52) travel as they are and are widened on
+    # the device; everything else is converted to little-endian float64 here
+    as_f32 = (not copy_back and np.asarray(data).dtype.kind == "f" and np.asarray(data).dtype.itemsize == 4
+              and np.asarray(errs).dtype == np.asarray(data).dtype)
+    if as_f32:
+        d, e = np.ascontiguousarray(data), np.ascontiguousarray(errs)
+    else:
+        d, e = _lib.f64(data), _lib.f64(errs)
     if d.ndim == 2:
         d, e = d[None], e[None]
         qual = np.asarray(qual)[None]
@@ -110,11 +116,17 @@ def run_frames(data, errs, qual, args, seeing, pixel_resolution, seeds=None, rng
         arr = np.zeros(shape, dtype=dtype)
         result[name] = arr
         setattr(out_struct, name, arr.ctypes.data)
+    rng_ptr = rng_states.ctypes.data if rng_states is not None else None
     with h.lock:
-        _lib.check(_lib.lib.motes_run_frames_host(
-            h.raw, d.ctypes.data, e.ctypes.data, q.ctypes.data, F, nspat, ndisp, cap, ctypes.byref(p),
-            see.ctypes.data, pix.ctypes.data, rng_states.ctypes.data if rng_states is not None else None,
-            int(bool(copy_back)), ctypes.byref(out_struct)))
+        if as_f32:
+            big_endian = int(d.dtype.byteorder == ">" or (d.dtype.byteorder == "=" and np.little_endian is False))
+            _lib.check(_lib.lib.motes_run_frames_host_f32(
+                h.raw, d.ctypes.data, e.ctypes.data, q.ctypes.data, F, nspat, ndisp, cap, ctypes.byref(p),
+                see.ctypes.data, pix.ctypes.data, rng_ptr, big_endian, 1, ctypes.byref(out_struct)))
+        else:
+            _lib.check(_lib.lib.motes_run_frames_host(
+                h.raw, d.ctypes.data, e.ctypes.data, q.ctypes.data, F, nspat, ndisp, cap, ctypes.byref(p),
+                see.ctypes.data, pix.ctypes.data, rng_ptr, int(bool(copy_back)), ctypes.byref(out_struct)))
     result["cap"] = cap
     if rng_states is not None:
         result["rng_states"] = rng_states

@@ -122,3 +122,21 @@ def test_linearity_property_full_size():
     cols = [100, 2048, 4000]
     for c in cols:
         assert a["spectra"][0, 2, c] == pytest.approx(frame["data"][lo[c]:hi[c], c].sum(), rel=1e-13)
+
+
+@pytest.mark.parametrize("dtype,config,over", [(">f4", "T1", {}), ("<f4", "T2", {}), (">f4", "T1", {"nspat": 97, "ndisp": 1003, "chip_gaps": ((333, 21),)})])
+def test_float32_planes_are_widened_on_the_device(dtype, config, over):
+    """GMOS planes arrive as big-endian float32 (gmosio.py:40-52).  motes_run_frames_host_f32 uploads them as they are
+    (4 bytes per pixel) and widens them on the device: every output equals, bit for bit, the float64 path on the same
+    values converted on the host - including frames whose pixel count is not a multiple of four."""
+    from motes_b200 import pipeline, synth
+    frame, axes, header = synth.make_frame(synth.config_spec(config, seed=41, **over))
+    args = synth.default_args()
+    d32, e32 = frame["data"].astype(dtype)[None], frame["errs"].astype(dtype)[None]
+    a = pipeline.run_frames(d32, e32, frame["qual"][None], args, header["seeing"], header["pixel_resolution"], seeds=[9], axes_dict=axes)
+    b = pipeline.run_frames(d32.astype(np.float64), e32.astype(np.float64), frame["qual"][None], args, header["seeing"],
+                            header["pixel_resolution"], seeds=[9], axes_dict=axes)
+    assert a["frame_status"][0] == 0
+    for key in pipeline.OUTPUT_SHAPES:
+        assert np.array_equal(a[key], b[key], equal_nan=True), key
+    assert np.array_equal(a["rng_states"], b["rng_states"])

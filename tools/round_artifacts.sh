@@ -1,11 +1,16 @@
-# usage (under gpurun): bash tools/round_artifacts.sh r01   -> gpurun_out/<tag>_*
-TAG=${1:-r01}
-python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest_gpu.log 2>&1; tail -2 gpurun_out/${TAG}_pytest_gpu.log
+# usage (under gpurun): bash tools/round_artifacts.sh r02   -> gpurun_out/<tag>_*
+# 1. pytest -m gpu   2. both bench arms   3. ncu launch list of ONE step (this repo's kernels only: torch's frame
+# generator is filtered out by name)   4. ncu --set full of the dominant kernels of that step
+TAG=${1:-r02}
+MINE='regex:moffat|fit_|sky_|mt_|seg_plan|row_median|frame_p|column_stats|qual_|bins_kernel|bin_p|limits_|optimal_|widen_|poly_|fp64_peak'
+ONE_STEP="python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-parity --no-e2e --no-single-frame --profile-steps 0"
+python -m pytest tests -m gpu -q > gpurun_out/${TAG}_pytest_gpu.log 2>&1; tail -2 gpurun_out/${TAG}_pytest_gpu.log
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${TAG}_bench_reference.json 2> gpurun_out/${TAG}_bench_reference.err
-python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err || exit 1
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv \
-    python bench.py --steps 1 --warmup 0 --no-cpu-baseline --profile-steps 0 > gpurun_out/${TAG}_launches.log 2>&1
-# (generator un-hoisted so that the launch order, and with it -s / -c, is the same on every run)
-MOTES_B200_HOIST=0 ncu --set full --clock-control none --import-source on -k regex:"moffat_fit_group|sky_column_hist|mt_stream|sky_walk|sky_prepare" -s 1 -c 6 \
-    -o gpurun_out/${TAG}_full -f python bench.py --steps 1 --warmup 0 --no-cpu-baseline --profile-steps 0 > gpurun_out/${TAG}_full.log 2>&1
+python bench.py --steps 10 --warmup 3 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err || exit 1
+# (generator un-hoisted under ncu so that the launch order is the same on every run)
+MOTES_B200_HOIST=0 ncu --metrics gpu__time_duration.sum --clock-control none -k "$MINE" --csv --log-file gpurun_out/${TAG}_launches.csv \
+    $ONE_STEP > gpurun_out/${TAG}_launches.log 2>&1
+MOTES_B200_HOIST=0 ncu --set full --clock-control none --import-source on \
+    -k regex:"fit_sweep_kernel|fit_step_kernel|sky_column_hist|mt_stream|sky_walk|sky_prepare" -c 40 \
+    -o gpurun_out/${TAG}_full -f $ONE_STEP > gpurun_out/${TAG}_full.log 2>&1
 ls -la gpurun_out | grep ${TAG}_
