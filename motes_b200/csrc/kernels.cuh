@@ -102,8 +102,12 @@ __global__ void frame_post_kernel(int nframes, const double* __restrict__ fit_pa
     s.median_params[4] = p[4] / s.scale;
     s.median_params[5] = p[5] / s.scale;
     double lo = p[1] - (3.0 * fwhm), hi = p[1] + (3.0 * fwhm);
-    s.row_lo = (int)floor(lo);
-    s.row_hi = (int)ceil(hi);
+    // a frame whose first fit could not start (the reference raises there) runs no further stage: every later
+    // kernel tests status; (int) of a non-finite limit would be undefined
+    const bool usable = s.status == 0 && is_finite(lo) && is_finite(hi) && fabs(lo) < 1e9 && fabs(hi) < 1e9;
+    if (!usable && s.status == 0) s.status = MOTES_E_FIT;
+    s.row_lo = usable ? (int)floor(lo) : 0;
+    s.row_hi = usable ? (int)ceil(hi) : 0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -139,11 +143,16 @@ __global__ void __launch_bounds__(1024)
 bins_kernel(const uint8_t* __restrict__ qual, size_t qual_stride, const uint8_t* __restrict__ allgood, const double* __restrict__ S,
             const double* __restrict__ V, int nspat, int ndisp, double snr_limit, double min_cols, int cap,
             int32_t* __restrict__ bins_i /* [F][2*cap] */, double* __restrict__ bins_snr /* [F][cap] */,
-            int32_t* __restrict__ tmp_i, double* __restrict__ tmp_snr, int32_t* __restrict__ nbins) {
+            int32_t* __restrict__ tmp_i, double* __restrict__ tmp_snr, int32_t* __restrict__ nbins,
+            const FrameState* __restrict__ st) {
     extern __shared__ __align__(16) int bins_counts[];      // nspat counters (padded to 16 bytes), then the column window
     __shared__ unsigned long long cell;
     BlockScope sc{(int)threadIdx.x};
     const int f = blockIdx.x;
+    if (st && st[f].status != 0) {                          // failed frame: no bins, hence no fits, limits or spectra
+        if (threadIdx.x == 0) nbins[f] = 0;
+        return;
+    }
     BinWindow win;
     win.S = reinterpret_cast<double*>(bins_counts + ((nspat + 3) & ~3));
     win.V = win.S + kBinWindow;
@@ -625,6 +634,7 @@ limits_kernel(const double* __restrict__ table, int cap, const int32_t* __restri
     __shared__ int icell;
     BlockScope sc{(int)threadIdx.x};
     const int f = blockIdx.x;
+    if (nbins[f] < 1) return;                               // failed frame (bins_kernel)
     interpolate_limits(sc, table + (size_t)f * 4 * cap, cap, nbins[f], ndisp, limits + (size_t)f * 2 * ndisp,
                        limits + (size_t)f * 2 * ndisp + ndisp, inner + (size_t)f * 2 * (ndisp + 2), keys, hist, &cell,
                        &icell);
@@ -818,6 +828,7 @@ sky_prepare_kernel(const double* __restrict__ data, size_t frame_stride, int nsp
     unsigned long long* cells = reinterpret_cast<unsigned long long*>(hist_all + kTileWarps * 256);
     uint16_t* rows_all = reinterpret_cast<uint16_t*>(cells + kTileWarps);
     const int f = blockIdx.y;
+    if (st[f].status != 0) return;                          // failed frame: left as it came
     const int col0 = blockIdx.x * kTileCols;
     const int ncols = min(kTileCols, ndisp - col0);
     const double* src = data + (size_t)f * frame_stride;
@@ -960,13 +971,19 @@ optimal_extract_kernel(double* __restrict__ data, const double* __restrict__ err
                        int ndisp, const double* __restrict__ limits /* [F][2][ndisp] */,
                        const double* __restrict__ bin_params /* [F][cap][8] */, const int32_t* __restrict__ nbins,
                        int cap, int wavelength_start, double* __restrict__ spectra /* [F][4][ndisp] */,
-                       int32_t* __restrict__ lo_idx, int32_t* __restrict__ hi_idx, uint8_t* __restrict__ crmask) {
+                       int32_t* __restrict__ lo_idx, int32_t* __restrict__ hi_idx, uint8_t* __restrict__ crmask,
+                       const FrameState* __restrict__ st) {
     extern __shared__ __align__(16) double ext_smem[];
     double* sd = ext_smem;
     double* se = ext_smem + (size_t)nspat * kTileStride;
     const int f = blockIdx.y;
     const int col0 = blockIdx.x * kTileCols;
     const int ncols = min(kTileCols, ndisp - col0);
+    if (st && st[f].status != 0) {      // failed frame: the reference raised before it got here - zero spectra, frame untouched
+        for (int i = threadIdx.x; i < 4 * ncols; i += blockDim.x)
+            spectra[(size_t)f * 4 * ndisp + (size_t)(i / ncols) * ndisp + col0 + i % ncols] = 0.0;
+        return;
+    }
     double* fdata = data + (size_t)f * frame_stride;
     const double* ferrs = errs + (size_t)f * frame_stride;
     // stage + scrub (extraction.py:31-34, 86)

@@ -283,7 +283,7 @@ static int stage_bins(motes_handle* h, Batch& b, const uint8_t* qual, size_t qua
     MOTES_LAUNCHED(h);
     bins_kernel<<<b.F, threads, smem, h->stream>>>(qual, qual_stride, b.allgood, b.S, b.V, b.nspat, b.ndisp, snr_limit, min_cols,
                                                    b.cap, b.bins_i[set], b.bins_snr[set], b.tmp_i, b.tmp_snr,
-                                                   b.nbins[set]);
+                                                   b.nbins[set], b.st);
     MOTES_LAUNCHED(h);
     return MOTES_OK;
 }
@@ -745,14 +745,15 @@ static int stage_sky(motes_handle* h, Batch& b, double* data, double* errs, size
 
 static int stage_extract(motes_handle* h, double* data, const double* errs, size_t frame_stride, int F, int nspat,
                          int ndisp, const double* limits, const double* bin_params, const int32_t* nbins, int cap,
-                         int wavelength_start, double* spectra, int32_t* lo_idx, int32_t* hi_idx, uint8_t* crmask) {
+                         int wavelength_start, double* spectra, int32_t* lo_idx, int32_t* hi_idx, uint8_t* crmask,
+                         const FrameState* st = nullptr) {
     StageTimer timer(h, ST_EXTRACT);
     size_t smem = (size_t)2 * nspat * kTileStride * sizeof(double);
     if (smem > h->smem_optin) return fail_arg("nspat too large for the extraction tile");
     MOTES_CUDA(cudaFuncSetAttribute(optimal_extract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     optimal_extract_kernel<<<dim3((ndisp + kTileCols - 1) / kTileCols, F), kTileThreads, smem, h->stream>>>(
         data, errs, frame_stride, nspat, ndisp, limits, bin_params, nbins, cap, wavelength_start, spectra, lo_idx,
-        hi_idx, crmask);
+        hi_idx, crmask, st);
     MOTES_LAUNCHED(h);
     return MOTES_OK;
 }
@@ -801,7 +802,7 @@ static int run_frames_core(motes_handle* h, Batch& b, double* data, double* errs
     }
     MOTES_TRY(stage_localise(h, b, data, errs, frame_stride, qual, frame_stride, p.extraction_snr_limit, p, 1));
     MOTES_TRY(stage_extract(h, data, errs, frame_stride, b.F, b.nspat, b.ndisp, b.limits[1], b.params8[1], b.nbins[1],
-                            b.cap, p.wavelength_start, b.spectra, nullptr, nullptr, nullptr));
+                            b.cap, p.wavelength_start, b.spectra, nullptr, nullptr, nullptr, b.st));
     return emit();
 }
 

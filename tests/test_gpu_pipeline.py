@@ -140,3 +140,29 @@ def test_float32_planes_are_widened_on_the_device(dtype, config, over):
     for key in pipeline.OUTPUT_SHAPES:
         assert np.array_equal(a[key], b[key], equal_nan=True), key
     assert np.array_equal(a["rng_states"], b["rng_states"])
+
+
+def test_frame_whose_first_fit_cannot_start_is_left_untouched():
+    """A frame on which the reference raises ValueError in median_moffat_fitting (x0 outside the bounds: scipy's check,
+    tracing.py:591-598) is reported with status MOTES_E_FIT, runs no further stage - its pixels come back exactly as
+    they went in, its spectra are zero - and does not disturb its neighbours."""
+    from motes_b200 import pipeline, synth
+    args = synth.default_args()
+    frames = [synth.make_frame(synth.config_spec("T2", seed=s)) for s in (51, 52)]
+    data = np.stack([f[0]["data"] for f in frames])
+    errs = np.stack([f[0]["errs"] for f in frames])
+    qual = np.stack([f[0]["qual"] for f in frames])
+    data[0] = -np.abs(data[0]) - 10.0                 # negative everywhere: the amplitude start value is below its bound
+    axes, header = frames[0][1], frames[0][2]
+    before, errs_before = data.copy(), errs.copy()
+    batch = pipeline.run_frames(data, errs, qual, args, header["seeing"], header["pixel_resolution"], seeds=[3, 4],
+                                axes_dict=axes, copy_back=True)
+    assert batch["frame_status"][0] == -5 and batch["frame_status"][1] == 0
+    assert np.array_equal(batch["data"][0], before[0]), "the failed frame was modified"
+    assert np.all(batch["spectra"][0] == 0.0) and batch["n_ext_bins"][0] == 0
+    assert np.array_equal(batch["errs"][0], errs_before[0]), "the failed frame's errors were modified"
+    single = pipeline.run_frames(before[1:2].copy(), errs_before[1:2].copy(), qual[1:2], args, header["seeing"],
+                                 header["pixel_resolution"], seeds=[4], axes_dict=axes)
+    assert np.array_equal(batch["spectra"][1], single["spectra"][0], equal_nan=True)
+    with pytest.raises(ValueError):
+        pipeline.run_frame({"data": before[0].copy(), "errs": errs_before[0].copy(), "qual": qual[0]}, axes, dict(header), args, seed=3)
