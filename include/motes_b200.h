@@ -13,6 +13,9 @@
  *   - "_host" entry points take host pointers and do their own H2D/D2H copies on the
  *     handle's stream and synchronise before returning; "_dev" entry points take device
  *     pointers, enqueue on the handle's stream and do NOT synchronise;
+ *   - sizes: nspat up to ~1000 rows (shared-memory slabs of the fit, sky and extraction kernels), any ndisp (rows
+ *     longer than ~28 000 columns take a global-memory median path), 100 * ndisp * 2^ceil(log2 nspat) < 2^32 for the
+ *     parallel bootstrap (beyond: one CTA per frame);
  *   - there is no CPU fallback: without a usable CUDA device every call fails with
  *     MOTES_E_CUDA.
  */

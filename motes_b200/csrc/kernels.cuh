@@ -52,6 +52,28 @@ row_median_kernel(const double* __restrict__ data, size_t frame_stride, int nspa
     if (threadIdx.x == 0) out[(size_t)f * nspat + row] = med;
 }
 
+// The same for dispersion axes too long to stage a row in shared memory (beyond ~28 k columns at 227 KB): the
+// radix selection reads the row from global memory in every pass (a row is a few hundred KB: it stays in L2).
+__global__ void __launch_bounds__(256)
+row_median_long_kernel(const double* __restrict__ data, size_t frame_stride, int nspat, int ndisp,
+                       double* __restrict__ out /* [F][nspat] */) {
+    __shared__ uint32_t hist[256];
+    __shared__ unsigned long long cell;
+    __shared__ int icell;
+    BlockScope sc{(int)threadIdx.x};
+    const int row = blockIdx.x, f = blockIdx.y;
+    const double* src = data + (size_t)f * frame_stride + (size_t)row * ndisp;
+    int nan = 0;
+    for (int i = threadIdx.x; i < ndisp; i += blockDim.x) nan += (src[i] != src[i]);
+    int n_nan = sc.isum(nan, &icell);
+    struct RowKeys {
+        const double* p;
+        __device__ unsigned long long operator()(int i) const { return key_or_excluded(p[i]); }
+    };
+    double med = median_of(sc, RowKeys{src}, ndisp, ndisp - n_nan, hist, &cell);
+    if (threadIdx.x == 0) out[(size_t)f * nspat + row] = med;
+}
+
 // exact 10^k for the scale factor (10 ** np.abs(np.floor(...)), tracing.py:437)
 __device__ __forceinline__ double pow10_int(double k) {
     if (k >= 0.0 && k <= 22.0) {

@@ -136,7 +136,11 @@ static int stage_row_median(motes_handle* h, const double* data, size_t frame_st
                             double* out) {
     StageTimer timer(h, ST_ROW_MEDIAN);
     size_t smem = (size_t)ndisp * 8 + 256 * 4 + 32;
-    if (smem > h->smem_optin) return fail_arg("dispersion axis too long for the shared-memory row median");
+    if (smem > h->smem_optin) {          // long merged axes: select straight from global memory / L2
+        row_median_long_kernel<<<dim3(nspat, F), 256, 0, h->stream>>>(data, frame_stride, nspat, ndisp, out);
+        MOTES_LAUNCHED(h);
+        return MOTES_OK;
+    }
     MOTES_CUDA(cudaFuncSetAttribute(row_median_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     row_median_kernel<<<dim3(nspat, F), 256, smem, h->stream>>>(data, frame_stride, nspat, ndisp, out);
     MOTES_LAUNCHED(h);

@@ -214,7 +214,15 @@ MOTES_HD bool residual_sweep_b(const Ctx& ctx, int m, const double* profile, dou
 MOTES_HD double expm1_small(double e) {          // |e| < 1e-2: truncation < 2e-17 relative
     return e * (1.0 + e * (0.5 + e * (1.0 / 6.0 + e * (1.0 / 24.0 + e * (1.0 / 120.0 + e * (1.0 / 720.0))))));
 }
+// -DMOTES_FIT_REAL_POW: every forward difference evaluates the real pow (A/B build for the parity table,
+// tools/parity_table.py: how much of the parameter tail is this shortcut and how much the reference's own jitter).
+#ifdef MOTES_FIT_REAL_POW
+constexpr bool kFitRealPow = true;
+#else
+constexpr bool kFitRealPow = false;
+#endif
 MOTES_HD bool shifted_unit(double u, double q_shift, double q, double inv_s, double beta, double* out) {
+    if (kFitRealPow) return false;
     const double delta = (q_shift - q) * inv_s;
     if (!(fabs(delta) < 1e-3)) return false;
     const double l = delta * (1.0 - delta * (0.5 - delta * (1.0 / 3.0 - delta * (0.25 - delta * 0.2))));   // log1p
@@ -224,6 +232,7 @@ MOTES_HD bool shifted_unit(double u, double q_shift, double q, double inv_s, dou
     return true;
 }
 MOTES_HD bool shifted_unit_beta(double u, double s, double dbeta, double* out) {
+    if (kFitRealPow) return false;
     const double e = -dbeta * log(s);
     if (!(fabs(e) < 1e-2)) return false;
     *out = fma(u, expm1_small(e), u);

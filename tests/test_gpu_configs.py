@@ -30,7 +30,7 @@ def check_against_golden(name, out, g, nspat, max_flip_fraction=1 / 500):
     rep = parity_report.compare(out, g, nspat, control=parity_report.control_of(g))
     try:
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-        with open(os.path.join(ROOT, "gpurun_out", f"parity_{name}.json"), "w") as fh:
+        with open(os.path.join(ROOT, "gpurun_out", f"parity_{os.environ.get('MOTES_PARITY_TAG', '')}{name}.json"), "w") as fh:
             json.dump(rep, fh, indent=1)
     except OSError:
         pass

@@ -26,6 +26,26 @@ def test_row_median_matches_numpy_nanmedian():
     assert np.array_equal(out, want, equal_nan=True)
 
 
+def test_row_median_of_a_dispersion_axis_longer_than_shared_memory():
+    """40 000 columns do not fit the shared-memory staging of row_median_kernel (227 KB): the long-axis kernel selects
+    straight from global memory and still equals np.nanmedian bit for bit (NaNs, ties, even and odd counts)."""
+    from motes_b200 import _lib
+    rng = np.random.default_rng(5)
+    data = rng.normal(100.0, 7.0, size=(6, 40001))
+    data[1, ::7] = np.nan
+    data[2, :] = np.round(data[2, :])                 # many ties
+    data[3, :20001] = np.nan                          # even number of valid values
+    data[4, :] = np.nan
+    out = np.zeros(data.shape[0])
+    h = _lib.default_handle()
+    _lib.check(_lib.lib.motes_row_median_host(h.raw, _lib.ptr(data), data.shape[0], data.shape[1], _lib.ptr(out)))
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        want = np.nanmedian(data, axis=1)
+    assert np.array_equal(out, want, equal_nan=True)
+
+
 @pytest.mark.parametrize("name", CASES)
 def test_get_bins_bit_exact(name):
     from motes_b200 import tracing
