@@ -2,6 +2,7 @@
 #include "handle.cuh"
 #include "kernels.cuh"
 #include "skyseg.cuh"
+#include "walktab.cuh"
 #include "mtjump.hpp"
 #include "peak.cuh"
 #include <utility>
@@ -10,7 +11,7 @@ namespace motes {
 
 // Work-area slots inside motes_handle::work
 enum WorkSlot { W_STATE = 0, W_F64, W_I32, W_U8, W_SORTED, W_RANKS, W_PROFILES, W_GOODROW, W_YSCRATCH, W_MODEL, W_MODELERR,
-                W_STREAM, W_WINDOWS, W_SNAPS, W_SEGI, W_SUBS, W_YPOOL, W_FITSTATE, W_FITLIST };
+                W_STREAM, W_WINDOWS, W_SNAPS, W_SEGI, W_SUBS, W_YPOOL, W_FITSTATE, W_FITLIST, W_WALKTAB };
 
 // Device-side working set of one batch.  All pointers are carved out of handle scratch.
 struct Batch {
@@ -533,8 +534,35 @@ static int stage_bootstrap_segmented(motes_handle* h, Batch& b, uint32_t* rng, b
         uint32_t* rng_w = rng + (size_t)f0 * 625;
         if (!plan.hoisted) MOTES_TRY(boot_generate(h, h->stream, &b, b.ndisp, plan, rng_w, f0, nf, true));
         StageTimer t_walk(h, ST_BOOT_WALK);
+        // Few frames in flight, or long ones: the per-column latency of the streaming walk (~2 us) is what costs, so the
+        // counting goes to a table built by every SM and one warp per frame walks the table (walktab.cuh).  Many frames:
+        // the streaming walk already reads the stream at the HBM roofline and needs no second pass.
+        const WalkTabInfo* tab_info = nullptr;
+        {
+            const double stream_s = (double)nf * (double)lay.stream_len * 2.0 / 5.6e12;
+            // (measured on B200: 2.1 us per column for the streaming walk below its bandwidth limit, 1.25 us for the table walk)
+            const double t_stream = stream_s > b.ndisp * 2.1e-6 ? stream_s : b.ndisp * 2.1e-6;
+            const double t_table = 1.1 * stream_s + b.ndisp * 1.3e-6 + 20e-6;
+            const bool use_table = h->walk_mode == 1 || (h->walk_mode == 0 && t_table < t_stream);
+            const size_t pieces = (size_t)(lay.stream_len >> kSubLog2) + 1;
+            if (use_table && h->work[W_WALKTAB].ensure((size_t)nf * pieces * kTabPiece * sizeof(uint16_t) + (size_t)nf * sizeof(WalkTabInfo) + 512) == MOTES_OK) {
+                WalkTabInfo* info = h->work[W_WALKTAB].as<WalkTabInfo>();
+                uint16_t* table = reinterpret_cast<uint16_t*>(reinterpret_cast<char*>(info) + (((size_t)nf * sizeof(WalkTabInfo) + 255) & ~(size_t)255));
+                walk_range_kernel<<<nf, 256, 0, h->stream>>>(b.ndisp, b.n_good + c0, b.sky_flag + c0, b.st + f0, info);
+                MOTES_LAUNCHED(h);
+                walk_table_kernel<<<dim3((unsigned)((pieces + 7) / 8), nf), 256, 0, h->stream>>>(stream, lay, rng_w, seg_need, info, pieces, table);
+                MOTES_LAUNCHED(h);
+                walk_serial_kernel<<<nf, 32, 0, h->stream>>>(stream, lay, rng_w, seg_need, b.ndisp, b.n_good + c0, b.sky_flag + c0, info, pieces,
+                                                             table, col_start, col_end, subs, end_pos, b.st + f0);
+                MOTES_LAUNCHED(h);
+                tab_info = info;
+            } else if (use_table) {
+                cudaGetLastError();
+            }
+        }
+        // (frames the table does not serve - a wide range of sky-pixel counts - and every frame in streaming mode)
         sky_walk_kernel<<<nf, kWalkThreads, walk_smem, h->stream>>>(stream, lay, rng_w, seg_need, b.ndisp, b.n_good + c0, b.sky_flag + c0,
-                                                   col_start, col_end, subs, end_pos, b.st + f0);
+                                                   col_start, col_end, subs, end_pos, b.st + f0, tab_info);
         MOTES_LAUNCHED(h);
         t_walk.stop();
         StageTimer t_col(h, ST_BOOT_COLUMN);
@@ -965,6 +993,8 @@ int motes_create(int device, motes_handle** out) {
     h->hoist = !(hoist && atoi(hoist) == 0);
     const char* hoist_ctas = getenv("MOTES_B200_HOIST_CTAS");
     if (hoist_ctas && atoi(hoist_ctas) > 0) h->hoist_ctas = atoi(hoist_ctas);
+    const char* walk = getenv("MOTES_B200_WALK");             // "table" / "stream": force one form of the position walk
+    h->walk_mode = (walk && strcmp(walk, "table") == 0) ? 1 : (walk && strcmp(walk, "stream") == 0) ? 2 : 0;
     const char* chunks = getenv("MOTES_B200_CHUNKS");
     if (chunks && atoi(chunks) > 0) h->chunks = atoi(chunks);
     e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);

@@ -348,6 +348,13 @@ __device__ __forceinline__ int walk_count8_from(const uint4& d, uint32_t pos0, u
     return walk_count8(d, pos0, from, limit, mask, top);
 }
 
+constexpr int kTabRange = 64;                       // thresholds per frame the walk table covers (row = 64 x u16 = 128 B)
+struct WalkTabInfo {                                // walktab.cuh
+    int n_lo, range;                                // thresholds n_lo .. n_lo + range - 1
+    uint32_t mask;                                  // their common rejection mask
+    int ok;                                         // 1: walk_serial_kernel serves this frame; 0: sky_walk_kernel does
+};
+
 constexpr int kWalkThreads = 512;
 constexpr int kWalkWarps = kWalkThreads / 32;
 constexpr int kWalkPieces = 32;                            // pieces per round (one per lane of the prefix)
@@ -365,12 +372,14 @@ __global__ void __launch_bounds__(kWalkThreads, 1)
 sky_walk_kernel(const uint16_t* __restrict__ stream, SegLayout lay, const uint32_t* __restrict__ rng,
                 const int32_t* __restrict__ seg_need, int ndisp, const int32_t* __restrict__ n_good,
                 const int32_t* __restrict__ flag, uint32_t* __restrict__ col_start, uint32_t* __restrict__ col_end,
-                uint32_t* __restrict__ sub_have, uint32_t* __restrict__ end_pos, FrameState* __restrict__ st) {
+                uint32_t* __restrict__ sub_have, uint32_t* __restrict__ end_pos, FrameState* __restrict__ st,
+                const WalkTabInfo* __restrict__ served /* optional: frames walk_serial_kernel has done */) {
     extern __shared__ __align__(128) unsigned char walk_smem[];      // kWalkStages x 16 KB
     __shared__ __align__(8) uint64_t full[kWalkStages];
     __shared__ uint32_t piece_cnt[2][kWalkPieces];
     __shared__ uint32_t cross;
     const int f = blockIdx.x;
+    if (served && served[f].ok) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint16_t* s = stream + (size_t)f * lay.stream_len;
     uint32_t* subs = sub_have + (size_t)f * lay.sub_len;
