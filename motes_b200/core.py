@@ -79,6 +79,54 @@ def fit_diagnostics(data, axes_dict, bin_parameters, handle=None):
     }
 
 
+def localisation_lines(axes_dict, boundaries):
+    """The lines the reference overplots for ``-dl`` / ``-dk`` (diagnostics.get_draw_lines, diagnostics.py:75-109):
+    ``boundaries`` is either the ``(4, nbins)`` limit table (bin centres, lower, upper, Moffat centre) or the
+    ``[lower(ndisp,), upper(ndisp,)]`` pair of interpolated limits; returns ``[x, lower, x, upper]`` in frame
+    coordinates (wavelength start and spatial floor added)."""
+    boundaries = [np.asarray(b) for b in boundaries]
+    if len(boundaries) > 2:
+        x = boundaries[0] + axes_dict["wavelength_start"]
+        lower, upper = boundaries[1], boundaries[2]
+    else:
+        x = np.arange(int(axes_dict["dispersion_axis_length"])) + axes_dict["wavelength_start"]
+        lower, upper = boundaries[0], boundaries[1]
+    floor = axes_dict["data_spatial_floor"]
+    return [x, lower + floor, x, upper + floor]
+
+
+def sky_fit_diagnostics(frame_before, sky_limits, sky_model, sky_uncertainty, axes_dict, columns):
+    """The numbers behind the reference's ``-df`` plots (sky.py:236-252, diagnostics.plot_sky_fit), without the plotting,
+    for the dispersion ``columns`` asked for: per column the good sky pixels the model was bootstrapped from (the sky
+    region outside the clamped limits, single-pass 10 sigma clip, sky.py:303-354), their errors and spatial positions,
+    the column's spatial axis, and the sky model and uncertainty along it as the device computed them.
+    ``frame_before`` holds the ``(nspat, ndisp)`` data / errs planes BEFORE sky subtraction; ``sky_limits`` the clamped
+    ``[lower, upper]`` pair ``sky.sky_locator`` returns; ``sky_model`` / ``sky_uncertainty`` the planes it left in
+    ``frame_dict`` (order 0: one value per modelled column tiled over the rows; order > 0: full planes)."""
+    data = np.asarray(frame_before["data"], dtype=np.float64)
+    errs = np.asarray(frame_before["errs"], dtype=np.float64)
+    nspat, ndisp = data.shape
+    floor = axes_dict["data_spatial_floor"]
+    column_axis = np.arange(nspat) + floor
+    # sky_model / sky_uncertainty only hold the modelled columns (constant chip-gap columns are skipped, sky.py:338-339)
+    modelled = np.array([len(set(data[(column_axis < sky_limits[0][c] + floor) | (column_axis > sky_limits[1][c] + floor), c])) != 1
+                         for c in range(ndisp)])
+    where = np.cumsum(modelled) - 1
+    out = {}
+    for c in columns:
+        in_sky = (column_axis < sky_limits[0][c] + floor) | (column_axis > sky_limits[1][c] + floor)
+        sky_pixels, sky_errors, sky_axis = data[in_sky, c], errs[in_sky, c], column_axis[in_sky]
+        entry = {"column": int(c), "column_axis": column_axis, "modelled": bool(modelled[c])}
+        if modelled[c]:
+            med, sig = np.nanmedian(sky_pixels), np.nanstd(sky_pixels)
+            good = (sky_pixels > med - 10 * sig) & (sky_pixels < med + 10 * sig)
+            entry.update({"good_sky_axis": sky_axis[good], "good_sky_pixels": sky_pixels[good], "good_sky_errs": sky_errors[good],
+                          "column_sky_model": np.asarray(sky_model)[:, where[c]],
+                          "column_sky_model_err": np.asarray(sky_uncertainty)[:, where[c]]})
+        out[int(c)] = entry
+    return out
+
+
 def extract_frames(frames, motes_args, rng_states=None, seeds=None, handle=None):
     """``frames``: list of ``(frame_dict, axes_dict, header_parameters)`` of ONE shape and ONE region offset.
     Returns one product dictionary per frame (see ``_frame_products``)."""

@@ -123,6 +123,7 @@ struct motes_handle {
     bool profiling = false;
     int fit_mode = 0;            // MOTES_B200_FIT: 0 auto (lock-step rounds for large batches, else the group kernel), 1 "warp", 2 "group"
     int fit_threads = 0;         // MOTES_B200_FIT_THREADS: threads per fit of the lock-step sweep kernel (0 = by nspat)
+    int fit_ctas = 0;            // MOTES_B200_FIT_CTAS: cap on the sweep kernel's CTAs per SM (0 = what fits)
     int fit_rounds = 40;         // MOTES_B200_FIT_ROUNDS: lock-step rounds before the finishing kernel takes the stragglers
     long long fit_rounds_min = 2048;   // MOTES_B200_FIT_MIN: fits per call from which the lock-step rounds are used
     int column_window = -1;      // MOTES_B200_COLUMN: histogram window of the bootstrap column kernel (-1 = auto, 0 = exact slot kernel only)

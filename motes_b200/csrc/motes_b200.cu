@@ -197,6 +197,7 @@ static int stage_fit_rounds_t(motes_handle* h, const FitBatch& fb) {
     int per_sm = 0;
     MOTES_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sweep, THREADS, smem));
     if (per_sm < 1) per_sm = 1;
+    if (h->fit_ctas > 0 && per_sm > h->fit_ctas) per_sm = h->fit_ctas;      // leave room for a kernel on the other stream
     long long grid = (long long)h->sm_count * per_sm;
     if (grid > items) grid = items;
     fit_init_kernel<<<(unsigned)((items + 7) / 8), 256, 0, h->stream>>>(fb, states, list[0], rounds);
@@ -985,6 +986,8 @@ int motes_create(int device, motes_handle** out) {
     if (fit_threads && atoi(fit_threads) > 0) h->fit_threads = atoi(fit_threads);
     const char* fit_rounds = getenv("MOTES_B200_FIT_ROUNDS");     // lock-step rounds before the finishing kernel
     if (fit_rounds && atoi(fit_rounds) > 0) h->fit_rounds = atoi(fit_rounds);
+    const char* fit_ctas = getenv("MOTES_B200_FIT_CTAS");         // cap on the sweep kernel's CTAs per SM (A/B: sharing the SMs with the generator)
+    if (fit_ctas && atoi(fit_ctas) > 0) h->fit_ctas = atoi(fit_ctas);
     const char* fit_min = getenv("MOTES_B200_FIT_MIN");           // fits per call from which the lock-step rounds are used
     if (fit_min && atoll(fit_min) >= 0) h->fit_rounds_min = atoll(fit_min);
     const char* budget = getenv("MOTES_B200_STREAM_GB");
