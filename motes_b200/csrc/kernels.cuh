@@ -543,8 +543,11 @@ fit_init_kernel(FitBatch fb, FitState* __restrict__ states, unsigned int* __rest
     }
 }
 
+#ifndef MOTES_FIT_SWEEP_WARPS
+#define MOTES_FIT_SWEEP_WARPS 16
+#endif
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS, 512 / THREADS)
+__global__ void __launch_bounds__(THREADS, MOTES_FIT_SWEEP_WARPS * 32 / THREADS)
 fit_sweep_kernel(FitBatch fb, FitState* __restrict__ states, const unsigned int* __restrict__ list,
                  FitRounds* __restrict__ rounds, int round) {
     extern __shared__ __align__(16) double fits_smem[];
