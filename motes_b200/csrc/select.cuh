@@ -40,6 +40,51 @@ struct ArrayKeys {
     MOTES_HD unsigned long long operator()(int i) const { return p[i]; }
 };
 
+// The digit of the k-th key among the 256 counters of one radix pass: cum = keys in the digits below it, equal = keys in
+// it.  Generic form: every thread scans the counters.  A 256-thread CTA does it with one block-wide prefix sum instead
+// (the scan was eight times the work of counting 16 keys per thread: row_median_kernel 3.7 -> 1.6 ms per 128 frames).
+template <class Scope>
+MOTES_HD void pick_digit(const Scope&, const uint32_t* hist, int k, int* digit, int* cum_out, int* equal) {
+    int cum = 0;
+    *digit = 255;
+    for (int d = 0; d < 256; ++d) {
+        int c = (int)hist[d];
+        if (cum + c > k) { *digit = d; *equal = c; break; }
+        cum += c;
+    }
+    *cum_out = cum;
+}
+#if defined(__CUDACC__)
+__device__ __forceinline__ void pick_digit(const BlockScope& sc, const uint32_t* hist, int k, int* digit, int* cum_out, int* equal) {
+    if (blockDim.x != 256) { pick_digit<BlockScope>(sc, hist, k, digit, cum_out, equal); return; }
+    __shared__ int warp_sum[8];
+    __shared__ int pick[3];
+    const int t = sc.tid, lane = t & 31, warp = t >> 5;
+    const int c = (int)hist[t];
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
+    }
+    if (lane == 31) warp_sum[warp] = incl;
+    if (t == 0) pick[0] = -1;
+    __syncthreads();
+    int total = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        const int ws = warp_sum[w];
+        if (w < warp) incl += ws;
+        total += ws;
+    }
+    if (incl - c <= k && k < incl) { pick[0] = t; pick[1] = incl - c; pick[2] = c; }
+    __syncthreads();
+    if (pick[0] >= 0) { *digit = pick[0]; *cum_out = pick[1]; *equal = pick[2]; }
+    else { *digit = 255; *cum_out = total; }
+    __syncthreads();
+}
+#endif
+
 // k-th smallest (0-based) of keys(0..n-1).  hist: 256 shared 32-bit counters.
 // Returns the key; *less / *equal receive the number of keys below it and equal to it.
 template <class Scope, class Keys>
@@ -57,11 +102,7 @@ MOTES_HD unsigned long long select_kth(const Scope& sc, const Keys& keys, int n,
         }
         sc.sync();
         int cum = 0, digit = 255;
-        for (int d = 0; d < 256; ++d) {
-            int c = (int)hist[d];
-            if (cum + c > k) { digit = d; equal = c; break; }
-            cum += c;
-        }
+        pick_digit(sc, hist, k, &digit, &cum, &equal);
         k -= cum;
         less += cum;
         prefix |= (unsigned long long)digit << shift;
