@@ -355,8 +355,8 @@ static size_t sky_col_smem(int nspat) {
     return (size_t)2 * kBootstrap * 8 + (size_t)kBootstrap * boot_row_words(nspat) * 4 + (size_t)nspat * 2 + 64;
 }
 static size_t sky_colh_smem(int nspat, bool packed) {
-    const int stride = packed ? HistLayout<true>::kStride : HistLayout<false>::kStride;
-    return (size_t)2 * kBootstrap * 8 + (size_t)(kBootstrap * stride) * 4 + (size_t)nspat * 2 + 64;
+    if (!packed) return (size_t)2 * kBootstrap * 8 + (size_t)(kH32Rows * kH32Stride) * 4 + (size_t)kH32Entries * 2 + 64;
+    return (size_t)2 * kBootstrap * 8 + (size_t)(kBootstrap * HistLayout<true>::kStride) * 4 + (size_t)nspat * 2 + 64;
 }
 
 // Layout of the segmented replay for a batch: frames per wave, segment stride, buffers (all from the a-priori bound
@@ -523,7 +523,7 @@ static int stage_bootstrap_segmented(motes_handle* h, Batch& b, uint32_t* rng, b
     // bins over a window of 128 ranks; wider frames: packed 8-bit bins over 256 ranks
     const bool packed = b.nspat > 400 || col_mode > HistLayout<false>::kBins;
     const size_t colh_smem = sky_colh_smem(b.nspat, packed);
-    auto hist_kernel = packed ? sky_column_hist_kernel<true> : sky_column_hist_kernel<false>;
+    auto hist_kernel = packed ? sky_column_hist_kernel<true> : sky_column_hist32_kernel;
     MOTES_CUDA(cudaFuncSetAttribute(hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)colh_smem));
     MOTES_CUDA(cudaFuncSetAttribute(sky_column_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)col_smem));
     const size_t walk_smem = (size_t)kWalkStages * kWalkChunkBytes;
@@ -571,7 +571,7 @@ static int stage_bootstrap_segmented(motes_handle* h, Batch& b, uint32_t* rng, b
             const int bins = packed ? HistLayout<true>::kBins : HistLayout<false>::kBins;
             const int window = (col_mode < 0 || col_mode > bins) ? bins : col_mode;
             MOTES_CUDA(cudaMemsetAsync(retry_count, 0, sizeof(uint32_t), h->stream));
-            hist_kernel<<<dim3(b.ndisp, nf), kColThreads, colh_smem, h->stream>>>(
+            hist_kernel<<<dim3(b.ndisp, nf), packed ? kColThreads : kH32Threads, colh_smem, h->stream>>>(
                 stream, lay, b.nspat, b.ndisp, window, b.n_good + c0, b.sky_flag + c0, b.sorted + c0 * b.nspat,
                 b.rank_of + c0 * b.nspat, col_start, col_end, subs, b.sky + c0, b.sky_err + c0, b.st + f0, 0u, retry_list,
                 retry_count);

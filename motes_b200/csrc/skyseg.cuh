@@ -141,16 +141,37 @@ __device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) {
     asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(d) : "r"(a), "r"(b), "r"(c), "n"(LUT));
     return d;
 }
+// Pipe balance (ncu, mt_stream_kernel: ALU pipe 79 % busy, FMA pipe 12 %): shifts and logic ops all issue to the ALU
+// pipe at one warp instruction per two cycles, so constant right shifts can be moved to the FMA pipe as the high half
+// of a multiplication by 2^(32 - s) (MOTES_MT_HI: bit 0 = the twist's y >> 1, bit 1 = y >> 11, bit 2 = y >> 18) and
+// the twist's conditional constant as a product (MOTES_MT_MAG).  Measured on B200, 128 frames of 4096 x 400 (29.7 ms as
+// it was): the product 28.6 ms; IMAD.HI is slow - with the product, y >> 18 through it 29.8 ms, y >> 11 and y >> 18
+// 31.2 ms, all three 32.8 ms.  So: the product, no high-half shifts.
+#ifndef MOTES_MT_HI
+#define MOTES_MT_HI 0
+#endif
+#ifndef MOTES_MT_MAG
+#define MOTES_MT_MAG 1
+#endif
+template <int S, bool HI>
+__device__ __forceinline__ uint32_t shr_const(uint32_t y) {
+    return HI ? __umulhi(y, 1u << (32 - S)) : (y >> S);
+}
 __device__ __forceinline__ uint32_t mt_mix_fast(uint32_t a, uint32_t b, uint32_t far) {
     const uint32_t y = lop3<0xE4>(b, a, 0x7fffffffu);                 // (b & 0x7fffffff) | (a & 0x80000000)
+#if MOTES_MT_MAG
+    uint32_t mag;                                                      // y & 1 == b & 1; (a plain product is turned into a select)
+    asm("mul.lo.u32 %0, %1, %2;" : "=r"(mag) : "r"(b & 1u), "r"(0x9908b0dfu));
+#else
     const uint32_t mag = (uint32_t)(-(int32_t)(b & 1u)) & 0x9908b0dfu;  // y & 1 == b & 1
-    return lop3<0x96>(far, y >> 1, mag);                               // far ^ (y >> 1) ^ mag
+#endif
+    return lop3<0x96>(far, shr_const<1, (MOTES_MT_HI & 1) != 0>(y), mag);       // far ^ (y >> 1) ^ mag
 }
 __device__ __forceinline__ uint32_t mt_temper_fast(uint32_t y) {
-    y ^= y >> 11;
+    y ^= shr_const<11, (MOTES_MT_HI & 2) != 0>(y);
     y = lop3<0x78>(y, y << 7, 0x9d2c5680u);                            // y ^ ((y << 7) & B)
     y = lop3<0x78>(y, y << 15, 0xefc60000u);                           // y ^ ((y << 15) & C)
-    return y ^ (y >> 18);
+    return y ^ shr_const<18, (MOTES_MT_HI & 4) != 0>(y);
 }
 
 template <int U, class OutT>
@@ -971,6 +992,241 @@ sky_column_hist_kernel(const uint16_t* __restrict__ stream, SegLayout lay, int n
     } else {
         if (tid == 0) failed = 0;
         for (int smp = tid; smp < kBootstrap; smp += kColThreads) meds[smp] = srt[0];
+    }
+    __syncthreads();
+    if (failed) {
+        if (tid == 0) list[atomicAdd(list_count, 1u)] = (frame0 + (uint32_t)f) * (uint32_t)ndisp + (uint32_t)c;
+        return;
+    }
+    if (warp == 0) column_mean_std(meds, sq, lane, sky + col, sky_err + col);
+}
+
+// ---- plain 32-bit histogram, second form (n <= 400) ------------------------------------------------------
+// The same counts as sky_column_hist_kernel<false>, with the row loop rebuilt around the pipe that limited it
+// (ncu: ALU pipe 67 %, 122 warp instructions per 128 words, a fifth of the kernel in the 100 warp-wide median
+// scans):
+//   * 8 words per lane and row (one 16-byte load); acceptance of two draws per operation - bit 15 of
+//     (half + 0x8000 - n) - gathered into one flag word per lane by two PRMT (the walk's packed form);
+//   * four ballots number the accepts of 256 words; the row total comes from one REDUX;
+//   * a lane's accepted draws go to consecutive samples: the row pointer just advances, and a run that passes
+//     sample 99 lands in rows 100 .. 106, which are added to rows 0 .. 6 before the medians are read - no wrap test
+//     per draw; every draw is four predicated instructions (table look-up, address, increment, advance);
+//   * medians: one THREAD per sample walks its 128 bins (rows are 16-byte aligned, stride 132 words: the four
+//     quarter-warp phases of a 16-byte shared load hit distinct banks) instead of one warp per sample.
+constexpr int kH32Bins = 128;
+constexpr int kH32Stride = kH32Bins + 4;                 // + draws below / above the window, 16-byte aligned rows
+constexpr int kH32Rows = kBootstrap + 7;                 // a lane's run of 8 draws may pass sample 99
+constexpr int kH32RowBytes = kH32Stride * 4;
+#ifndef MOTES_H32_THREADS
+#define MOTES_H32_THREADS 416
+#endif
+#ifndef MOTES_H32_FLIGHT
+#define MOTES_H32_FLIGHT 2
+#endif
+#ifndef MOTES_H32_DRAW
+#define MOTES_H32_DRAW 0
+#endif
+// 13 warps: a column of 257 .. 512 good sky pixels spans 100 x 512 words = 25 pieces of 2048, i.e. 26 with the two
+// partial ones at its ends - two pieces per warp; three CTAs per SM leave 48 registers per thread
+constexpr int kH32Threads = MOTES_H32_THREADS;
+constexpr int kH32Flight = MOTES_H32_FLIGHT;             // 256-word rows a warp has in flight
+constexpr int kH32Entries = 512;                         // table entries (mask + 1 for n <= 512: any masked word stays inside)
+
+__device__ __forceinline__ uint32_t lds_u16(uint32_t at) {
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(at) : "memory");
+    return v;
+}
+__device__ __forceinline__ void reds_inc(uint32_t at) {
+    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(at) : "memory");
+}
+// one draw: bump the counter its pixel's table entry names in the sample row at `rowaddr`, move on to the next sample
+__device__ __forceinline__ void h32_draw(uint32_t& rowaddr, uint32_t flag, uint32_t entry_at) {
+#if MOTES_H32_DRAW == 0
+    if (flag) {
+        reds_inc(rowaddr + 4u * lds_u16(entry_at));
+        rowaddr += (uint32_t)kH32RowBytes;
+    }
+#elif MOTES_H32_DRAW == 1
+    // branch-free: the look-up of a rejected word is harmless (the table covers every masked value)
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b32 a, en;\n"
+        "setp.ne.b32 p, %1, 0;\n"
+        "ld.shared.u16 en, [%2];\n"
+        "mad.lo.u32 a, en, 4, %0;\n"
+        "@p red.shared.add.u32 [a], 1;\n"
+        "@p add.u32 %0, %0, %3;\n"
+        "}\n"
+        : "+r"(rowaddr)
+        : "r"(flag), "r"(entry_at), "n"(kH32RowBytes)
+        : "memory");
+#else
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b32 a, en;\n"
+        "setp.ne.b32 p, %1, 0;\n"
+        "mov.b32 en, 0;\n"
+        "@p ld.shared.u16 en, [%2];\n"
+        "mad.lo.u32 a, en, 4, %0;\n"
+        "@p red.shared.add.u32 [a], 1;\n"
+        "@p add.u32 %0, %0, %3;\n"
+        "}\n"
+        : "+r"(rowaddr)
+        : "r"(flag), "r"(entry_at), "n"(kH32RowBytes)
+        : "memory");
+#endif
+}
+// lanes whose x has bit BIT set
+template <uint32_t BIT>
+__device__ __forceinline__ unsigned ballot_bit(uint32_t x) {
+    unsigned r;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b32 t;\n"
+        "and.b32 t, %1, %2;\n"
+        "setp.ne.b32 p, t, 0;\n"
+        "vote.sync.ballot.b32 %0, p, 0xffffffff;\n"
+        "}\n"
+        : "=r"(r)
+        : "r"(x), "n"(BIT));
+    return r;
+}
+
+__global__ void __launch_bounds__(kH32Threads, 3)
+sky_column_hist32_kernel(const uint16_t* __restrict__ stream, SegLayout lay, int nspat, int ndisp, int window,
+                         const int32_t* __restrict__ n_good, const int32_t* __restrict__ flag,
+                         const double* __restrict__ sorted, const uint16_t* __restrict__ rank_of,
+                         const uint32_t* __restrict__ col_start, const uint32_t* __restrict__ col_end,
+                         const uint32_t* __restrict__ sub_have, double* __restrict__ sky, double* __restrict__ sky_err,
+                         const FrameState* __restrict__ st, uint32_t frame0, uint32_t* __restrict__ list,
+                         uint32_t* __restrict__ list_count) {
+    extern __shared__ __align__(16) unsigned char colh_smem[];
+    double* meds = reinterpret_cast<double*>(colh_smem);
+    double* sq = meds + kBootstrap;
+    uint32_t* hist = reinterpret_cast<uint32_t*>(sq + kBootstrap);                   // kH32Rows x kH32Stride
+    uint16_t* entry = reinterpret_cast<uint16_t*>(hist + kH32Rows * kH32Stride);      // kH32Entries: word a draw of this pixel bumps
+    __shared__ int failed;
+    const int c = blockIdx.x, f = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int nwarps = kH32Threads / 32;
+    if (st[f].status != 0) return;
+    const size_t col = (size_t)f * ndisp + c;
+    if (flag[col] != kSkyModelled) {
+        if (tid == 0) { sky[col] = 0.0; sky_err[col] = 0.0; }
+        return;
+    }
+    const int n = n_good[col];
+    if (n == 0) {
+        if (tid == 0) { sky[col] = NAN; sky_err[col] = NAN; }
+        return;
+    }
+    const double* srt = sorted + col * nspat;
+    const int lo = max(0, n / 2 - window / 2);     // ranks [lo, lo + window) are histogrammed
+    if (n > 1) {
+        {
+            uint4* h4 = reinterpret_cast<uint4*>(hist);
+            for (int i = tid; i < kH32Rows * kH32Stride / 4; i += kH32Threads) h4[i] = make_uint4(0u, 0u, 0u, 0u);
+        }
+        for (int i = tid; i < kH32Entries; i += kH32Threads) {
+            uint16_t en = (uint16_t)(kH32Bins + 2);                                   // (never a draw: a spare word of the row)
+            if (i < n) {
+                const int r = (int)rank_of[col * nspat + i] - lo;
+                en = ((unsigned)r < (unsigned)window) ? (uint16_t)r : (uint16_t)(r < 0 ? kH32Bins : kH32Bins + 1);
+            }
+            entry[i] = en;
+        }
+        if (tid == 0) failed = 0;
+        __syncthreads();
+        const uint32_t P = col_start[col], Pend = col_end[col];
+        if (Pend > P) {
+            const uint16_t* s = stream + (size_t)f * lay.stream_len;
+            const uint32_t* subs = sub_have + (size_t)f * lay.sub_len;
+            // (volatile: otherwise the address conversion is rematerialised - four instructions - in every row)
+            uint32_t hist_at, entry_at;
+            asm volatile("{\n.reg .u64 t;\ncvta.to.shared.u64 t, %2;\ncvt.u32.u64 %0, t;\nadd.u32 %1, %0, %3;\n}\n"
+                         : "=r"(hist_at), "=r"(entry_at)
+                         : "l"(hist), "n"(kH32Rows * kH32Stride * 4));
+            const int need = n * kBootstrap;
+            const uint32_t mask = rejection_mask((uint32_t)n);
+            const uint32_t mask2 = mask * 0x00010001u, kk2 = (uint32_t)(0x8000 - n) * 0x00010001u, mask_hi = mask << 1;
+            const unsigned lanes_below = (1u << lane) - 1u;
+            const uint32_t first = P >> kSubLog2, last = (Pend - 1) >> kSubLog2;
+            for (uint32_t sub = first + warp; sub <= last; sub += nwarps) {
+                const uint32_t sb = sub << kSubLog2;
+                const uint32_t start = max(P, sb), end = min(Pend, sb + (uint32_t)kSubChunk);
+                int ord0 = (sb > P) ? (int)subs[sub] : 0;
+                for (uint32_t row0 = start & ~255u; row0 < end; row0 += 256u * kH32Flight) {
+                    uint4 raw4[kH32Flight];
+#pragma unroll
+                    for (int r = 0; r < kH32Flight; ++r) raw4[r] = __ldg(reinterpret_cast<const uint4*>(s + row0 + 256u * r + 8u * lane));
+#pragma unroll
+                    for (int r = 0; r < kH32Flight; ++r) {
+                        const uint32_t row = row0 + 256u * r;
+                        if (row >= end) break;
+                        const uint4 d = raw4[r];
+                        const uint32_t t0 = (d.x & mask2) + kk2, t1 = (d.y & mask2) + kk2, t2 = (d.z & mask2) + kk2,
+                                       t3 = (d.w & mask2) + kk2;
+                        // accept flags: word e < 4 at bit 8 e + 7, word e >= 4 at bit 8 (e - 4) + 6
+                        const uint32_t u0 = __byte_perm(t0, t1, 0x7531), u1 = __byte_perm(t2, t3, 0x7531);
+                        uint32_t acc = (~u0 & 0x80808080u) | ((~u1 >> 1) & 0x40404040u);
+                        if (row < start || row + 256u > end) {           // first / last row of the column
+                            const uint32_t pos = row + 8u * lane;
+#pragma unroll
+                            for (int e = 0; e < 8; ++e)
+                                if (pos + e < start || pos + e >= end) acc &= ~(e < 4 ? 0x80u << (8 * e) : 0x40u << (8 * (e - 4)));
+                        }
+                        const uint32_t cnt = (uint32_t)__popc(acc);
+                        const unsigned c0 = ballot_bit<1>(cnt), c1 = ballot_bit<2>(cnt), c2 = ballot_bit<4>(cnt), c3 = ballot_bit<8>(cnt);
+                        const int total = __reduce_add_sync(0xffffffffu, (int)cnt);
+                        if (ord0 + total <= need) {                      // always, unless walk and column disagree
+                            const uint32_t ord = (uint32_t)ord0 + __popc(c0 & lanes_below) + 2 * __popc(c1 & lanes_below) +
+                                                 4 * __popc(c2 & lanes_below) + 8 * __popc(c3 & lanes_below);
+                            const uint32_t smp = ord - __umulhi(ord, 42949673u) * (uint32_t)kBootstrap;       // ord % 100 (ord < 2^22)
+                            uint32_t rowaddr = hist_at + smp * (uint32_t)kH32RowBytes;
+                            const uint32_t w[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) {
+                                const uint32_t bit = e < 4 ? 0x80u << (8 * e) : 0x40u << (8 * (e - 4));
+                                // byte offset of the draw's table entry: 2 v
+                                const uint32_t v2 = (e & 1) ? ((w[e >> 1] >> 15) & mask_hi) : ((w[e >> 1] & mask) << 1);
+                                h32_draw(rowaddr, acc & bit, entry_at + v2);
+                            }
+                        }
+                        ord0 += total;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < 7 * kH32Stride; i += kH32Threads) hist[i] += hist[kBootstrap * kH32Stride + i];
+        __syncthreads();
+        if (tid < kBootstrap) {
+            const int k1 = (n - 1) / 2, k2 = n / 2;
+            const uint4* row4 = reinterpret_cast<const uint4*>(hist + tid * kH32Stride);
+            const uint4 tail = row4[kH32Bins / 4];
+            const int nb = (int)tail.x, na = (int)tail.y;
+            // bins whose running count stays <= t: the bin holding the sample's t-th draw inside the window
+            const int t1 = k1 - nb, t2 = k2 - nb;
+            int cum = 0, x1 = 0, x2 = 0;
+#pragma unroll 4
+            for (int q = 0; q < kH32Bins / 4; ++q) {
+                const uint4 b = row4[q];
+                cum += (int)b.x; x1 += (cum <= t1); x2 += (cum <= t2);
+                cum += (int)b.y; x1 += (cum <= t1); x2 += (cum <= t2);
+                cum += (int)b.z; x1 += (cum <= t1); x2 += (cum <= t2);
+                cum += (int)b.w; x1 += (cum <= t1); x2 += (cum <= t2);
+            }
+            const bool ok = (nb + cum + na == n) && (k1 >= nb) && (k2 < nb + cum);
+            if (!ok) failed = 1;
+            else meds[tid] = (k1 == k2) ? srt[lo + x1] : (srt[lo + x1] + srt[lo + x2]) * 0.5;
+        }
+    } else {
+        if (tid == 0) failed = 0;
+        for (int smp = tid; smp < kBootstrap; smp += kH32Threads) meds[smp] = srt[0];
     }
     __syncthreads();
     if (failed) {
