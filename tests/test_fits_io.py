@@ -93,6 +93,11 @@ def _reference_io():
     standin.install()
     if REFERENCE_SRC not in sys.path:
         sys.path.insert(0, REFERENCE_SRC)
+    staged = sys.modules.get("motes")
+    if staged is not None and os.path.join(REFERENCE_SRC, "motes") not in list(getattr(staged, "__path__", [])):
+        # an earlier test loaded the staged hot-path modules (oracle/_ref has no io package): let the same package
+        # find its io sub-package in the reference tree
+        staged.__path__ = list(staged.__path__) + [os.path.join(REFERENCE_SRC, "motes")]
     import motes.io.motesio as ref_motesio
     import motes.io.gmosio as ref_gmosio
     return ref_motesio, ref_gmosio
