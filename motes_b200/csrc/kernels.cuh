@@ -676,40 +676,71 @@ constexpr int kTileThreads = 256;
 constexpr int kTileWarps = kTileThreads / 32;
 
 // Warp-level bitonic sort of EPL * 32 (key, row) pairs held in registers (position = lane * EPL + k),
-// ascending by key, ties by row - the order np.sort gives the sky pixels and the order in which the
-// rank-by-counting of sky_prepare_column breaks ties.
+// ascending by key - the order np.sort gives the sky pixels.  MOTES_PREP_TIES = 1 also orders equal keys by row
+// (the order in which the rank-by-counting of sky_prepare_column breaks ties); no output depends on it.
+#ifndef MOTES_PREP_TIES
+#define MOTES_PREP_TIES 0
+#endif
+#ifndef MOTES_PREP_CTAS
+#define MOTES_PREP_CTAS 2
+#endif
+__device__ __forceinline__ bool pair_gt(unsigned long long ka, uint32_t ra, unsigned long long kb, uint32_t rb) {
+#if MOTES_PREP_TIES
+    return (ka > kb) || (ka == kb && ra > rb);
+#else
+    // equal values: either order gives the same sorted values, the same clip and the same bootstrap medians
+    // (a draw's rank only selects a value), so the row is carried but not compared
+    return ka > kb;
+#endif
+}
+template <int EPL>
+__device__ __forceinline__ void pair_cswap(unsigned long long (&key)[EPL], uint32_t (&row)[EPL], int k, int k2, bool up) {
+    const bool gt = pair_gt(key[k], row[k], key[k2], row[k2]);
+    if (gt == up) {
+        const unsigned long long tk = key[k]; key[k] = key[k2]; key[k2] = tk;
+        const uint32_t tr = row[k]; row[k] = row[k2]; row[k2] = tr;
+    }
+}
+// The network as loops: the stages inside a lane (register indices are compile-time) are unrolled once - the lane's own
+// sort, then one merge tail shared by all larger sizes - and the stages across lanes, identical but for the partner
+// distance and the direction, are a run-time loop.  Fully unrolled the kernel was 33 k instructions (0.5 MB) per
+// template instance; this form is ~1.5 k.
 template <int EPL>
 __device__ __forceinline__ void sort_pairs_warp(unsigned long long (&key)[EPL], uint32_t (&row)[EPL], int lane) {
-    constexpr int N = EPL * 32;
+    // sizes 2 .. EPL: inside the lane
 #pragma unroll
-    for (int size = 2; size <= N; size <<= 1) {
+    for (int size = 2; size <= EPL; size <<= 1) {
 #pragma unroll
         for (int d = size >> 1; d > 0; d >>= 1) {
-            if (d < EPL) {
 #pragma unroll
-                for (int k = 0; k < EPL; ++k) {
-                    if ((k & d) == 0) {
-                        const int k2 = k | d;
-                        const bool up = (size < EPL) ? ((k & size) == 0) : ((lane & (size / EPL)) == 0);
-                        const bool gt = (key[k] > key[k2]) || (key[k] == key[k2] && row[k] > row[k2]);
-                        if (gt == up) {
-                            const unsigned long long tk = key[k]; key[k] = key[k2]; key[k2] = tk;
-                            const uint32_t tr = row[k]; row[k] = row[k2]; row[k2] = tr;
-                        }
-                    }
-                }
-            } else {
-                const int dl = d / EPL;
-                const bool up = (lane & (size / EPL)) == 0 || size == N;
-                const bool keep_min = (((lane & dl) == 0) == up);
-#pragma unroll
-                for (int k = 0; k < EPL; ++k) {
-                    const unsigned long long ok = __shfl_xor_sync(0xffffffffu, key[k], dl);
-                    const uint32_t orow = __shfl_xor_sync(0xffffffffu, row[k], dl);
-                    const bool gt = (key[k] > ok) || (key[k] == ok && row[k] > orow);
-                    if (gt == keep_min) { key[k] = ok; row[k] = orow; }
+            for (int k = 0; k < EPL; ++k) {
+                if ((k & d) == 0) {
+                    const bool up = (size < EPL) ? ((k & size) == 0) : ((lane & 1) == 0);
+                    pair_cswap<EPL>(key, row, k, k | d, up);
                 }
             }
+        }
+    }
+    // sizes 2 EPL .. 32 EPL: partner lanes at distance sl / 2 .. 1, then the tail inside the lane
+#pragma unroll 1
+    for (int sl = 2; sl <= 32; sl <<= 1) {
+        const bool up = (lane & sl) == 0 || sl == 32;
+#pragma unroll 1
+        for (int dl = sl >> 1; dl > 0; dl >>= 1) {
+            const bool keep_min = (((lane & dl) == 0) == up);
+#pragma unroll
+            for (int k = 0; k < EPL; ++k) {
+                const unsigned long long ok = __shfl_xor_sync(0xffffffffu, key[k], dl);
+                const uint32_t orow = __shfl_xor_sync(0xffffffffu, row[k], dl);
+                const bool gt = pair_gt(key[k], row[k], ok, orow);
+                if (gt == keep_min) { key[k] = ok; row[k] = orow; }
+            }
+        }
+#pragma unroll
+        for (int d = EPL >> 1; d > 0; d >>= 1) {
+#pragma unroll
+            for (int k = 0; k < EPL; ++k)
+                if ((k & d) == 0) pair_cswap<EPL>(key, row, k, k | d, up);
         }
     }
 }
@@ -771,15 +802,17 @@ __device__ __forceinline__ void sky_prepare_column_sorted(int lane, const double
 
     sort_pairs_warp<EPL>(key, row, lane);
     // np.nanmedian / np.nanstd of the valid sky pixels
-#pragma unroll
-    for (int k = 0; k < EPL; ++k) {
-        const int p = lane * EPL + k;
-        if (p < n_valid) skeys[p] = key[k];
-    }
-    __syncwarp();
     double med = NAN;
     if (n_valid > 0) {
-        const double a = value_of(skeys[(n_valid - 1) / 2]), b = value_of(skeys[n_valid / 2]);
+        // sorted position p sits in register p % EPL of lane p / EPL
+        const int p1 = (n_valid - 1) / 2, p2 = n_valid / 2;
+        unsigned long long k1 = 0ull, k2 = 0ull;
+#pragma unroll
+        for (int k = 0; k < EPL; ++k) {
+            if ((p1 % EPL) == k) k1 = key[k];
+            if ((p2 % EPL) == k) k2 = key[k];
+        }
+        const double a = value_of(__shfl_sync(0xffffffffu, k1, p1 / EPL)), b = value_of(__shfl_sync(0xffffffffu, k2, p2 / EPL));
         med = ((n_valid & 1) ? a : (a + b) * 0.5);
     }
     double part = 0.0;
@@ -840,7 +873,7 @@ __device__ __forceinline__ void sky_prepare_column_sorted(int lane, const double
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(kTileThreads)
+__global__ void __launch_bounds__(kTileThreads, MOTES_PREP_CTAS)
 sky_prepare_kernel(const double* __restrict__ data, size_t frame_stride, int nspat, int ndisp,
                    double* __restrict__ limits /* [F][2][ndisp], clamped in place */, int spatial_floor,
                    int32_t* __restrict__ n_sky, int32_t* __restrict__ n_good, int32_t* __restrict__ flag,
@@ -848,8 +881,10 @@ sky_prepare_kernel(const double* __restrict__ data, size_t frame_stride, int nsp
                    uint16_t* __restrict__ good_row /* optional, same shape as rank_of */, FrameState* __restrict__ st) {
     extern __shared__ __align__(16) unsigned char sp_smem[];
     double* tile = reinterpret_cast<double*>(sp_smem);
+    // (staged keys and digit histograms: only the general path, nspat > 512, has them - sky_prepare_smem)
+    const size_t nkeys = nspat > 512 ? (size_t)kTileWarps * nspat : 0;
     unsigned long long* keys_all = reinterpret_cast<unsigned long long*>(tile + (size_t)nspat * kTileStride);
-    uint32_t* hist_all = reinterpret_cast<uint32_t*>(keys_all + (size_t)kTileWarps * nspat);
+    uint32_t* hist_all = reinterpret_cast<uint32_t*>(keys_all + nkeys);
     unsigned long long* cells = reinterpret_cast<unsigned long long*>(hist_all + kTileWarps * 256);
     uint16_t* rows_all = reinterpret_cast<uint16_t*>(cells + kTileWarps);
     const int f = blockIdx.y;

@@ -334,8 +334,8 @@ static int stage_localise(motes_handle* h, Batch& b, const double* data, const d
 }
 
 static size_t sky_prepare_smem(int nspat) {
-    return (size_t)nspat * kTileStride * 8 + (size_t)kTileWarps * nspat * 8 + kTileWarps * 256 * 4 + kTileWarps * 8 +
-           (size_t)kTileWarps * nspat * 2 + 64;
+    const size_t keys = nspat > 512 ? (size_t)kTileWarps * nspat * 8 : 0;      // staged keys: the general path only
+    return (size_t)nspat * kTileStride * 8 + keys + kTileWarps * 256 * 4 + kTileWarps * 8 + (size_t)kTileWarps * nspat * 2 + 64;
 }
 static size_t sky_boot_smem(int nspat) {
     return (size_t)2 * kBootstrap * 8 + kRing * 4 + 64 * 4 + 4 * 4 + (size_t)kBootstrap * boot_row_words(nspat) * 4 +
@@ -519,9 +519,10 @@ static int stage_bootstrap_segmented(motes_handle* h, Batch& b, uint32_t* rng, b
     uint32_t* retry_list = col_end + (size_t)wave * b.ndisp;          // columns the histogram kernel hands to the exact one
     uint32_t* retry_count = retry_list + (size_t)wave * b.ndisp;
     const int col_mode = h->column_window;      // 0: exact kernel only; < 0: the layout's whole window; else that window
-    // n <= nspat <= 400: the median rank of a bootstrap sample stays within 64 (6.4 sigma) of n / 2 -> plain 32-bit
+    // n <= nspat <= 512: the median rank of a bootstrap sample stays within 64 (5.7 sigma at n = 512, 6.4 at 400; a
+    // sample outside sends its column to the exact kernel) of n / 2 -> plain 32-bit
     // bins over a window of 128 ranks; wider frames: packed 8-bit bins over 256 ranks
-    const bool packed = b.nspat > 400 || col_mode > HistLayout<false>::kBins;
+    const bool packed = b.nspat > kH32Entries || col_mode > HistLayout<false>::kBins;
     const size_t colh_smem = sky_colh_smem(b.nspat, packed);
     auto hist_kernel = packed ? sky_column_hist_kernel<true> : sky_column_hist32_kernel;
     MOTES_CUDA(cudaFuncSetAttribute(hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)colh_smem));
@@ -571,7 +572,7 @@ static int stage_bootstrap_segmented(motes_handle* h, Batch& b, uint32_t* rng, b
             const int bins = packed ? HistLayout<true>::kBins : HistLayout<false>::kBins;
             const int window = (col_mode < 0 || col_mode > bins) ? bins : col_mode;
             MOTES_CUDA(cudaMemsetAsync(retry_count, 0, sizeof(uint32_t), h->stream));
-            hist_kernel<<<dim3(b.ndisp, nf), packed ? kColThreads : kH32Threads, colh_smem, h->stream>>>(
+            hist_kernel<<<dim3(b.ndisp, nf), packed ? kColThreads : h32_threads(b.nspat), colh_smem, h->stream>>>(
                 stream, lay, b.nspat, b.ndisp, window, b.n_good + c0, b.sky_flag + c0, b.sorted + c0 * b.nspat,
                 b.rank_of + c0 * b.nspat, col_start, col_end, subs, b.sky + c0, b.sky_err + c0, b.st + f0, 0u, retry_list,
                 retry_count);

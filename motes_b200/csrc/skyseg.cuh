@@ -1027,10 +1027,20 @@ constexpr int kH32RowBytes = kH32Stride * 4;
 #define MOTES_H32_DRAW 0
 #endif
 // 13 warps: a column of 257 .. 512 good sky pixels spans 100 x 512 words = 25 pieces of 2048, i.e. 26 with the two
-// partial ones at its ends - two pieces per warp; three CTAs per SM leave 48 registers per thread
+// partial ones at its ends - two pieces per warp; three CTAs per SM leave 48 registers per thread.  Narrower slits
+// (shorter columns) are launched with one warp per expected piece (h32_threads)
 constexpr int kH32Threads = MOTES_H32_THREADS;
 constexpr int kH32Flight = MOTES_H32_FLIGHT;             // 256-word rows a warp has in flight
 constexpr int kH32Entries = 512;                         // table entries (mask + 1 for n <= 512: any masked word stays inside)
+
+inline int h32_threads(int nspat) {
+    unsigned p2 = 1;
+    while (p2 < (unsigned)nspat) p2 <<= 1;
+    int warps = (int)((100u * p2 + kSubChunk - 1) / kSubChunk) + 1;          // pieces a column of nspat draws can touch
+    if (warps > kH32Threads / 32) warps = kH32Threads / 32;
+    if (warps < 4) warps = 4;                                                 // (the medians: 100 threads)
+    return warps * 32;
+}
 
 __device__ __forceinline__ uint32_t lds_u16(uint32_t at) {
     uint32_t v;
@@ -1112,7 +1122,7 @@ sky_column_hist32_kernel(const uint16_t* __restrict__ stream, SegLayout lay, int
     __shared__ int failed;
     const int c = blockIdx.x, f = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int nwarps = kH32Threads / 32;
+    const int nthreads = (int)blockDim.x, nwarps = nthreads >> 5;     // <= kH32Threads: fewer warps for short columns
     if (st[f].status != 0) return;
     const size_t col = (size_t)f * ndisp + c;
     if (flag[col] != kSkyModelled) {
@@ -1129,9 +1139,9 @@ sky_column_hist32_kernel(const uint16_t* __restrict__ stream, SegLayout lay, int
     if (n > 1) {
         {
             uint4* h4 = reinterpret_cast<uint4*>(hist);
-            for (int i = tid; i < kH32Rows * kH32Stride / 4; i += kH32Threads) h4[i] = make_uint4(0u, 0u, 0u, 0u);
+            for (int i = tid; i < kH32Rows * kH32Stride / 4; i += nthreads) h4[i] = make_uint4(0u, 0u, 0u, 0u);
         }
-        for (int i = tid; i < kH32Entries; i += kH32Threads) {
+        for (int i = tid; i < kH32Entries; i += nthreads) {
             uint16_t en = (uint16_t)(kH32Bins + 2);                                   // (never a draw: a spare word of the row)
             if (i < n) {
                 const int r = (int)rank_of[col * nspat + i] - lo;
@@ -1202,7 +1212,7 @@ sky_column_hist32_kernel(const uint16_t* __restrict__ stream, SegLayout lay, int
             }
         }
         __syncthreads();
-        for (int i = tid; i < 7 * kH32Stride; i += kH32Threads) hist[i] += hist[kBootstrap * kH32Stride + i];
+        for (int i = tid; i < 7 * kH32Stride; i += nthreads) hist[i] += hist[kBootstrap * kH32Stride + i];
         __syncthreads();
         if (tid < kBootstrap) {
             const int k1 = (n - 1) / 2, k2 = n / 2;
@@ -1226,7 +1236,7 @@ sky_column_hist32_kernel(const uint16_t* __restrict__ stream, SegLayout lay, int
         }
     } else {
         if (tid == 0) failed = 0;
-        for (int smp = tid; smp < kBootstrap; smp += kH32Threads) meds[smp] = srt[0];
+        for (int smp = tid; smp < kBootstrap; smp += nthreads) meds[smp] = srt[0];
     }
     __syncthreads();
     if (failed) {
