@@ -127,7 +127,7 @@ struct motes_handle {
     int fit_rounds = 40;         // MOTES_B200_FIT_ROUNDS: lock-step rounds before the finishing kernel takes the stragglers
     long long fit_rounds_min = 2048;   // MOTES_B200_FIT_MIN: fits per call from which the lock-step rounds are used
     int column_window = -1;      // MOTES_B200_COLUMN: histogram window of the bootstrap column kernel (-1 = auto, 0 = exact slot kernel only)
-    int walk_mode = 0;           // MOTES_B200_WALK: 0 auto, 1 "table" (walktab.cuh), 2 "stream" (sky_walk_kernel)
+    int walk_mode = 0;           // MOTES_B200_WALK: 0 auto, 1 "table" (walktab.cuh, by runs), 2 "stream" (sky_walk_kernel), 3 "serial" (table, one column at a time)
     int boot_mode = 0;           // MOTES_B200_BOOTSTRAP: 0 segmented (default), 1 classic (one CTA per frame)
     motes::Scratch jump_polys;   // device copy of the MT19937 jump polynomial table (mtjump.hpp)
     bool jump_ready = false;

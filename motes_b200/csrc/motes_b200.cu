@@ -545,7 +545,7 @@ static int stage_bootstrap_segmented(motes_handle* h, Batch& b, uint32_t* rng, b
             // (measured on B200: 2.1 us per column for the streaming walk below its bandwidth limit, 1.25 us for the table walk)
             const double t_stream = stream_s > b.ndisp * 2.1e-6 ? stream_s : b.ndisp * 2.1e-6;
             const double t_table = 1.1 * stream_s + b.ndisp * 1.3e-6 + 20e-6;
-            const bool use_table = h->walk_mode == 1 || (h->walk_mode == 0 && t_table < t_stream);
+            const bool use_table = h->walk_mode == 1 || h->walk_mode == 3 || (h->walk_mode == 0 && t_table < t_stream);
             const size_t pieces = (size_t)(lay.stream_len >> kSubLog2) + 1;
             if (use_table && h->work[W_WALKTAB].ensure((size_t)nf * pieces * kTabPiece * sizeof(uint16_t) + (size_t)nf * sizeof(WalkTabInfo) + 512) == MOTES_OK) {
                 WalkTabInfo* info = h->work[W_WALKTAB].as<WalkTabInfo>();
@@ -554,8 +554,9 @@ static int stage_bootstrap_segmented(motes_handle* h, Batch& b, uint32_t* rng, b
                 MOTES_LAUNCHED(h);
                 walk_table_kernel<<<dim3((unsigned)((pieces + 7) / 8), nf), 256, 0, h->stream>>>(stream, lay, rng_w, seg_need, info, pieces, table);
                 MOTES_LAUNCHED(h);
-                walk_serial_kernel<<<nf, 32, 0, h->stream>>>(stream, lay, rng_w, seg_need, b.ndisp, b.n_good + c0, b.sky_flag + c0, info, pieces,
-                                                             table, col_start, col_end, subs, end_pos, b.st + f0);
+                auto serial = h->walk_mode == 3 ? walk_serial_kernel : walk_runs_kernel;      // (3: one column at a time)
+                serial<<<nf, 32, 0, h->stream>>>(stream, lay, rng_w, seg_need, b.ndisp, b.n_good + c0, b.sky_flag + c0, info, pieces,
+                                                 table, col_start, col_end, subs, end_pos, b.st + f0);
                 MOTES_LAUNCHED(h);
                 tab_info = info;
             } else if (use_table) {
@@ -998,7 +999,8 @@ int motes_create(int device, motes_handle** out) {
     const char* hoist_ctas = getenv("MOTES_B200_HOIST_CTAS");
     if (hoist_ctas && atoi(hoist_ctas) > 0) h->hoist_ctas = atoi(hoist_ctas);
     const char* walk = getenv("MOTES_B200_WALK");             // "table" / "stream": force one form of the position walk
-    h->walk_mode = (walk && strcmp(walk, "table") == 0) ? 1 : (walk && strcmp(walk, "stream") == 0) ? 2 : 0;
+    h->walk_mode = (walk && strcmp(walk, "table") == 0) ? 1 : (walk && strcmp(walk, "stream") == 0) ? 2 :
+                   (walk && strcmp(walk, "serial") == 0) ? 3 : 0;
     const char* chunks = getenv("MOTES_B200_CHUNKS");
     if (chunks && atoi(chunks) > 0) h->chunks = atoi(chunks);
     e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);

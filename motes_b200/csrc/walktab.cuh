@@ -432,4 +432,181 @@ walk_serial_kernel(const uint16_t* __restrict__ stream, SegLayout lay, const uin
 #endif
 }
 
+// ---- walk by runs -----------------------------------------------------------------------------------------------------
+// Consecutive columns that draw with the same number n of good sky pixels (the sky region moves slowly along the
+// dispersion axis, and a column whose sky was not modelled draws nothing) share their acceptance test, so the k-th of
+// them ends at the (k + 1) 100 n-th accepted word behind the run's start: the serial dependency is between RUNS, not
+// columns.  One warp per frame, up to 32 columns per iteration (lane i looks at column c + i):
+//   * A = accepted words of the piece the run starts in that lie in front of its start P (table rows + P's row);
+//   * the pieces behind, 32 at a time (one table entry per lane, one warp prefix): every lane knows the accepted count
+//     S at the start and end of its piece, hence which targets A + (k + 1) need fall into it (it posts piece and
+//     remainder for each) and - at every piece boundary - how many draws the running column has had (sub_have);
+//   * lane k resolves target k on its own: the piece's eight cumulative row counts, then a scan of the 256-word row.
+// A run of one column costs about what walk_serial_kernel spends on it; a long run costs ~1 / 10 per column.
+// Same outputs as walk_serial_kernel / sky_walk_kernel, bit for bit.
+__device__ __forceinline__ uint32_t group_rejects(const uint4& d, uint32_t mask2, uint32_t kk2) {
+    const uint32_t r0 = ((d.x & mask2) + kk2) & 0x80008000u, r1 = ((d.y & mask2) + kk2) & 0x80008000u;
+    const uint32_t r2 = ((d.z & mask2) + kk2) & 0x80008000u, r3 = ((d.w & mask2) + kk2) & 0x80008000u;
+    return r0 | (r1 >> 1) | (r2 >> 2) | (r3 >> 3);        // word e: bit (e & 1) * 16 + 15 - (e >> 1)
+}
+// words in front of the want-th (1..8) accepted one of a group with reject flags `rej`
+__device__ __forceinline__ uint32_t nth_accept(uint32_t rej, uint32_t want) {
+    const uint32_t okb = ~rej;
+    uint32_t e = 0, seen = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        seen += (okb >> (15 - i)) & 1u;
+        e += (seen < want) ? 1u : 0u;
+        seen += (okb >> (31 - i)) & 1u;
+        e += (seen < want) ? 1u : 0u;
+    }
+    return e;
+}
+
+__global__ void __launch_bounds__(32)
+walk_runs_kernel(const uint16_t* __restrict__ stream, SegLayout lay, const uint32_t* __restrict__ rng,
+                 const int32_t* __restrict__ seg_need, int ndisp, const int32_t* __restrict__ n_good,
+                 const int32_t* __restrict__ flag, const WalkTabInfo* __restrict__ info, size_t pieces_per_frame,
+                 const uint16_t* __restrict__ table, uint32_t* __restrict__ col_start, uint32_t* __restrict__ col_end,
+                 uint32_t* __restrict__ sub_have, uint32_t* __restrict__ end_pos, FrameState* __restrict__ st) {
+    __shared__ uint32_t t_piece[32], t_rem[32], t_pos[32];
+    const int f = blockIdx.x, lane = threadIdx.x;
+    const WalkTabInfo t = info[f];
+    if (!t.ok) return;
+    const uint16_t* s = stream + (size_t)f * lay.stream_len;
+    const uint16_t* tab = table + (size_t)f * pieces_per_frame * kTabPiece;
+    uint32_t* subs = sub_have + (size_t)f * lay.sub_len;
+    uint32_t* cs = col_start + (size_t)f * ndisp;
+    uint32_t* ce = col_end + (size_t)f * ndisp;
+    const int32_t* ng = n_good + (size_t)f * ndisp;
+    const int32_t* fl = flag + (size_t)f * ndisp;
+    const uint32_t limit = ((uint32_t)seg_need[f] << lay.log2_stride) + 1u;
+    const uint32_t last_piece = (limit - 1u) >> kSubLog2;
+    const uint32_t mask2 = t.mask * 0x00010001u;
+    const unsigned below = (1u << lane) - 1u;
+    uint32_t P = rng[(size_t)f * 625 + 624];
+    bool failed = false;
+    int c = 0;
+    while (c < ndisp) {
+        // ---- the run: columns c .. c + L - 1, K of them draw (all with the same n)
+        const int ci = c + lane;
+        const bool inside = ci < ndisp;
+        const int n_i = inside ? ng[ci] : 0;
+        const bool draws = inside && fl[ci] == kSkyModelled && n_i > 1;
+        const unsigned draw_mask = __ballot_sync(0xffffffffu, draws);
+        if (failed || draw_mask == 0u) {
+            if (inside) { cs[ci] = P; ce[ci] = P; }
+            c += 32;
+            continue;
+        }
+        const int n = __shfl_sync(0xffffffffu, n_i, __ffs(draw_mask) - 1);
+        const unsigned other = __ballot_sync(0xffffffffu, draws && n_i != n);
+        const int L = other ? __ffs(other) - 1 : min(32, ndisp - c);
+        const unsigned members = (L >= 32) ? 0xffffffffu : ((1u << L) - 1u);
+        const uint32_t K = (uint32_t)__popc(draw_mask & members);
+        const uint32_t my_k = (uint32_t)__popc(draw_mask & members & below);      // drawing columns in front of this one
+        const uint32_t need = (uint32_t)n * kBootstrap;
+        const uint32_t kk2 = (0x8000u - (uint32_t)n) * 0x00010001u;
+        const int j = n - t.n_lo;
+        const uint32_t p0 = P >> kSubLog2, r0 = (P >> 8) & 7u, rs0 = P & ~255u;
+        auto entry16 = [&](uint32_t piece, uint32_t row) -> uint32_t {              // accepted in rows 0 .. row of the piece
+            return (uint32_t)__ldg(tab + (size_t)piece * kTabPiece + row * kTabRange + j);
+        };
+        bool bad = p0 > last_piece;
+        uint32_t A = 0;
+        if (!bad) {
+            // A: accepted words of piece p0 in front of P
+            const uint32_t rows_before = r0 ? entry16(p0, r0 - 1u) : 0u;
+            uint32_t in_front = 0;
+            if (P & 255u) {
+                const uint4 d = __ldg(reinterpret_cast<const uint4*>(s + rs0) + lane);
+                const uint32_t rej = group_rejects(d, mask2, kk2);
+                const uint32_t pos0 = rs0 + (uint32_t)lane * 8u;
+                const uint32_t lead = P > pos0 ? min(P - pos0, 8u) : 0u;            // this lane's words in front of P
+                in_front = lead - (uint32_t)__popc(rej & first_words_mask(lead));
+                in_front = (uint32_t)__reduce_add_sync(0xffffffffu, (int)in_front);
+            }
+            A = rows_before + in_front;
+            // ---- the pieces from p0 on, 32 at a time
+            uint32_t S = 0, base = p0;
+            while (true) {
+                const uint32_t piece = base + (uint32_t)lane;
+                const bool exists = piece <= last_piece;
+                const uint32_t tl = exists ? entry16(piece, kPieceRows - 1) : 0u;
+                uint32_t incl = tl;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += up;
+                }
+                const uint32_t s_lo = S + incl - tl, s_hi = S + incl;              // accepted from p0's start to the piece's start / end
+                // targets A + (k + 1) need <= s: (s - A) / need of them
+                const uint32_t c_lo = s_lo >= A ? min(K, (s_lo - A) / need) : 0u;
+                const uint32_t c_hi = s_hi >= A ? min(K, (s_hi - A) / need) : 0u;
+                if (exists && piece > p0 && c_lo < K) subs[piece] = s_lo - A - c_lo * need;   // draws of the running column so far
+                for (uint32_t k = c_lo; k < c_hi; ++k) { t_piece[k] = piece; t_rem[k] = A + (k + 1u) * need - s_lo; }
+                if (__shfl_sync(0xffffffffu, c_hi, 31) >= K) break;
+                S += __shfl_sync(0xffffffffu, incl, 31);
+                base += 32u;
+                if (base > last_piece) { bad = true; break; }
+            }
+        }
+        __syncwarp();
+        // ---- lane k: where target k lies
+        uint32_t pos = 0;
+        if (!bad && (uint32_t)lane < K) {
+            const uint32_t q = t_piece[lane], rem = t_rem[lane];
+            uint32_t cum[kPieceRows];
+#pragma unroll
+            for (int r = 0; r < kPieceRows; ++r) cum[r] = entry16(q, (uint32_t)r);
+            uint32_t row = 0, prev = 0;
+#pragma unroll
+            for (int r = 0; r < kPieceRows - 1; ++r)
+                if (cum[r] < rem) { row = (uint32_t)r + 1u; prev = cum[r]; }
+            const uint32_t t_row = rem - prev;                                      // 1-based ordinal inside the row
+            const uint32_t rs = (q << kSubLog2) + row * 256u;
+            const uint4* rowp = reinterpret_cast<const uint4*>(s + rs);
+            uint32_t seen = 0;
+            for (int g0 = 0; g0 < 32 && pos == 0u; g0 += 8) {
+                uint4 d[8];
+#pragma unroll
+                for (int g = 0; g < 8; ++g) d[g] = __ldg(rowp + g0 + g);
+#pragma unroll
+                for (int g = 0; g < 8; ++g) {
+                    if (pos != 0u) break;
+                    uint32_t rej = group_rejects(d[g], mask2, kk2);
+                    const uint32_t gp = rs + (uint32_t)(g0 + g) * 8u;
+                    if (gp + 8u > limit) {                                          // the end of the stream: rare
+#pragma unroll
+                        for (int e = 0; e < 8; ++e)
+                            if (gp + (uint32_t)e >= limit) rej |= 1u << ((e & 1) * 16 + 15 - (e >> 1));
+                    }
+                    const uint32_t cnt = 8u - (uint32_t)__popc(rej);
+                    if (seen + cnt >= t_row) pos = gp + nth_accept(rej, t_row - seen) + 1u;
+                    seen += cnt;
+                }
+            }
+            t_pos[lane] = pos;
+        }
+        const unsigned lost = __ballot_sync(0xffffffffu, (uint32_t)lane < K && pos == 0u);
+        __syncwarp();
+        // ---- positions of the run's columns
+        const uint32_t good = bad ? 0u : (lost ? (uint32_t)(__ffs(lost) - 1) : K);   // targets found
+        if (lane < L) {
+            const uint32_t kb = min(my_k, good);
+            const uint32_t start = kb ? t_pos[kb - 1u] : P;
+            cs[ci] = start;
+            ce[ci] = (draws && my_k < good) ? t_pos[my_k] : start;
+        }
+        if (good) P = t_pos[good - 1u];
+        if (good < K) {
+            failed = true;
+            if (lane == 0) atomicMin(&st[f].status, (int)MOTES_E_INTERNAL);
+        }
+        __syncwarp();
+        c += L;
+    }
+    if (lane == 0) end_pos[f] = P;
+}
+
 }  // namespace motes
