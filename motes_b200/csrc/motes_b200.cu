@@ -542,9 +542,10 @@ static int stage_bootstrap_segmented(motes_handle* h, Batch& b, uint32_t* rng, b
         const WalkTabInfo* tab_info = nullptr;
         {
             const double stream_s = (double)nf * (double)lay.stream_len * 2.0 / 5.6e12;
-            // (measured on B200: 2.1 us per column for the streaming walk below its bandwidth limit, 1.25 us for the table walk)
+            // (measured on B200: 2.1 us per column for the streaming walk below its bandwidth limit; the table walk by runs:
+            // 0.26 us per column of a 4096 x 400 frame, 0.15 us for 24000 x 80 - 1.25 us one column at a time)
             const double t_stream = stream_s > b.ndisp * 2.1e-6 ? stream_s : b.ndisp * 2.1e-6;
-            const double t_table = 1.1 * stream_s + b.ndisp * 1.3e-6 + 20e-6;
+            const double t_table = 1.1 * stream_s + b.ndisp * (h->walk_mode == 3 ? 1.3e-6 : 0.35e-6) + 20e-6;
             const bool use_table = h->walk_mode == 1 || h->walk_mode == 3 || (h->walk_mode == 0 && t_table < t_stream);
             const size_t pieces = (size_t)(lay.stream_len >> kSubLog2) + 1;
             if (use_table && h->work[W_WALKTAB].ensure((size_t)nf * pieces * kTabPiece * sizeof(uint16_t) + (size_t)nf * sizeof(WalkTabInfo) + 512) == MOTES_OK) {
@@ -554,9 +555,12 @@ static int stage_bootstrap_segmented(motes_handle* h, Batch& b, uint32_t* rng, b
                 MOTES_LAUNCHED(h);
                 walk_table_kernel<<<dim3((unsigned)((pieces + 7) / 8), nf), 256, 0, h->stream>>>(stream, lay, rng_w, seg_need, info, pieces, table);
                 MOTES_LAUNCHED(h);
-                auto serial = h->walk_mode == 3 ? walk_serial_kernel : walk_runs_kernel;      // (3: one column at a time)
-                serial<<<nf, 32, 0, h->stream>>>(stream, lay, rng_w, seg_need, b.ndisp, b.n_good + c0, b.sky_flag + c0, info, pieces,
-                                                 table, col_start, col_end, subs, end_pos, b.st + f0);
+                if (h->walk_mode == 3)                                                        // (one column at a time)
+                    walk_serial_kernel<<<nf, 32, 0, h->stream>>>(stream, lay, rng_w, seg_need, b.ndisp, b.n_good + c0, b.sky_flag + c0, info, pieces,
+                                                                 table, col_start, col_end, subs, end_pos, b.st + f0);
+                else
+                    walk_runs_kernel<<<nf, kRunWarps * 32, 0, h->stream>>>(stream, lay, rng_w, seg_need, b.ndisp, b.n_good + c0, b.sky_flag + c0, info,
+                                                                           pieces, table, col_start, col_end, subs, end_pos, b.st + f0);
                 MOTES_LAUNCHED(h);
                 tab_info = info;
             } else if (use_table) {

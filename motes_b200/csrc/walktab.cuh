@@ -463,14 +463,17 @@ __device__ __forceinline__ uint32_t nth_accept(uint32_t rej, uint32_t want) {
     return e;
 }
 
-__global__ void __launch_bounds__(32)
+constexpr int kRunWarps = 8;                                // warps per frame: 256 pieces per round of the piece scan
+
+__global__ void __launch_bounds__(kRunWarps * 32)
 walk_runs_kernel(const uint16_t* __restrict__ stream, SegLayout lay, const uint32_t* __restrict__ rng,
                  const int32_t* __restrict__ seg_need, int ndisp, const int32_t* __restrict__ n_good,
                  const int32_t* __restrict__ flag, const WalkTabInfo* __restrict__ info, size_t pieces_per_frame,
                  const uint16_t* __restrict__ table, uint32_t* __restrict__ col_start, uint32_t* __restrict__ col_end,
                  uint32_t* __restrict__ sub_have, uint32_t* __restrict__ end_pos, FrameState* __restrict__ st) {
     __shared__ uint32_t t_piece[32], t_rem[32], t_pos[32];
-    const int f = blockIdx.x, lane = threadIdx.x;
+    __shared__ uint32_t chunk_tot[2][kRunWarps];
+    const int f = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const WalkTabInfo t = info[f];
     if (!t.ok) return;
     const uint16_t* s = stream + (size_t)f * lay.stream_len;
@@ -488,14 +491,14 @@ walk_runs_kernel(const uint16_t* __restrict__ stream, SegLayout lay, const uint3
     bool failed = false;
     int c = 0;
     while (c < ndisp) {
-        // ---- the run: columns c .. c + L - 1, K of them draw (all with the same n)
+        // ---- the run: columns c .. c + L - 1, K of them draw (all with the same n).  Every warp works this out for itself.
         const int ci = c + lane;
         const bool inside = ci < ndisp;
         const int n_i = inside ? ng[ci] : 0;
         const bool draws = inside && fl[ci] == kSkyModelled && n_i > 1;
         const unsigned draw_mask = __ballot_sync(0xffffffffu, draws);
         if (failed || draw_mask == 0u) {
-            if (inside) { cs[ci] = P; ce[ci] = P; }
+            if (warp == 0 && inside) { cs[ci] = P; ce[ci] = P; }
             c += 32;
             continue;
         }
@@ -513,9 +516,10 @@ walk_runs_kernel(const uint16_t* __restrict__ stream, SegLayout lay, const uint3
             return (uint32_t)__ldg(tab + (size_t)piece * kTabPiece + row * kTabRange + j);
         };
         bool bad = p0 > last_piece;
-        uint32_t A = 0;
         if (!bad) {
-            // A: accepted words of piece p0 in front of P
+            // the first round's entries, then A: accepted words of piece p0 in front of P
+            uint32_t piece = p0 + 32u * (uint32_t)warp + (uint32_t)lane;
+            uint32_t tl = piece <= last_piece ? entry16(piece, kPieceRows - 1) : 0u;
             const uint32_t rows_before = r0 ? entry16(p0, r0 - 1u) : 0u;
             uint32_t in_front = 0;
             if (P & 255u) {
@@ -526,73 +530,112 @@ walk_runs_kernel(const uint16_t* __restrict__ stream, SegLayout lay, const uint3
                 in_front = lead - (uint32_t)__popc(rej & first_words_mask(lead));
                 in_front = (uint32_t)__reduce_add_sync(0xffffffffu, (int)in_front);
             }
-            A = rows_before + in_front;
-            // ---- the pieces from p0 on, 32 at a time
+            const uint32_t A = rows_before + in_front;
+            // ---- the pieces from p0 on, 32 per warp and round: accepted counts S at the start / end of every piece, hence
+            // the targets A + (k + 1) need inside it and the draws the running column has had at its boundary
             uint32_t S = 0, base = p0;
-            while (true) {
-                const uint32_t piece = base + (uint32_t)lane;
-                const bool exists = piece <= last_piece;
-                const uint32_t tl = exists ? entry16(piece, kPieceRows - 1) : 0u;
+            for (int rnd = 0;; ++rnd) {
                 uint32_t incl = tl;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
                     const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
                     if (lane >= o) incl += up;
                 }
-                const uint32_t s_lo = S + incl - tl, s_hi = S + incl;              // accepted from p0's start to the piece's start / end
+                if (lane == 31) chunk_tot[rnd & 1][warp] = incl;
+                // (the next round's entries are requested before the barrier)
+                const uint32_t piece_next = piece + 32u * (uint32_t)kRunWarps;
+                const uint32_t tl_next = piece_next <= last_piece ? entry16(piece_next, kPieceRows - 1) : 0u;
+                __syncthreads();
+                uint32_t off = S, all = 0;
+#pragma unroll
+                for (int w = 0; w < kRunWarps; ++w) {
+                    const uint32_t tw = chunk_tot[rnd & 1][w];
+                    if (w < warp) off += tw;
+                    all += tw;
+                }
+                const bool exists = piece <= last_piece;
+                const uint32_t s_lo = off + incl - tl, s_hi = off + incl;          // accepted from p0's start to the piece's start / end
                 // targets A + (k + 1) need <= s: (s - A) / need of them
                 const uint32_t c_lo = s_lo >= A ? min(K, (s_lo - A) / need) : 0u;
                 const uint32_t c_hi = s_hi >= A ? min(K, (s_hi - A) / need) : 0u;
                 if (exists && piece > p0 && c_lo < K) subs[piece] = s_lo - A - c_lo * need;   // draws of the running column so far
-                for (uint32_t k = c_lo; k < c_hi; ++k) { t_piece[k] = piece; t_rem[k] = A + (k + 1u) * need - s_lo; }
-                if (__shfl_sync(0xffffffffu, c_hi, 31) >= K) break;
-                S += __shfl_sync(0xffffffffu, incl, 31);
-                base += 32u;
+                if (c_lo < c_hi) {
+                    // what resolving the targets will read, towards L2: the piece's row counts and the predicted rows of the stream
+                    const char* block = reinterpret_cast<const char*>(tab + (size_t)piece * kTabPiece);
+#pragma unroll
+                    for (int r = 0; r < kPieceRows; ++r) asm volatile("prefetch.global.L2 [%0];" ::"l"(block + 128 * r));
+                    for (uint32_t k = c_lo; k < c_hi; ++k) {
+                        const uint32_t rem = A + (k + 1u) * need - s_lo;
+                        t_piece[k] = piece;
+                        t_rem[k] = rem;
+                        const int guess = (int)((rem * (uint32_t)kPieceRows) / (tl + 1u));
+#pragma unroll
+                        for (int dr = -1; dr <= 1; ++dr) {
+                            const int r = guess + dr;
+                            if (r >= 0 && r < kPieceRows) {
+                                const char* row = reinterpret_cast<const char*>(s + ((size_t)piece << kSubLog2) + (size_t)r * 256);
+#pragma unroll
+                                for (int l = 0; l < 4; ++l) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + 128 * l));
+                            }
+                        }
+                    }
+                }
+                S += all;
+                const bool done = S >= A && (S - A) / need >= K;                    // uniform over the CTA
+                if (done) {
+                    // the next run starts in one of these pieces: their entries, towards L2
+                    if (exists) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(tab + (size_t)piece * kTabPiece + (kPieceRows - 1) * kTabRange)));
+                    if (piece_next <= last_piece) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(tab + (size_t)piece_next * kTabPiece + (kPieceRows - 1) * kTabRange)));
+                    break;
+                }
+                base += 32u * (uint32_t)kRunWarps;
                 if (base > last_piece) { bad = true; break; }
+                piece = piece_next;
+                tl = tl_next;
             }
         }
-        __syncwarp();
-        // ---- lane k: where target k lies
-        uint32_t pos = 0;
-        if (!bad && (uint32_t)lane < K) {
-            const uint32_t q = t_piece[lane], rem = t_rem[lane];
-            uint32_t cum[kPieceRows];
+        __syncthreads();
+        // ---- where the targets lie: a warp per target (k = warp, warp + 8, ..), the eight row counts of its piece in lanes
+        // 0 .. 7, then the 256-word row, 8 words per lane
+        if (!bad) {
+            uint32_t cum[4], rem4[4], q4[4];
 #pragma unroll
-            for (int r = 0; r < kPieceRows; ++r) cum[r] = entry16(q, (uint32_t)r);
-            uint32_t row = 0, prev = 0;
+            for (int i = 0; i < 4; ++i) {
+                const uint32_t k = (uint32_t)(warp + kRunWarps * i);
+                q4[i] = k < K ? t_piece[k] : 0u;
+                rem4[i] = k < K ? t_rem[k] : 0u;
+                cum[i] = (k < K && lane < kPieceRows) ? entry16(q4[i], (uint32_t)lane) : 0xffffffffu;
+            }
+            uint32_t rs4[4], trow4[4];
+            uint4 d4[4];
 #pragma unroll
-            for (int r = 0; r < kPieceRows - 1; ++r)
-                if (cum[r] < rem) { row = (uint32_t)r + 1u; prev = cum[r]; }
-            const uint32_t t_row = rem - prev;                                      // 1-based ordinal inside the row
-            const uint32_t rs = (q << kSubLog2) + row * 256u;
-            const uint4* rowp = reinterpret_cast<const uint4*>(s + rs);
-            uint32_t seen = 0;
-            for (int g0 = 0; g0 < 32 && pos == 0u; g0 += 8) {
-                uint4 d[8];
+            for (int i = 0; i < 4; ++i) {
+                const uint32_t k = (uint32_t)(warp + kRunWarps * i);
+                const unsigned reach = __ballot_sync(0xffffffffu, lane < kPieceRows && cum[i] >= rem4[i]) & 0xffu;
+                const uint32_t row = reach ? (uint32_t)(__ffs(reach) - 1) : (uint32_t)(kPieceRows - 1);
+                const uint32_t prev = row ? __shfl_sync(0xffffffffu, cum[i], (int)row - 1) : 0u;
+                trow4[i] = rem4[i] - prev;
+                rs4[i] = (q4[i] << kSubLog2) + row * 256u;
+                d4[i] = k < K ? __ldg(reinterpret_cast<const uint4*>(s + rs4[i]) + lane) : make_uint4(0u, 0u, 0u, 0u);
+            }
 #pragma unroll
-                for (int g = 0; g < 8; ++g) d[g] = __ldg(rowp + g0 + g);
-#pragma unroll
-                for (int g = 0; g < 8; ++g) {
-                    if (pos != 0u) break;
-                    uint32_t rej = group_rejects(d[g], mask2, kk2);
-                    const uint32_t gp = rs + (uint32_t)(g0 + g) * 8u;
-                    if (gp + 8u > limit) {                                          // the end of the stream: rare
-#pragma unroll
-                        for (int e = 0; e < 8; ++e)
-                            if (gp + (uint32_t)e >= limit) rej |= 1u << ((e & 1) * 16 + 15 - (e >> 1));
-                    }
-                    const uint32_t cnt = 8u - (uint32_t)__popc(rej);
-                    if (seen + cnt >= t_row) pos = gp + nth_accept(rej, t_row - seen) + 1u;
-                    seen += cnt;
+            for (int i = 0; i < 4; ++i) {
+                const uint32_t k = (uint32_t)(warp + kRunWarps * i);
+                if (k < K) {                                                        // uniform over the warp
+                    const uint32_t rej = row_rejects(d4[i], rs4[i], lane, rs4[i], limit, mask2, kk2);
+                    const uint32_t pos = row_locate(rej, rs4[i], lane, trow4[i]);
+                    if (lane == 0) t_pos[k] = pos;
                 }
             }
-            t_pos[lane] = pos;
         }
-        const unsigned lost = __ballot_sync(0xffffffffu, (uint32_t)lane < K && pos == 0u);
-        __syncwarp();
+        __syncthreads();
         // ---- positions of the run's columns
-        const uint32_t good = bad ? 0u : (lost ? (uint32_t)(__ffs(lost) - 1) : K);   // targets found
-        if (lane < L) {
+        uint32_t good = 0;
+        if (!bad) {
+            const unsigned lost = __ballot_sync(0xffffffffu, (uint32_t)lane < K && t_pos[lane] == 0u);
+            good = lost ? (uint32_t)(__ffs(lost) - 1) : K;                        // targets found
+        }
+        if (warp == 0 && lane < L) {
             const uint32_t kb = min(my_k, good);
             const uint32_t start = kb ? t_pos[kb - 1u] : P;
             cs[ci] = start;
@@ -601,12 +644,11 @@ walk_runs_kernel(const uint16_t* __restrict__ stream, SegLayout lay, const uint3
         if (good) P = t_pos[good - 1u];
         if (good < K) {
             failed = true;
-            if (lane == 0) atomicMin(&st[f].status, (int)MOTES_E_INTERNAL);
+            if (threadIdx.x == 0) atomicMin(&st[f].status, (int)MOTES_E_INTERNAL);
         }
-        __syncwarp();
         c += L;
     }
-    if (lane == 0) end_pos[f] = P;
+    if (threadIdx.x == 0) end_pos[f] = P;
 }
 
 }  // namespace motes
