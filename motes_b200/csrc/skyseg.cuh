@@ -1014,7 +1014,13 @@ sky_column_hist_kernel(const uint16_t* __restrict__ stream, SegLayout lay, int n
 //   * medians: one THREAD per sample walks its 128 bins (rows are 16-byte aligned, stride 132 words: the four
 //     quarter-warp phases of a 16-byte shared load hit distinct banks) instead of one warp per sample.
 constexpr int kH32Bins = 128;
-constexpr int kH32Stride = kH32Bins + 4;                 // + draws below / above the window, 16-byte aligned rows
+#ifndef MOTES_H32_STRIDE
+#define MOTES_H32_STRIDE 132
+#endif
+// + draws below / above the window.  132: 16-byte aligned rows (the medians read them with 16-byte loads); 133: an odd
+// stride - the below / above counters of consecutive samples, 60 % of all draws, then lie in distinct banks
+constexpr int kH32Stride = MOTES_H32_STRIDE;
+constexpr int kH32HistWords = (kH32Stride * (kBootstrap + 7) + 3) & ~3;
 constexpr int kH32Rows = kBootstrap + 7;                 // a lane's run of 8 draws may pass sample 99
 constexpr int kH32RowBytes = kH32Stride * 4;
 #ifndef MOTES_H32_THREADS
@@ -1022,9 +1028,6 @@ constexpr int kH32RowBytes = kH32Stride * 4;
 #endif
 #ifndef MOTES_H32_FLIGHT
 #define MOTES_H32_FLIGHT 2
-#endif
-#ifndef MOTES_H32_DRAW
-#define MOTES_H32_DRAW 0
 #endif
 // 13 warps: a column of 257 .. 512 good sky pixels spans 100 x 512 words = 25 pieces of 2048, i.e. 26 with the two
 // partial ones at its ends - two pieces per warp; three CTAs per SM leave 48 registers per thread.  Narrower slits
@@ -1052,42 +1055,10 @@ __device__ __forceinline__ void reds_inc(uint32_t at) {
 }
 // one draw: bump the counter its pixel's table entry names in the sample row at `rowaddr`, move on to the next sample
 __device__ __forceinline__ void h32_draw(uint32_t& rowaddr, uint32_t flag, uint32_t entry_at) {
-#if MOTES_H32_DRAW == 0
     if (flag) {
         reds_inc(rowaddr + 4u * lds_u16(entry_at));
         rowaddr += (uint32_t)kH32RowBytes;
     }
-#elif MOTES_H32_DRAW == 1
-    // branch-free: the look-up of a rejected word is harmless (the table covers every masked value)
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        ".reg .b32 a, en;\n"
-        "setp.ne.b32 p, %1, 0;\n"
-        "ld.shared.u16 en, [%2];\n"
-        "mad.lo.u32 a, en, 4, %0;\n"
-        "@p red.shared.add.u32 [a], 1;\n"
-        "@p add.u32 %0, %0, %3;\n"
-        "}\n"
-        : "+r"(rowaddr)
-        : "r"(flag), "r"(entry_at), "n"(kH32RowBytes)
-        : "memory");
-#else
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        ".reg .b32 a, en;\n"
-        "setp.ne.b32 p, %1, 0;\n"
-        "mov.b32 en, 0;\n"
-        "@p ld.shared.u16 en, [%2];\n"
-        "mad.lo.u32 a, en, 4, %0;\n"
-        "@p red.shared.add.u32 [a], 1;\n"
-        "@p add.u32 %0, %0, %3;\n"
-        "}\n"
-        : "+r"(rowaddr)
-        : "r"(flag), "r"(entry_at), "n"(kH32RowBytes)
-        : "memory");
-#endif
 }
 // lanes whose x has bit BIT set
 template <uint32_t BIT>
@@ -1118,7 +1089,7 @@ sky_column_hist32_kernel(const uint16_t* __restrict__ stream, SegLayout lay, int
     double* meds = reinterpret_cast<double*>(colh_smem);
     double* sq = meds + kBootstrap;
     uint32_t* hist = reinterpret_cast<uint32_t*>(sq + kBootstrap);                   // kH32Rows x kH32Stride
-    uint16_t* entry = reinterpret_cast<uint16_t*>(hist + kH32Rows * kH32Stride);      // kH32Entries: word a draw of this pixel bumps
+    uint16_t* entry = reinterpret_cast<uint16_t*>(hist + kH32HistWords);              // kH32Entries: word a draw of this pixel bumps
     __shared__ int failed;
     const int c = blockIdx.x, f = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1139,7 +1110,7 @@ sky_column_hist32_kernel(const uint16_t* __restrict__ stream, SegLayout lay, int
     if (n > 1) {
         {
             uint4* h4 = reinterpret_cast<uint4*>(hist);
-            for (int i = tid; i < kH32Rows * kH32Stride / 4; i += nthreads) h4[i] = make_uint4(0u, 0u, 0u, 0u);
+            for (int i = tid; i < kH32HistWords / 4; i += nthreads) h4[i] = make_uint4(0u, 0u, 0u, 0u);
         }
         for (int i = tid; i < kH32Entries; i += nthreads) {
             uint16_t en = (uint16_t)(kH32Bins + 2);                                   // (never a draw: a spare word of the row)
@@ -1159,7 +1130,7 @@ sky_column_hist32_kernel(const uint16_t* __restrict__ stream, SegLayout lay, int
             uint32_t hist_at, entry_at;
             asm volatile("{\n.reg .u64 t;\ncvta.to.shared.u64 t, %2;\ncvt.u32.u64 %0, t;\nadd.u32 %1, %0, %3;\n}\n"
                          : "=r"(hist_at), "=r"(entry_at)
-                         : "l"(hist), "n"(kH32Rows * kH32Stride * 4));
+                         : "l"(hist), "n"(kH32HistWords * 4));
             const int need = n * kBootstrap;
             const uint32_t mask = rejection_mask((uint32_t)n);
             const uint32_t mask2 = mask * 0x00010001u, kk2 = (uint32_t)(0x8000 - n) * 0x00010001u, mask_hi = mask << 1;
@@ -1216,12 +1187,13 @@ sky_column_hist32_kernel(const uint16_t* __restrict__ stream, SegLayout lay, int
         __syncthreads();
         if (tid < kBootstrap) {
             const int k1 = (n - 1) / 2, k2 = n / 2;
+            // bins whose running count stays <= t: the bin holding the sample's t-th draw inside the window
+            int cum = 0, x1 = 0, x2 = 0;
+#if (MOTES_H32_STRIDE % 4) == 0
             const uint4* row4 = reinterpret_cast<const uint4*>(hist + tid * kH32Stride);
             const uint4 tail = row4[kH32Bins / 4];
             const int nb = (int)tail.x, na = (int)tail.y;
-            // bins whose running count stays <= t: the bin holding the sample's t-th draw inside the window
             const int t1 = k1 - nb, t2 = k2 - nb;
-            int cum = 0, x1 = 0, x2 = 0;
 #pragma unroll 4
             for (int q = 0; q < kH32Bins / 4; ++q) {
                 const uint4 b = row4[q];
@@ -1230,6 +1202,13 @@ sky_column_hist32_kernel(const uint16_t* __restrict__ stream, SegLayout lay, int
                 cum += (int)b.z; x1 += (cum <= t1); x2 += (cum <= t2);
                 cum += (int)b.w; x1 += (cum <= t1); x2 += (cum <= t2);
             }
+#else
+            const uint32_t* row = hist + tid * kH32Stride;        // (odd stride: consecutive samples, distinct banks)
+            const int nb = (int)row[kH32Bins], na = (int)row[kH32Bins + 1];
+            const int t1 = k1 - nb, t2 = k2 - nb;
+#pragma unroll 8
+            for (int q = 0; q < kH32Bins; ++q) { cum += (int)row[q]; x1 += (cum <= t1); x2 += (cum <= t2); }
+#endif
             const bool ok = (nb + cum + na == n) && (k1 >= nb) && (k2 < nb + cum);
             if (!ok) failed = 1;
             else meds[tid] = (k1 == k2) ? srt[lo + x1] : (srt[lo + x1] + srt[lo + x2]) * 0.5;
