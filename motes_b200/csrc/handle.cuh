@@ -121,6 +121,7 @@ struct motes_handle {
     std::vector<cudaEvent_t> events;
     int chunks = 0;              // MOTES_B200_CHUNKS: sub-batches per call (0 = auto)
     bool profiling = false;
+    bool profile_hoist = false;  // MOTES_B200_PROFILE_HOIST
     int fit_mode = 0;            // MOTES_B200_FIT: 0 auto (lock-step rounds for large batches, else the group kernel), 1 "warp", 2 "group"
     int fit_threads = 0;         // MOTES_B200_FIT_THREADS: threads per fit of the lock-step sweep kernel (0 = by nspat)
     int fit_ctas = 0;            // MOTES_B200_FIT_CTAS: cap on the sweep kernel's CTAs per SM (0 = what fits)

@@ -472,7 +472,7 @@ static int boot_generate(motes_handle* h, cudaStream_t cs, const Batch* b, int n
 static int boot_hoist(motes_handle* h, const Batch& b, uint32_t* rng) {
     h->boot.ok = false;
     h->boot.hoisted = false;
-    if (!h->hoist || h->profiling || h->boot_mode != 0 || h->chunks > 1 || !rng) return MOTES_OK;
+    if (!h->hoist || (h->profiling && !h->profile_hoist) || h->boot_mode != 0 || h->chunks > 1 || !rng) return MOTES_OK;
     BootPlan plan;
     MOTES_TRY(boot_plan(h, b, &plan, h->hoist_ctas));
     if (!plan.ok || plan.wave != b.F) return MOTES_OK;
@@ -543,9 +543,10 @@ static int stage_bootstrap_segmented(motes_handle* h, Batch& b, uint32_t* rng, b
         {
             const double stream_s = (double)nf * (double)lay.stream_len * 2.0 / 5.6e12;
             // (measured on B200: 2.1 us per column for the streaming walk below its bandwidth limit; the table walk by runs:
-            // 0.26 us per column of a 4096 x 400 frame, 0.15 us for 24000 x 80 - 1.25 us one column at a time)
+            // 0.26 us per column of a 4096 x 400 frame, 0.15 us for 24000 x 80 - 1.25 us one column at a time; the table pass
+            // reads the stream at 4.2 TB/s.  128 frames of 3000 x 200: 5.9 ms streaming, 6.5 ms by table)
             const double t_stream = stream_s > b.ndisp * 2.1e-6 ? stream_s : b.ndisp * 2.1e-6;
-            const double t_table = 1.1 * stream_s + b.ndisp * (h->walk_mode == 3 ? 1.3e-6 : 0.35e-6) + 20e-6;
+            const double t_table = 1.4 * stream_s + b.ndisp * (h->walk_mode == 3 ? 1.3e-6 : 0.5e-6) + 50e-6;
             const bool use_table = h->walk_mode == 1 || h->walk_mode == 3 || (h->walk_mode == 0 && t_table < t_stream);
             const size_t pieces = (size_t)(lay.stream_len >> kSubLog2) + 1;
             if (use_table && h->work[W_WALKTAB].ensure((size_t)nf * pieces * kTabPiece * sizeof(uint16_t) + (size_t)nf * sizeof(WalkTabInfo) + 512) == MOTES_OK) {
@@ -1002,6 +1003,8 @@ int motes_create(int device, motes_handle** out) {
     h->hoist = !(hoist && atoi(hoist) == 0);
     const char* hoist_ctas = getenv("MOTES_B200_HOIST_CTAS");
     if (hoist_ctas && atoi(hoist_ctas) > 0) h->hoist_ctas = atoi(hoist_ctas);
+    const char* prof_hoist = getenv("MOTES_B200_PROFILE_HOIST");   // 1: per-stage timers leave the generator hoisted (main-stream stage times under overlap)
+    h->profile_hoist = prof_hoist && atoi(prof_hoist) != 0;
     const char* walk = getenv("MOTES_B200_WALK");             // "table" / "stream": force one form of the position walk
     h->walk_mode = (walk && strcmp(walk, "table") == 0) ? 1 : (walk && strcmp(walk, "stream") == 0) ? 2 :
                    (walk && strcmp(walk, "serial") == 0) ? 3 : 0;

@@ -247,24 +247,38 @@ inline double moffat_unit_call(double r, double c, double alpha, double beta) { 
 #endif
 
 // Householder step K of the QR of [J_h | f] with the sparse pivot row sqrt(diag_h[K]) (see linearize).
+// `part` holds this thread's share of the dot products of column K with columns K .. n (the step's only reduction);
+// the pass that applies the reflector accumulates, from the values it has just written, the same dot products for
+// column K + 1 - operand for operand what a separate pass over the updated columns would compute - so a step is one
+// pass over the slab instead of two (MOTES_FIT_QR_FUSED = 0: the two-pass form).
+#ifndef MOTES_FIT_QR_FUSED
+#define MOTES_FIT_QR_FUSED 1
+#endif
 template <int K, class Ctx>
-MOTES_HD void qr_step(const Ctx& ctx, int m, double* a, double diag_hk, FitState* st) {
+MOTES_HD void qr_step(const Ctx& ctx, int m, double* a, double diag_hk, FitState* st, double (&part)[kParams + 1]) {
     constexpr int n = kParams;
     constexpr int W = n + 1 - K;              // columns K .. n (n = the residual column)
     const bool leader = ctx.lane == 0;
     const double* colk = a + (size_t)K * m;
-    double part[W], c[W];
+    double mine[W], c[W];
+#if MOTES_FIT_QR_FUSED
 #pragma unroll
-    for (int j = 0; j < W; ++j) part[j] = 0.0;
+    for (int j = 0; j < W; ++j) mine[j] = part[j];
+#else
+#pragma unroll
+    for (int j = 0; j < W; ++j) mine[j] = 0.0;
     // (the point loops of the sweeps are not unrolled: six specialisations of this step, unrolled four times each,
     // made the kernel 104 KB of code and instruction fetch its first stall reason - ncu, round 2)
 #pragma unroll kFitUnrollQr
     for (int i = ctx.lane; i < m; i += Ctx::kLanes) {
         double aki = colk[i];
 #pragma unroll
-        for (int j = 0; j < W; ++j) part[j] = fma(aki, a[(size_t)(K + j) * m + i], part[j]);
+        for (int j = 0; j < W; ++j) mine[j] = fma(aki, a[(size_t)(K + j) * m + i], mine[j]);
     }
-    ctx.template sum_vec<W>(part, c);
+#endif
+    ctx.template sum_vec<W>(mine, c);
+#pragma unroll
+    for (int j = 0; j < n + 1; ++j) part[j] = 0.0;
     double ek = trf_detail::ool_sqrt(diag_hk);
     double norm2 = c[0] + ek * ek;
     if (norm2 > 0.0) {
@@ -282,14 +296,36 @@ MOTES_HD void qr_step(const Ctx& ctx, int m, double* a, double diag_hk, FitState
                 if (K + j < n) st->R[K * n + K + j] = rkj; else st->z[K] = rkj;
             }
         }
+        // (the point loops of the sweeps are not unrolled: six specialisations of this step, unrolled four times each,
+        // made the kernel 104 KB of code and instruction fetch its first stall reason - ncu, round 2)
 #pragma unroll kFitUnrollQr
         for (int i = ctx.lane; i < m; i += Ctx::kLanes) {
             double aki = colk[i];
+            double nv[W];
 #pragma unroll
-            for (int j = 1; j < W; ++j) a[(size_t)(K + j) * m + i] = fma(-wj[j], aki, a[(size_t)(K + j) * m + i]);
+            for (int j = 1; j < W; ++j) {
+                nv[j] = fma(-wj[j], aki, a[(size_t)(K + j) * m + i]);
+                a[(size_t)(K + j) * m + i] = nv[j];
+            }
+#if MOTES_FIT_QR_FUSED
+            if (W > 1) {
+#pragma unroll
+                for (int j = 1; j < W; ++j) part[j - 1] = fma(nv[1], nv[j], part[j - 1]);
+            }
+#endif
         }
-    } else if (leader) {
-        st->z[K] = 0.0;
+    } else {
+        if (leader) st->z[K] = 0.0;
+#if MOTES_FIT_QR_FUSED
+        // (a column that is exactly zero: nothing to apply; the next column's products from the slab as it is)
+        if (W > 1) {
+            for (int i = ctx.lane; i < m; i += Ctx::kLanes) {
+                double aki = a[(size_t)(K + 1) * m + i];
+#pragma unroll
+                for (int j = 1; j < W; ++j) part[j - 1] = fma(aki, a[(size_t)(K + j) * m + i], part[j - 1]);
+            }
+        }
+#endif
     }
     ctx.sync();
 }
@@ -356,18 +392,28 @@ MOTES_HD void linearize(const Ctx& ctx, int m, const double* profile, double sca
         for (int k = 0; k < n; ++k) st->g[k] = g[k];
         for (int i = 0; i < n * n; ++i) st->R[i] = 0.0;
     }
+    // scaled Jacobian J diag(d); with it the products of its first column with every column (qr_step<0>)
+    double part[n + 1];
+#pragma unroll
+    for (int k = 0; k < n + 1; ++k) part[k] = 0.0;
 #pragma unroll 1
     for (int i = ctx.lane; i < m; i += Ctx::kLanes) {
+        double sc[n];
 #pragma unroll
-        for (int k = 0; k < n; ++k) a[(size_t)k * m + i] *= d[k];
+        for (int k = 0; k < n; ++k) { sc[k] = a[(size_t)k * m + i] * d[k]; a[(size_t)k * m + i] = sc[k]; }
+#if MOTES_FIT_QR_FUSED
+#pragma unroll
+        for (int k = 0; k < n; ++k) part[k] = fma(sc[0], sc[k], part[k]);
+        part[n] = fma(sc[0], f0[i], part[n]);
+#endif
     }
     ctx.sync();
-    qr_step<0>(ctx, m, a, diag_h[0], st);
-    qr_step<1>(ctx, m, a, diag_h[1], st);
-    qr_step<2>(ctx, m, a, diag_h[2], st);
-    qr_step<3>(ctx, m, a, diag_h[3], st);
-    qr_step<4>(ctx, m, a, diag_h[4], st);
-    qr_step<5>(ctx, m, a, diag_h[5], st);
+    qr_step<0>(ctx, m, a, diag_h[0], st, part);
+    qr_step<1>(ctx, m, a, diag_h[1], st, part);
+    qr_step<2>(ctx, m, a, diag_h[2], st, part);
+    qr_step<3>(ctx, m, a, diag_h[3], st, part);
+    qr_step<4>(ctx, m, a, diag_h[4], st, part);
+    qr_step<5>(ctx, m, a, diag_h[5], st, part);
 }
 
 // One trial: advances *st exactly as one pass of scipy's inner loop body after the step has been
