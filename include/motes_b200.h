@@ -49,6 +49,7 @@ typedef struct motes_handle motes_handle;
  *   MOTES_B200_BOOTSTRAP=classic  one CTA replays a frame's whole generator stream (the literal form of sky.py:34-38)
  *   MOTES_B200_COLUMN=0|<window>  exact rank-slot kernel only / histogram window of the bootstrap column kernel
  *   MOTES_B200_HOIST=0            generate the bootstrap stream where it is consumed instead of at the start of the call
+ *   MOTES_B200_WALK=table|stream|serial  position walk: by runs over the accept-count table / streaming / table, one column at a time
  *   MOTES_B200_HOIST_CTAS=<n>     generator CTAs per SM while it runs beside the localisation stages (default 8)
  *   MOTES_B200_STREAM_GB=<x>      device memory the generator streams may take (default: half of what is free)
  *   MOTES_B200_FIT=warp           round-1 one-warp-per-fit kernel
