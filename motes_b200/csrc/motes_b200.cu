@@ -355,7 +355,7 @@ static size_t sky_col_smem(int nspat) {
     return (size_t)2 * kBootstrap * 8 + (size_t)kBootstrap * boot_row_words(nspat) * 4 + (size_t)nspat * 2 + 64;
 }
 static size_t sky_colh_smem(int nspat, bool packed) {
-    if (!packed) return (size_t)2 * kBootstrap * 8 + (size_t)kH32HistWords * 4 + (size_t)kH32TableBytes + 64;
+    if (!packed) return (size_t)2 * kBootstrap * 8 + (size_t)kH32HistWords * 4 + (size_t)kH32Entries * 2 + 64;
     return (size_t)2 * kBootstrap * 8 + (size_t)(kBootstrap * HistLayout<true>::kStride) * 4 + (size_t)nspat * 2 + 64;
 }
 

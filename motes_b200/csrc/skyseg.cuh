@@ -1035,12 +1035,6 @@ constexpr int kH32RowBytes = kH32Stride * 4;
 constexpr int kH32Threads = MOTES_H32_THREADS;
 constexpr int kH32Flight = MOTES_H32_FLIGHT;             // 256-word rows a warp has in flight
 constexpr int kH32Entries = 512;                         // table entries (mask + 1 for n <= 512: any masked word stays inside)
-// MOTES_H32_LANETAB = 1: the pixel -> bin table as 8-bit entries in 32 copies, copy l in bank l (word g of a copy holds
-// the entries 4 g .. 4 g + 3): a lane's look-ups never meet another lane's bank, for two more address instructions per draw
-#ifndef MOTES_H32_LANETAB
-#define MOTES_H32_LANETAB 0
-#endif
-constexpr int kH32TableBytes = MOTES_H32_LANETAB ? (kH32Entries + kH32Entries * 32) : kH32Entries * 2;
 
 inline int h32_threads(int nspat) {
     unsigned p2 = 1;
@@ -1060,18 +1054,9 @@ __device__ __forceinline__ void reds_inc(uint32_t at) {
     asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(at) : "memory");
 }
 // one draw: bump the counter its pixel's table entry names in the sample row at `rowaddr`, move on to the next sample
-__device__ __forceinline__ uint32_t lds_u8(uint32_t at) {
-    uint32_t v;
-    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(at) : "memory");
-    return v;
-}
 __device__ __forceinline__ void h32_draw(uint32_t& rowaddr, uint32_t flag, uint32_t entry_at) {
     if (flag) {
-#if MOTES_H32_LANETAB
-        reds_inc(rowaddr + 4u * lds_u8(entry_at));
-#else
         reds_inc(rowaddr + 4u * lds_u16(entry_at));
-#endif
         rowaddr += (uint32_t)kH32RowBytes;
     }
 }
@@ -1127,23 +1112,6 @@ sky_column_hist32_kernel(const uint16_t* __restrict__ stream, SegLayout lay, int
             uint4* h4 = reinterpret_cast<uint4*>(hist);
             for (int i = tid; i < kH32HistWords / 4; i += nthreads) h4[i] = make_uint4(0u, 0u, 0u, 0u);
         }
-#if MOTES_H32_LANETAB
-        uint8_t* entry8 = reinterpret_cast<uint8_t*>(entry);                          // kH32Entries bytes, then the 32 copies
-        for (int i = tid; i < kH32Entries; i += nthreads) {
-            uint8_t en = (uint8_t)(kH32Bins + 2);                                     // (never a draw: a spare word of the row)
-            if (i < n) {
-                const int r = (int)rank_of[col * nspat + i] - lo;
-                en = ((unsigned)r < (unsigned)window) ? (uint8_t)r : (uint8_t)(r < 0 ? kH32Bins : kH32Bins + 1);
-            }
-            entry8[i] = en;
-        }
-        __syncthreads();
-        {
-            const uint32_t* packed4 = reinterpret_cast<const uint32_t*>(entry8);
-            uint32_t* copies = reinterpret_cast<uint32_t*>(entry8 + kH32Entries);
-            for (int i = tid; i < kH32Entries * 8; i += nthreads) copies[i] = packed4[i >> 5];
-        }
-#else
         for (int i = tid; i < kH32Entries; i += nthreads) {
             uint16_t en = (uint16_t)(kH32Bins + 2);                                   // (never a draw: a spare word of the row)
             if (i < n) {
@@ -1152,7 +1120,6 @@ sky_column_hist32_kernel(const uint16_t* __restrict__ stream, SegLayout lay, int
             }
             entry[i] = en;
         }
-#endif
         if (tid == 0) failed = 0;
         __syncthreads();
         const uint32_t P = col_start[col], Pend = col_end[col];
@@ -1166,13 +1133,7 @@ sky_column_hist32_kernel(const uint16_t* __restrict__ stream, SegLayout lay, int
                          : "l"(hist), "n"(kH32HistWords * 4));
             const int need = n * kBootstrap;
             const uint32_t mask = rejection_mask((uint32_t)n);
-            const uint32_t mask2 = mask * 0x00010001u, kk2 = (uint32_t)(0x8000 - n) * 0x00010001u;
-#if MOTES_H32_LANETAB
-            const uint32_t lane_at = entry_at + (uint32_t)kH32Entries + 4u * (uint32_t)lane;     // this lane's bank of the copies
-            const uint32_t m_word = mask & 0x1fcu, m_byte = mask & 3u;
-#else
-            const uint32_t mask_hi = mask << 1;
-#endif
+            const uint32_t mask2 = mask * 0x00010001u, kk2 = (uint32_t)(0x8000 - n) * 0x00010001u, mask_hi = mask << 1;
             const unsigned lanes_below = (1u << lane) - 1u;
             const uint32_t first = P >> kSubLog2, last = (Pend - 1) >> kSubLog2;
             for (uint32_t sub = first + warp; sub <= last; sub += nwarps) {
@@ -1211,15 +1172,9 @@ sky_column_hist32_kernel(const uint16_t* __restrict__ stream, SegLayout lay, int
 #pragma unroll
                             for (int e = 0; e < 8; ++e) {
                                 const uint32_t bit = e < 4 ? 0x80u << (8 * e) : 0x40u << (8 * (e - 4));
-#if MOTES_H32_LANETAB
-                                // entry v: byte v & 3 of word v >> 2 of the lane's copy (words of a copy are 128 bytes apart)
-                                const uint32_t hw = (e & 1) ? (w[e >> 1] >> 16) : w[e >> 1];
-                                h32_draw(rowaddr, acc & bit, ((hw & m_word) << 5) + lane_at + (hw & m_byte));
-#else
                                 // byte offset of the draw's table entry: 2 v
                                 const uint32_t v2 = (e & 1) ? ((w[e >> 1] >> 15) & mask_hi) : ((w[e >> 1] & mask) << 1);
                                 h32_draw(rowaddr, acc & bit, entry_at + v2);
-#endif
                             }
                         }
                         ord0 += total;
