@@ -682,7 +682,7 @@ constexpr int kTileWarps = kTileThreads / 32;
 #define MOTES_PREP_TIES 0
 #endif
 #ifndef MOTES_PREP_CTAS
-#define MOTES_PREP_CTAS 2
+#define MOTES_PREP_CTAS 4
 #endif
 __device__ __forceinline__ bool pair_gt(unsigned long long ka, uint32_t ra, unsigned long long kb, uint32_t rb) {
 #if MOTES_PREP_TIES
@@ -873,7 +873,17 @@ __device__ __forceinline__ void sky_prepare_column_sorted(int lane, const double
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(kTileThreads, MOTES_PREP_CTAS)
+// Tile geometry of the sky preparation (MOTES_PREP_COLS columns, MOTES_PREP_THREADS threads, MOTES_PREP_CTAS CTAs per SM).
+// Measured on B200, 128 frames of 4096 x 400: 16 columns x 256 threads x 2 CTAs per SM 9.26 ms; 8 x 128 x 4 (the same 16
+// warps per SM in finer units) 8.67 ms; 8 x 128 x 5 (96 registers: the sort spills) 20.4 ms.
+#ifndef MOTES_PREP_COLS
+#define MOTES_PREP_COLS 8
+#endif
+#ifndef MOTES_PREP_THREADS
+#define MOTES_PREP_THREADS 128
+#endif
+constexpr int kPrepCols = MOTES_PREP_COLS, kPrepStride = kPrepCols + 1, kPrepThreads = MOTES_PREP_THREADS, kPrepWarps = kPrepThreads / 32;
+__global__ void __launch_bounds__(kPrepThreads, MOTES_PREP_CTAS)
 sky_prepare_kernel(const double* __restrict__ data, size_t frame_stride, int nspat, int ndisp,
                    double* __restrict__ limits /* [F][2][ndisp], clamped in place */, int spatial_floor,
                    int32_t* __restrict__ n_sky, int32_t* __restrict__ n_good, int32_t* __restrict__ flag,
@@ -882,24 +892,24 @@ sky_prepare_kernel(const double* __restrict__ data, size_t frame_stride, int nsp
     extern __shared__ __align__(16) unsigned char sp_smem[];
     double* tile = reinterpret_cast<double*>(sp_smem);
     // (staged keys and digit histograms: only the general path, nspat > 512, has them - sky_prepare_smem)
-    const size_t nkeys = nspat > 512 ? (size_t)kTileWarps * nspat : 0;
-    unsigned long long* keys_all = reinterpret_cast<unsigned long long*>(tile + (size_t)nspat * kTileStride);
+    const size_t nkeys = nspat > 512 ? (size_t)kPrepWarps * nspat : 0;
+    unsigned long long* keys_all = reinterpret_cast<unsigned long long*>(tile + (size_t)nspat * kPrepStride);
     uint32_t* hist_all = reinterpret_cast<uint32_t*>(keys_all + nkeys);
-    unsigned long long* cells = reinterpret_cast<unsigned long long*>(hist_all + kTileWarps * 256);
-    uint16_t* rows_all = reinterpret_cast<uint16_t*>(cells + kTileWarps);
+    unsigned long long* cells = reinterpret_cast<unsigned long long*>(hist_all + kPrepWarps * 256);
+    uint16_t* rows_all = reinterpret_cast<uint16_t*>(cells + kPrepWarps);
     const int f = blockIdx.y;
     if (st[f].status != 0) return;                          // failed frame: left as it came
-    const int col0 = blockIdx.x * kTileCols;
-    const int ncols = min(kTileCols, ndisp - col0);
+    const int col0 = blockIdx.x * kPrepCols;
+    const int ncols = min(kPrepCols, ndisp - col0);
     const double* src = data + (size_t)f * frame_stride;
-    for (int idx = threadIdx.x; idx < nspat * kTileCols; idx += blockDim.x) {
-        int row = idx / kTileCols, c = idx % kTileCols;
-        if (c < ncols) tile[row * kTileStride + c] = src[(size_t)row * ndisp + col0 + c];
+    for (int idx = threadIdx.x; idx < nspat * kPrepCols; idx += blockDim.x) {
+        int row = idx / kPrepCols, c = idx % kPrepCols;
+        if (c < ncols) tile[row * kPrepStride + c] = src[(size_t)row * ndisp + col0 + c];
     }
     __syncthreads();
     const int warp = threadIdx.x >> 5;
     WarpScope sc{(int)(threadIdx.x & 31)};
-    for (int c = warp; c < ncols; c += kTileWarps) {
+    for (int c = warp; c < ncols; c += kPrepWarps) {
         const size_t col = (size_t)f * ndisp + col0 + c;
         double* lo = limits + (size_t)f * 2 * ndisp + col0 + c;
         double* hi = lo + ndisp;
@@ -907,19 +917,19 @@ sky_prepare_kernel(const double* __restrict__ data, size_t frame_stride, int nsp
         int icell;
         uint16_t* grow = (good_row != nullptr) ? good_row + col * nspat : nullptr;
         if (nspat <= 128) {
-            sky_prepare_column_sorted<4>(sc.tid, tile + c, kTileStride, nspat, lo, hi, spatial_floor, &ns, &ng, &fl,
+            sky_prepare_column_sorted<4>(sc.tid, tile + c, kPrepStride, nspat, lo, hi, spatial_floor, &ns, &ng, &fl,
                                          sorted + col * nspat, rank_of + col * nspat, grow, keys_all + (size_t)warp * nspat,
                                          rows_all + (size_t)warp * nspat);
         } else if (nspat <= 256) {
-            sky_prepare_column_sorted<8>(sc.tid, tile + c, kTileStride, nspat, lo, hi, spatial_floor, &ns, &ng, &fl,
+            sky_prepare_column_sorted<8>(sc.tid, tile + c, kPrepStride, nspat, lo, hi, spatial_floor, &ns, &ng, &fl,
                                          sorted + col * nspat, rank_of + col * nspat, grow, keys_all + (size_t)warp * nspat,
                                          rows_all + (size_t)warp * nspat);
         } else if (nspat <= 512) {
-            sky_prepare_column_sorted<16>(sc.tid, tile + c, kTileStride, nspat, lo, hi, spatial_floor, &ns, &ng, &fl,
+            sky_prepare_column_sorted<16>(sc.tid, tile + c, kPrepStride, nspat, lo, hi, spatial_floor, &ns, &ng, &fl,
                                           sorted + col * nspat, rank_of + col * nspat, grow, keys_all + (size_t)warp * nspat,
                                           rows_all + (size_t)warp * nspat);
         } else {
-            sky_prepare_column(sc, tile + c, kTileStride, nspat, lo, hi, spatial_floor, &ns, &ng, &fl,
+            sky_prepare_column(sc, tile + c, kPrepStride, nspat, lo, hi, spatial_floor, &ns, &ng, &fl,
                                sorted + col * nspat, rank_of + col * nspat, rows_all + (size_t)warp * nspat,
                                keys_all + (size_t)warp * nspat, hist_all + warp * 256, cells + warp, &icell);
             if (good_row && fl == kSkyModelled)

@@ -334,8 +334,8 @@ static int stage_localise(motes_handle* h, Batch& b, const double* data, const d
 }
 
 static size_t sky_prepare_smem(int nspat) {
-    const size_t keys = nspat > 512 ? (size_t)kTileWarps * nspat * 8 : 0;      // staged keys: the general path only
-    return (size_t)nspat * kTileStride * 8 + keys + kTileWarps * 256 * 4 + kTileWarps * 8 + (size_t)kTileWarps * nspat * 2 + 64;
+    const size_t keys = nspat > 512 ? (size_t)kPrepWarps * nspat * 8 : 0;      // staged keys: the general path only
+    return (size_t)nspat * kPrepStride * 8 + keys + kPrepWarps * 256 * 4 + kPrepWarps * 8 + (size_t)kPrepWarps * nspat * 2 + 64;
 }
 static size_t sky_boot_smem(int nspat) {
     return (size_t)2 * kBootstrap * 8 + kRing * 4 + 64 * 4 + 4 * 4 + (size_t)kBootstrap * boot_row_words(nspat) * 4 +
@@ -738,7 +738,7 @@ static int stage_sky(motes_handle* h, Batch& b, double* data, double* errs, size
     MOTES_CUDA(cudaFuncSetAttribute(sky_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     {
         StageTimer timer(h, ST_SKY_PREPARE);
-        sky_prepare_kernel<<<dim3((b.ndisp + kTileCols - 1) / kTileCols, b.F), kTileThreads, smem, h->stream>>>(
+        sky_prepare_kernel<<<dim3((b.ndisp + kPrepCols - 1) / kPrepCols, b.F), kPrepThreads, smem, h->stream>>>(
             data, frame_stride, b.nspat, b.ndisp, limits, p.spatial_floor, b.n_sky, b.n_good, b.sky_flag, b.sorted,
             b.rank_of, poly ? b.good_row : nullptr, b.st);
         MOTES_LAUNCHED(h);
