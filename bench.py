@@ -166,15 +166,25 @@ class ClockSampler(threading.Thread):
         self.samples, self.reasons = [], set()
         self.max_mhz = None
         self.stop_flag = threading.Event()
-
-    def run(self):
+        # NVML is initialised HERE, before the timed region: nvmlInit enumerates every GPU of the box and can hold driver
+        # locks for tens of milliseconds - inside the timed region that showed up as steps 5 - 15 ms slower on some boxes
+        self.nv = self.dev = None
         try:
             import pynvml as nv
             nv.nvmlInit()
             visible = os.environ.get("CUDA_VISIBLE_DEVICES")
-            idx = int(visible.split(",")[self.index]) if visible and visible.split(",")[self.index].isdigit() else self.index
-            dev = nv.nvmlDeviceGetHandleByIndex(idx)
-            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(dev, nv.NVML_CLOCK_SM)
+            idx = int(visible.split(",")[index]) if visible and visible.split(",")[index].isdigit() else index
+            self.dev = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(self.dev, nv.NVML_CLOCK_SM)
+            self.nv = nv
+        except Exception as exc:           # NVML missing
+            self.reasons.add(f"nvml_unavailable:{type(exc).__name__}")
+
+    def run(self):
+        nv, dev = self.nv, self.dev
+        if nv is None:
+            return
+        try:
             names = {
                 getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
                 getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
@@ -191,8 +201,8 @@ class ClockSampler(threading.Thread):
                     if mask & bit:
                         self.reasons.add(name)
                 time.sleep(0.1)
-        except Exception as exc:           # NVML missing: fall back to one nvidia-smi query
-            self.reasons.add(f"nvml_unavailable:{type(exc).__name__}")
+        except Exception as exc:
+            self.reasons.add(f"nvml_error:{type(exc).__name__}")
 
     def result(self):
         self.stop_flag.set()
