@@ -676,30 +676,35 @@ constexpr int kTileThreads = 256;
 constexpr int kTileWarps = kTileThreads / 32;
 
 // Warp-level bitonic sort of EPL * 32 (key, row) pairs held in registers (position = lane * EPL + k),
-// ascending by key - the order np.sort gives the sky pixels.  MOTES_PREP_TIES = 1 also orders equal keys by row
-// (the order in which the rank-by-counting of sky_prepare_column breaks ties); no output depends on it.
-#ifndef MOTES_PREP_TIES
-#define MOTES_PREP_TIES 0
-#endif
+// ascending by key - the order np.sort gives the sky pixels -, equal keys by row (the order in which the
+// rank-by-counting of sky_prepare_column breaks ties).
 #ifndef MOTES_PREP_CTAS
 #define MOTES_PREP_CTAS 4
 #endif
-__device__ __forceinline__ bool pair_gt(unsigned long long ka, uint32_t ra, unsigned long long kb, uint32_t rb) {
-#if MOTES_PREP_TIES
-    return (ka > kb) || (ka == kb && ra > rb);
-#else
-    // equal values: either order gives the same sorted values, the same clip and the same bootstrap medians
-    // (a draw's rank only selects a value), so the row is carried but not compared
-    return ka > kb;
-#endif
+// (key, row) pairs compared as one 96-bit number.  The row makes the order STRICT, which
+// the exchange across lanes relies on: both lanes evaluate "mine > partner's" and exactly one of them sees true, so
+// exactly one pair moves each way.  Compared by key alone, two EQUAL keys (quantised counts: float32 or integer
+// detectors) made both lanes see false, the lane keeping the larger pair took its partner's, and one row was
+// duplicated while the other was lost (found by the float32 end-to-end check of bench.py;
+// tests/test_gpu_vs_oracle.py::test_equal_sky_values_keep_every_pixel).
+// All ones when (ka, ra) > (kb, rb): the borrow of (kb, rb) - (ka, ra) through a three-word subtract-with-carry chain.
+__device__ __forceinline__ uint32_t pair_gt_mask(unsigned long long ka, uint32_t ra, unsigned long long kb, uint32_t rb) {
+    uint32_t m;
+    asm("{\n\t.reg .u32 t;\n\tsub.cc.u32 t, %6, %3;\n\tsubc.cc.u32 t, %5, %2;\n\tsubc.cc.u32 t, %4, %1;\n\tsubc.u32 %0, 0, 0;\n\t}"
+        : "=r"(m)
+        : "r"((uint32_t)(ka >> 32)), "r"((uint32_t)ka), "r"(ra), "r"((uint32_t)(kb >> 32)), "r"((uint32_t)kb), "r"(rb));
+    return m;
 }
+// compare-exchange inside a lane, without branches or predicates: `up` = ascending
 template <int EPL>
 __device__ __forceinline__ void pair_cswap(unsigned long long (&key)[EPL], uint32_t (&row)[EPL], int k, int k2, bool up) {
-    const bool gt = pair_gt(key[k], row[k], key[k2], row[k2]);
-    if (gt == up) {
-        const unsigned long long tk = key[k]; key[k] = key[k2]; key[k2] = tk;
-        const uint32_t tr = row[k]; row[k] = row[k2]; row[k2] = tr;
-    }
+    const uint32_t gt = pair_gt_mask(key[k], row[k], key[k2], row[k2]);
+    const uint32_t take = up ? gt : ~gt;                                   // swap when (k > k2) == up
+    const unsigned long long take64 = ((unsigned long long)take << 32) | take;
+    const unsigned long long dk = (key[k] ^ key[k2]) & take64;
+    const uint32_t dr = (row[k] ^ row[k2]) & take;
+    key[k] ^= dk; key[k2] ^= dk;
+    row[k] ^= dr; row[k2] ^= dr;
 }
 // The network as loops: the stages inside a lane (register indices are compile-time) are unrolled once - the lane's own
 // sort, then one merge tail shared by all larger sizes - and the stages across lanes, identical but for the partner
@@ -732,8 +737,11 @@ __device__ __forceinline__ void sort_pairs_warp(unsigned long long (&key)[EPL], 
             for (int k = 0; k < EPL; ++k) {
                 const unsigned long long ok = __shfl_xor_sync(0xffffffffu, key[k], dl);
                 const uint32_t orow = __shfl_xor_sync(0xffffffffu, row[k], dl);
-                const bool gt = pair_gt(key[k], row[k], ok, orow);
-                if (gt == keep_min) { key[k] = ok; row[k] = orow; }
+                const uint32_t gt = pair_gt_mask(key[k], row[k], ok, orow);       // (strict: the rows differ)
+                const uint32_t take = keep_min ? gt : ~gt;                         // take the partner's when (mine > its) == keep_min
+                const unsigned long long take64 = ((unsigned long long)take << 32) | take;
+                key[k] = (ok & take64) | (key[k] & ~take64);
+                row[k] = (orow & take) | (row[k] & ~take);
             }
         }
 #pragma unroll
