@@ -1027,7 +1027,7 @@ constexpr int kH32RowBytes = kH32Stride * 4;
 #define MOTES_H32_THREADS 416
 #endif
 #ifndef MOTES_H32_FLIGHT
-#define MOTES_H32_FLIGHT 2
+#define MOTES_H32_FLIGHT 4       // B200, 128 frames of 4096 x 400: 1 row in flight 29.3 ms, 2: 26.0, 3: 25.3, 4: 24.8 (48 registers)
 #endif
 // 13 warps: a column of 257 .. 512 good sky pixels spans 100 x 512 words = 25 pieces of 2048, i.e. 26 with the two
 // partial ones at its ends - two pieces per warp; three CTAs per SM leave 48 registers per thread.  Narrower slits
