@@ -1001,16 +1001,16 @@ sky_column_hist_kernel(const uint16_t* __restrict__ stream, SegLayout lay, int n
     if (warp == 0) column_mean_std(meds, sq, lane, sky + col, sky_err + col);
 }
 
-// ---- plain 32-bit histogram, second form (n <= 400) ------------------------------------------------------
-// The same counts as sky_column_hist_kernel<false>, with the row loop rebuilt around the pipe that limited it
-// (ncu: ALU pipe 67 %, 122 warp instructions per 128 words, a fifth of the kernel in the 100 warp-wide median
-// scans):
+// ---- plain 32-bit histogram, second form (n <= 512) ------------------------------------------------------
+// The same counts as the plain layout of sky_column_hist_kernel above (which now only runs its packed layout, for
+// n > 512), with the row loop rebuilt around the pipe that limited it (ncu: ALU pipe 67 %, 122 warp instructions per
+// 128 words, a fifth of the kernel in the 100 warp-wide median scans):
 //   * 8 words per lane and row (one 16-byte load); acceptance of two draws per operation - bit 15 of
 //     (half + 0x8000 - n) - gathered into one flag word per lane by two PRMT (the walk's packed form);
 //   * four ballots number the accepts of 256 words; the row total comes from one REDUX;
 //   * a lane's accepted draws go to consecutive samples: the row pointer just advances, and a run that passes
 //     sample 99 lands in rows 100 .. 106, which are added to rows 0 .. 6 before the medians are read - no wrap test
-//     per draw; every draw is four predicated instructions (table look-up, address, increment, advance);
+//     per draw: table look-up, address, increment, advance (behind a branch: ptxas does not predicate shared atomics);
 //   * medians: one THREAD per sample walks its 128 bins (rows are 16-byte aligned, stride 132 words: the four
 //     quarter-warp phases of a 16-byte shared load hit distinct banks) instead of one warp per sample.
 constexpr int kH32Bins = 128;
